@@ -1,0 +1,155 @@
+// Host side of the DMMA evaluation path: plan (fragment re-layout) and launch.
+#include <algorithm>
+#include <cstring>
+#include "eval_dmma_launch.h"
+
+namespace fastcheb {
+
+namespace {
+// Julia layout -> fragment stream of one component group (see the header comment).
+__global__ void __launch_bounds__(256) relayout_frag_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                                            long long total, int E, int e0, int ec, int n1, int M,
+                                                            int KS) {
+  const int U = KS * 32 + 8;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int u = (int)(g % U);
+    long long rem = g / U;
+    const int e = (int)(rem % ec);
+    const long long tile = rem / ec;
+    int k1;
+    long long m;
+    if (u < 8) {
+      k1 = 0;
+      m = tile * 8 + u;
+    } else {
+      const int l = (u - 8) & 31, ks = (u - 8) >> 5;
+      k1 = 1 + 4 * ks + (l & 3);
+      m = tile * 8 + (l >> 2);
+    }
+    dst[g] = (k1 < n1 && m < M) ? src[(e0 + e) + (long long)E * (k1 + (long long)n1 * m)] : 0.0;
+  }
+}
+
+
+typedef cudaError_t (*DmmaFn)(int, int, int, const DmmaParams&, int, int, size_t, cudaStream_t, int*);
+DmmaFn dmma_fn(int ks, bool jac) {
+  switch (ks) {
+    case 4: return jac ? dmma_dispatch_ks4_jac : dmma_dispatch_ks4_val;
+    case 8: return jac ? dmma_dispatch_ks8_jac : dmma_dispatch_ks8_val;
+    case 16: return jac ? dmma_dispatch_ks16_jac : dmma_dispatch_ks16_val;
+  }
+  return nullptr;
+}
+}  // namespace
+
+int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
+  DmmaPlan& pl = p->dmma;
+  pl.ok = false;
+  if (p->dtype != FASTCHEB_F64 || p->ndim < 2 || p->ndim > 4) return FASTCHEB_OK;
+  const int n1 = (int)p->dims[0];
+  if (n1 < 5 || n1 - 1 > 64) return FASTCHEB_OK;
+  long long M = 1;
+  int tab = 0;
+  for (int d = 1; d < p->ndim; ++d) {
+    M *= p->dims[d];
+    tab += (int)p->dims[d];
+  }
+  if (M < 8 || M > (1 << 28)) return FASTCHEB_OK;  // fewer than one column tile: the Clenshaw path is the right tool
+  if (tab > 1024) return FASTCHEB_OK;              // weight tables would not fit shared memory
+  pl.KS = n1 - 1 <= 16 ? 4 : (n1 - 1 <= 32 ? 8 : 16);
+  pl.M = (int)M;
+  pl.ntiles = (int)((M + 7) / 8);
+  pl.tabStride = tab | 1;  // odd row stride: spreads the rows over the banks
+  const int U = pl.KS * 32 + 8;
+  size_t off = 0;
+  for (int e0 = 0; e0 < p->E;) {
+    const int left = p->E - e0;
+    const int ec = left <= kDmmaMaxEC ? left : (left == 4 ? 2 : 3);
+    DmmaGroup g;
+    g.e0 = e0;
+    g.ec = ec;
+    g.offset = off;
+    off += (size_t)pl.ntiles * ec * U;
+    pl.groups.push_back(g);
+    e0 += ec;
+  }
+  pl.frag_bytes = off * sizeof(double);
+  FC_CUDA(cudaMalloc(&pl.d_frag, pl.frag_bytes));
+  for (const DmmaGroup& g : pl.groups) {
+    const long long total = (long long)pl.ntiles * g.ec * U;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)p->di->sms * 16));
+    relayout_frag_kernel<<<grid, 256, 0, st>>>((const double*)p->d_coefs, (double*)pl.d_frag + g.offset, total, p->E,
+                                               g.e0, g.ec, n1, pl.M, pl.KS);
+    FC_CUDA(cudaGetLastError());
+    note_launch();
+  }
+  pl.ok = true;
+  return FASTCHEB_OK;
+}
+
+int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st) {
+  const DmmaPlan& pl = p->dmma;
+  DmmaFn fn = dmma_fn(pl.KS, jac);
+  if (!fn) return fail(FASTCHEB_EUNSUPPORTED, "no DMMA instantiation for KS = %d", pl.KS);
+  const int U = pl.KS * 32 + 8;
+  const int rows = kDmmaMT * 8;
+  for (const DmmaGroup& g : pl.groups) {
+    DmmaParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.frag = (const double*)pl.d_frag + g.offset;
+    prm.pts = (const double*)pts;
+    prm.out_v = (double*)out_v;
+    prm.out_J = (double*)out_J;
+    prm.bad = (&g == &pl.groups[0]) ? bad_dev : nullptr;
+    prm.npts = npts;
+    prm.idx_base = idx_base;
+    prm.v_stride = v_stride;
+    prm.J_stride = J_stride;
+    prm.e0 = g.e0;
+    prm.Etot = p->E;
+    for (int d = 0; d < p->ndim; ++d) {
+      prm.n[d] = (int)p->dims[d];
+      prm.lb[d] = p->lb[d];
+      prm.ub[d] = p->ub[d];
+    }
+    prm.ntiles = pl.ntiles;
+    prm.M = pl.M;
+    prm.tabStride = pl.tabStride;
+    // warps per CTA: as many as the instantiation allows, fewer for small batches (spread over the SMs)
+    int warps = dmma_max_warps(jac);
+    const long long per_sm = (npts + (long long)p->di->sms * rows - 1) / ((long long)p->di->sms * rows);
+    if (per_sm < warps) warps = (int)std::max<long long>(1, per_sm);
+    const size_t unitBytes = (size_t)g.ec * U * 8;
+    const size_t budget = p->di->smem_optin - 1024 - 128;
+    int tps = 0, nstage = 0;
+    for (;; --warps) {
+      const size_t tabBytes = (size_t)warps * rows * pl.tabStride * 8 * (jac ? 2 : 1);
+      if (tabBytes + 3 * unitBytes <= budget) {
+        const size_t room = budget - tabBytes;
+        tps = (int)std::max<size_t>(1, std::min<size_t>(16384 / unitBytes, room / (4 * unitBytes)));
+        tps = std::min(tps, pl.ntiles);
+        nstage = (int)std::min<size_t>(4, room / (tps * unitBytes));
+        if (nstage >= 3) break;
+      }
+      if (warps == 1) return fail(FASTCHEB_EUNSUPPORTED, "DMMA path: shared memory too small for this shape");
+    }
+    prm.tilesPerStage = tps;
+    prm.nstage = nstage;
+    const size_t smem = 128 + (size_t)nstage * tps * unitBytes + (size_t)warps * rows * pl.tabStride * 8 * (jac ? 2 : 1);
+    const int threads = warps * 32;
+    int bps = 1;
+    cudaError_t e = fn(1, p->ndim, g.ec, prm, threads, 0, smem, st, &bps);
+    if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "DMMA occupancy query failed: %s", cudaGetErrorString(e));
+    if (bps < 1) return fail(FASTCHEB_ECUDA, "DMMA kernel does not fit an SM (smem %zu B)", smem);
+    const long long pass_pts = (long long)warps * rows;
+    const long long npass = (npts + pass_pts - 1) / pass_pts;
+    const int grid = (int)std::min<long long>(npass, (long long)p->di->sms * bps);
+    e = fn(0, p->ndim, g.ec, prm, threads, grid, smem, st, nullptr);
+    if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "DMMA kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  return FASTCHEB_OK;
+}
+
+}  // namespace fastcheb

@@ -1,0 +1,25 @@
+// Host-side entry points of the DMMA evaluation path (eval_dmma.cuh).
+#pragma once
+#include "eval_dmma.cuh"
+#include "poly.h"
+
+namespace fastcheb {
+
+constexpr int kDmmaMaxEC = 3;
+
+inline int dmma_max_warps(bool jac) { return jac ? 8 : 16; }
+
+// per-(KS, JAC) translation units: op 0 = launch, op 1 = occupancy query
+cudaError_t dmma_dispatch_ks4_val(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks8_val(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks16_val(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks4_jac(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks8_jac(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks16_jac(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+
+// decide whether the handle gets a DMMA plan and build the fragment stream (no-op when not applicable)
+int dmma_plan(fastcheb_poly* p, cudaStream_t st);
+int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st);
+
+}  // namespace fastcheb

@@ -1,0 +1,378 @@
+// C ABI: the coefficient fit — chebcoefs / droptol / chebinterp (include/fastcheb.h).
+//   chebcoefs   /root/reference/src/interp.jl:39-71
+//   droptol     interp.jl:77-93
+//   chebinterp  interp.jl:95-99, 140-141 (default tol: :102)
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "fit_direct.cuh"
+#include "fit_dmma_launch.h"
+#include "poly.h"
+
+using namespace fastcheb;
+
+namespace {
+
+std::mutex g_tab_mu;
+std::map<std::pair<int, int>, double2*> g_ctab;  // (device, n) -> cos(pi r/(n-1)) as (hi, lo), r in [0, 2(n-1))
+
+// exactly reduced cosine table: cos(pi/2) = 0, cos(pi) = -1 and the symmetries hold bit for bit
+int cos_table(int dev, int n, const double2** out) {
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  auto key = std::make_pair(dev, n);
+  auto it = g_ctab.find(key);
+  if (it != g_ctab.end()) {
+    *out = it->second;
+    return FASTCHEB_OK;
+  }
+  const int m = n - 1;
+  std::vector<double2> h((size_t)2 * m);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int r = 0; r < 2 * m; ++r) {
+    const int rr = r <= m ? r : 2 * m - r;
+    long double v;
+    if (2 * rr == m)
+      v = 0;
+    else if (2 * rr < m)
+      v = cosl(pi * (long double)rr / (long double)m);
+    else
+      v = -cosl(pi * (long double)(m - rr) / (long double)m);
+    h[r].x = (double)v;
+    h[r].y = (double)(v - (long double)h[r].x);
+  }
+  double2* d = nullptr;
+  FC_CUDA(cudaMalloc(&d, h.size() * sizeof(double2)));
+  FC_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  g_ctab[key] = d;
+  *out = d;
+  return FASTCHEB_OK;
+}
+
+int grid_for(long long total, int threads, int sms) {
+  long long b = (total + threads - 1) / threads;
+  return (int)std::max<long long>(1, std::min<long long>(b, (long long)sms * 32));
+}
+
+template <typename R>
+int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int E, int64_t howmany, const R* vals,
+               R* coefs, cudaStream_t st) {
+  long long per_fit = E;
+  for (int d = 0; d < ndim; ++d) per_fit *= dims[d];
+  const long long total = per_fit * howmany;
+  int npass = 0;
+  for (int d = 0; d < ndim; ++d) npass += dims[d] > 1;
+  if (npass == 0) {
+    if ((const void*)vals != (void*)coefs)
+      FC_CUDA(cudaMemcpyAsync(coefs, vals, (size_t)total * sizeof(R), cudaMemcpyDeviceToDevice, st));
+    return FASTCHEB_OK;
+  }
+  // the bandwidth-bound path: batched 1-D transforms of short lines on the FP64 tensor cores
+  if (ndim == 1 && fit_dmma_applicable((int)dims[0], E, howmany))
+    return fit_dmma_1d(di, dev, (int)dims[0], (long long)E * howmany, sizeof(R) == 8 ? FASTCHEB_F64 : FASTCHEB_F32, vals,
+                       coefs, E, st);
+
+  // ping-pong so that the last pass lands in `coefs`; `vals` is never written
+  R* tmp = nullptr;
+  R* tmp2 = nullptr;
+  if (npass > 1 || (const void*)vals == (void*)coefs) {
+    tmp = (R*)ws_acquire(dev, (size_t)total * sizeof(R));
+    if (!tmp) return fail(FASTCHEB_ENOMEM, "fit scratch of %lld bytes", total * (long long)sizeof(R));
+  }
+  const R* src = vals;
+  int rc = FASTCHEB_OK;
+  int pass = 0;
+  long long inner = E;
+  for (int d = 0; d < ndim && rc == FASTCHEB_OK; ++d) {
+    const int n = (int)dims[d];
+    if (n > 1) {
+      // destination: coefs if the remaining pass count (including this one) is odd, else tmp
+      const int remaining = npass - pass;
+      R* dst = (remaining % 2 == 1) ? coefs : tmp;
+      if ((const void*)dst == (const void*)src) {
+        // only possible on pass 0 with vals == coefs and odd npass: move vals out of the way first
+        tmp2 = (R*)ws_acquire(dev, (size_t)total * sizeof(R));
+        if (!tmp2) {
+          rc = fail(FASTCHEB_ENOMEM, "fit scratch of %lld bytes", total * (long long)sizeof(R));
+          break;
+        }
+        cudaMemcpyAsync(tmp2, src, (size_t)total * sizeof(R), cudaMemcpyDeviceToDevice, st);
+        src = tmp2;
+      }
+      const double2* ctab = nullptr;
+      if ((rc = cos_table(dev, n, &ctab)) != FASTCHEB_OK) break;
+      dct1_direct_kernel<R><<<grid_for(total, 256, di->sms), 256, 0, st>>>(src, dst, ctab, total, n, inner);
+      if (cudaGetLastError() != cudaSuccess) {
+        rc = fail(FASTCHEB_ECUDA, "DCT-I kernel launch failed");
+        break;
+      }
+      note_launch();
+      src = dst;
+      ++pass;
+    }
+    inner *= n;
+  }
+  if (tmp || tmp2) cudaStreamSynchronize(st);  // scratch goes back to the cache only once the work is done
+  if (tmp) ws_release(dev, tmp);
+  if (tmp2) ws_release(dev, tmp2);
+  return rc;
+}
+
+template <typename R>
+int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int cplx, int K, int64_t howmany,
+                 const R* vals, R* coefs, double* maxabs_dev, long long* bad_dev, cudaStream_t st) {
+  const int E = K * (cplx ? 2 : 1);
+  long long elems = 1;
+  for (int d = 0; d < ndim; ++d) elems *= dims[d];
+  const long long total = elems * E * howmany;
+  if (bad_dev) {
+    nonfinite_kernel<R><<<grid_for(total, 256, di->sms), 256, 0, st>>>(vals, total, bad_dev);  // interp.jl:40
+    FC_CUDA(cudaGetLastError());
+    note_launch();
+  }
+  FC_TRY(fit_passes<R>(di, dev, ndim, dims, E, howmany, vals, coefs, st));
+  if (maxabs_dev) {
+    FC_CUDA(cudaMemsetAsync(maxabs_dev, 0, (size_t)howmany * sizeof(double), st));
+    const long long nchunks = ((elems + 1023) / 1024) * howmany;
+    coef_max_kernel<R><<<grid_for(nchunks * 32, 256, di->sms), 256, 0, st>>>(coefs, elems, howmany, K, cplx, maxabs_dev);
+    FC_CUDA(cudaGetLastError());
+    note_launch();
+  }
+  return FASTCHEB_OK;
+}
+
+int fit_device(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int dtype, int cplx, int K, int64_t howmany,
+               const void* vals, void* coefs, double* maxabs_dev, long long* bad_dev, cudaStream_t st) {
+  if (dtype == FASTCHEB_F64)
+    return fit_device_t<double>(di, dev, ndim, dims, cplx, K, howmany, (const double*)vals, (double*)coefs, maxabs_dev,
+                                bad_dev, st);
+  return fit_device_t<float>(di, dev, ndim, dims, cplx, K, howmany, (const float*)vals, (float*)coefs, maxabs_dev,
+                             bad_dev, st);
+}
+
+int check_args(int ndim, const int64_t* dims, int dtype, int ncomp, int mem) {
+  if (!dims) return fail(FASTCHEB_EINVAL, "null dims");
+  if (ndim < 1 || ndim > FASTCHEB_MAX_NDIM) return fail(FASTCHEB_EINVAL, "ndim = %d outside 1..%d", ndim, FASTCHEB_MAX_NDIM);
+  if (dtype != FASTCHEB_F32 && dtype != FASTCHEB_F64) return fail(FASTCHEB_EINVAL, "bad dtype %d", dtype);
+  if (ncomp < 1) return fail(FASTCHEB_EINVAL, "ncomp = %d < 1", ncomp);
+  if (mem != FASTCHEB_MEM_HOST && mem != FASTCHEB_MEM_DEVICE) return fail(FASTCHEB_EINVAL, "bad mem %d", mem);
+  for (int d = 0; d < ndim; ++d)
+    if (dims[d] < 1 || dims[d] > (1 << 30)) return fail(FASTCHEB_EINVAL, "dims[%d] = %lld", d, (long long)dims[d]);
+  return FASTCHEB_OK;
+}
+
+// droptol's shape decision from device coefficients (interp.jl:77-93)
+int droptol_device(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int dtype, int cplx, int K,
+                   const void* d_coefs, double tol, int64_t* newdims, double* maxabs_out, cudaStream_t st) {
+  long long elems = 1;
+  int hsum = 0;
+  NormParams np;
+  memset(&np, 0, sizeof np);
+  np.ndim = ndim;
+  for (int d = 0; d < ndim; ++d) {
+    elems *= dims[d];
+    np.n[d] = (int)dims[d];
+    np.hoff[d] = hsum;
+    hsum += (int)dims[d];
+    newdims[d] = dims[d];
+  }
+  const size_t nd = 2 + (size_t)hsum;
+  double* d_stats = (double*)ws_acquire(dev, nd * sizeof(double));
+  if (!d_stats) return fail(FASTCHEB_ENOMEM, "droptol scratch");
+  std::vector<double> h(nd);
+  int rc = FASTCHEB_OK;
+  do {
+    // stats[0] = max (init 0), stats[1] = min (init +inf), hyperplane maxima (init 0)
+    std::vector<double> init(nd, 0.0);
+    init[1] = INFINITY;
+    if (cudaMemcpyAsync(d_stats, init.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      rc = fail(FASTCHEB_ECUDA, "droptol init copy failed");
+      break;
+    }
+    cudaStreamSynchronize(st);  // `init` is pageable: finish the copy before it goes out of scope
+    const int grid = grid_for(elems, 256, di->sms);
+    if (dtype == FASTCHEB_F64)
+      coef_norm_kernel<double><<<grid, 256, 0, st>>>((const double*)d_coefs, elems, 1, K, cplx, d_stats, d_stats + 2, np);
+    else
+      coef_norm_kernel<float><<<grid, 256, 0, st>>>((const float*)d_coefs, elems, 1, K, cplx, d_stats, d_stats + 2, np);
+    if (cudaGetLastError() != cudaSuccess ||
+        cudaMemcpyAsync(h.data(), d_stats, nd * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = fail(FASTCHEB_ECUDA, "droptol reduction failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+  } while (0);
+  ws_release(dev, d_stats);
+  if (rc != FASTCHEB_OK) return rc;
+  const double mx = h[0], mn = h[1];
+  if (maxabs_out) *maxabs_out = mx;
+  const double abstol = mx * tol;  // interp.jl:78
+  if (mn >= abstol) return FASTCHEB_OK;  // interp.jl:79: nothing to drop
+  for (int d = 0; d < ndim; ++d) {   // interp.jl:83-91
+    int64_t n = dims[d];
+    while (n > 1 && !(h[2 + np.hoff[d] + (n - 1)] >= abstol)) --n;
+    newdims[d] = n;
+  }
+  return FASTCHEB_OK;
+}
+
+struct HostStage {
+  int dev;
+  void* d = nullptr;
+  HostStage(int dev_) : dev(dev_) {}
+  ~HostStage() {
+    if (d) ws_release(dev, d);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp, int64_t howmany, const void* vals,
+                 void* coefs, double* maxabs, int mem, int device, void* stream) {
+  FC_TRY(check_args(ndim, dims, dtype, ncomp, mem));
+  if (howmany < 0) return fail(FASTCHEB_EINVAL, "howmany < 0");
+  if (howmany == 0) return FASTCHEB_OK;
+  if (!vals || !coefs) return fail(FASTCHEB_EINVAL, "null buffer");
+  const DeviceInfo* di = device_info(device);
+  if (!di) return FASTCHEB_ECUDA;
+  DeviceGuard dg(device);
+  if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = real_size(dtype);
+  const int E = ncomp * (is_complex ? 2 : 1);
+  long long elems = 1;
+  for (int d = 0; d < ndim; ++d) elems *= dims[d];
+  const size_t bytes = (size_t)elems * E * howmany * rs;
+  FlagSlot fs;
+  FC_TRY(flag_acquire(device, &fs));
+  struct Rel {
+    FlagSlot& f;
+    ~Rel() { flag_release(f); }
+  } rel{fs};
+  FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+
+  if (mem == FASTCHEB_MEM_DEVICE) {
+    FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, howmany, vals, coefs, maxabs, fs.dev, st));
+  } else {
+    HostStage in(device), out(device), mx(device);
+    in.d = ws_acquire(device, bytes);
+    out.d = ws_acquire(device, bytes);
+    if (maxabs) mx.d = ws_acquire(device, (size_t)howmany * sizeof(double));
+    if (!in.d || !out.d || (maxabs && !mx.d)) return fail(FASTCHEB_ENOMEM, "device staging of %zu bytes", bytes);
+    FC_CUDA(cudaMemcpyAsync(in.d, vals, bytes, cudaMemcpyHostToDevice, st));
+    FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, howmany, in.d, out.d, (double*)mx.d, fs.dev, st));
+    FC_CUDA(cudaMemcpyAsync(coefs, out.d, bytes, cudaMemcpyDeviceToHost, st));
+    if (maxabs) FC_CUDA(cudaMemcpyAsync(maxabs, mx.d, (size_t)howmany * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(cudaStreamSynchronize(st));
+  }
+  FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaStreamSynchronize(st));
+  if (*fs.host != kNoBad) {
+    err_state().index = *fs.host;
+    return fail(FASTCHEB_ENONFINITE, "non-finite interpolant value at flat index %lld (interp.jl:40)", *fs.host);
+  }
+  return FASTCHEB_OK;
+}
+
+int fastcheb_droptol_shape(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp, const void* coefs,
+                           double tol, int64_t* newdims, int mem, int device, void* stream) {
+  FC_TRY(check_args(ndim, dims, dtype, ncomp, mem));
+  if (!coefs || !newdims) return fail(FASTCHEB_EINVAL, "null buffer");
+  const DeviceInfo* di = device_info(device);
+  if (!di) return FASTCHEB_ECUDA;
+  DeviceGuard dg(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int E = ncomp * (is_complex ? 2 : 1);
+  long long elems = 1;
+  for (int d = 0; d < ndim; ++d) elems *= dims[d];
+  const size_t bytes = (size_t)elems * E * real_size(dtype);
+  HostStage in(device);
+  const void* d_c = coefs;
+  if (mem == FASTCHEB_MEM_HOST) {
+    in.d = ws_acquire(device, bytes);
+    if (!in.d) return fail(FASTCHEB_ENOMEM, "device staging of %zu bytes", bytes);
+    FC_CUDA(cudaMemcpyAsync(in.d, coefs, bytes, cudaMemcpyHostToDevice, st));
+    d_c = in.d;
+  }
+  return droptol_device(di, device, ndim, dims, dtype, is_complex, ncomp, d_c, tol, newdims, nullptr, st);
+}
+
+int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
+                    const void* vals, int mem, const double* lb, const double* ub, double tol, int device,
+                    void* stream) {
+  if (!out || !lb || !ub || !vals) return fail(FASTCHEB_EINVAL, "null argument");
+  *out = nullptr;
+  FC_TRY(check_args(ndim, dims, dtype, ncomp, mem));
+  const DeviceInfo* di = device_info(device);
+  if (!di) return FASTCHEB_ECUDA;
+  DeviceGuard dg(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = real_size(dtype);
+  const int E = ncomp * (is_complex ? 2 : 1);
+  long long elems = 1;
+  for (int d = 0; d < ndim; ++d) elems *= dims[d];
+  const size_t bytes = (size_t)elems * E * rs;
+  if (tol < 0) tol = dtype == FASTCHEB_F64 ? DBL_EPSILON : (double)FLT_EPSILON;  // interp.jl:102
+
+  FlagSlot fs;
+  FC_TRY(flag_acquire(device, &fs));
+  struct Rel {
+    FlagSlot& f;
+    ~Rel() { flag_release(f); }
+  } rel{fs};
+  FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+  HostStage in(device), co(device), blk(device);
+  const void* d_vals = vals;
+  if (mem == FASTCHEB_MEM_HOST) {
+    in.d = ws_acquire(device, bytes);
+    if (!in.d) return fail(FASTCHEB_ENOMEM, "device staging of %zu bytes", bytes);
+    FC_CUDA(cudaMemcpyAsync(in.d, vals, bytes, cudaMemcpyHostToDevice, st));
+    d_vals = in.d;
+  }
+  co.d = ws_acquire(device, bytes);
+  if (!co.d) return fail(FASTCHEB_ENOMEM, "device scratch of %zu bytes", bytes);
+  FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, 1, d_vals, co.d, nullptr, fs.dev, st));
+  FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaStreamSynchronize(st));
+  if (*fs.host != kNoBad) {
+    err_state().index = *fs.host;
+    return fail(FASTCHEB_ENONFINITE, "non-finite interpolant value at flat index %lld (interp.jl:40)", *fs.host);
+  }
+  int64_t newdims[FASTCHEB_MAX_NDIM];
+  FC_TRY(droptol_device(di, device, ndim, dims, dtype, is_complex, ncomp, co.d, tol, newdims, nullptr, st));
+  bool same = true;
+  long long new_elems = 1;
+  for (int d = 0; d < ndim; ++d) {
+    same = same && newdims[d] == dims[d];
+    new_elems *= newdims[d];
+  }
+  const void* d_final = co.d;
+  if (!same) {
+    const size_t nb = (size_t)new_elems * E * rs;
+    blk.d = ws_acquire(device, nb);
+    if (!blk.d) return fail(FASTCHEB_ENOMEM, "device scratch of %zu bytes", nb);
+    BlockParams bp;
+    memset(&bp, 0, sizeof bp);
+    bp.ndim = ndim;
+    for (int d = 0; d < ndim; ++d) {
+      bp.n_old[d] = (int)dims[d];
+      bp.n_new[d] = (int)newdims[d];
+    }
+    const long long tot = new_elems * E;
+    const int grid = grid_for(tot, 256, di->sms);
+    if (dtype == FASTCHEB_F64)
+      leading_block_kernel<double><<<grid, 256, 0, st>>>((const double*)co.d, (double*)blk.d, tot, E, bp);  // interp.jl:92
+    else
+      leading_block_kernel<float><<<grid, 256, 0, st>>>((const float*)co.d, (float*)blk.d, tot, E, bp);
+    FC_CUDA(cudaGetLastError());
+    d_final = blk.d;
+  }
+  return create_from_device(out, ndim, newdims, dtype, is_complex, ncomp, d_final, lb, ub, device, st);
+}
+
+}  // extern "C"

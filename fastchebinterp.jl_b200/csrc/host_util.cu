@@ -1,0 +1,195 @@
+#include "host_util.h"
+#include <atomic>
+#include <map>
+
+namespace fastcheb {
+
+ErrState& err_state() {
+  static thread_local ErrState st;
+  return st;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  err_state().msg = buf;
+  return code;
+}
+
+namespace {
+std::mutex g_mu;
+std::map<int, DeviceInfo> g_devinfo;
+
+struct WsBuf {
+  void* p;
+  size_t bytes;
+  bool busy;
+};
+std::map<int, std::vector<WsBuf>> g_ws;
+
+constexpr int kFlagSlots = 64;
+struct FlagPool {
+  long long* dev = nullptr;
+  long long* host = nullptr;
+  uint64_t used = 0;
+};
+std::map<int, FlagPool> g_flags;
+
+__global__ void set_flag_kernel(long long* f, long long v) { *f = v; }
+}  // namespace
+
+std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+cudaError_t set_flag_async(long long* dev_flag, long long value, cudaStream_t st) {
+  note_launch();
+  set_flag_kernel<<<1, 1, 0, st>>>(dev_flag, value);
+  return cudaGetLastError();
+}
+
+const DeviceInfo* device_info(int dev) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_devinfo.find(dev);
+  if (it != g_devinfo.end()) return it->second.ok ? &it->second : nullptr;
+  DeviceInfo di;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || dev < 0 || dev >= count) {
+    fail(FASTCHEB_ECUDA, "no usable CUDA device %d (%s); libfastcheb_cuda has no CPU fallback", dev,
+         e != cudaSuccess ? cudaGetErrorString(e) : "index out of range");
+    cudaGetLastError();
+    return nullptr;  // not cached: a later call may see a device
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    fail(FASTCHEB_ECUDA, "cudaGetDeviceProperties(%d) failed", dev);
+    return nullptr;
+  }
+  di.sms = prop.multiProcessorCount;
+  di.cc_major = prop.major;
+  di.cc_minor = prop.minor;
+  di.smem_optin = prop.sharedMemPerBlockOptin;
+  di.ok = prop.major == 10;  // the fat binary holds sm_100a code only
+  g_devinfo[dev] = di;
+  if (!di.ok) {
+    fail(FASTCHEB_ECUDA, "device %d is sm_%d%d; libfastcheb_cuda is built for sm_100a (B200) only", dev, prop.major,
+         prop.minor);
+    return nullptr;
+  }
+  return &g_devinfo[dev];
+}
+
+DeviceGuard::DeviceGuard(int dev) {
+  if (cudaGetDevice(&prev_) != cudaSuccess) {
+    ok_ = false;
+    return;
+  }
+  if (prev_ != dev) {
+    ok_ = cudaSetDevice(dev) == cudaSuccess;
+    switched_ = ok_;
+  }
+}
+DeviceGuard::~DeviceGuard() {
+  if (switched_) cudaSetDevice(prev_);
+}
+
+void* ws_acquire(int dev, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto& v = g_ws[dev];
+    int best = -1;
+    for (int i = 0; i < (int)v.size(); ++i)
+      if (!v[i].busy && v[i].bytes >= bytes && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+    if (best >= 0) {
+      v[best].busy = true;
+      return v[best].p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    // drop idle cached buffers and retry once
+    std::vector<void*> drop;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      auto& v = g_ws[dev];
+      for (size_t i = 0; i < v.size();)
+        if (!v[i].busy) {
+          drop.push_back(v[i].p);
+          v.erase(v.begin() + i);
+        } else
+          ++i;
+    }
+    for (void* d : drop) cudaFree(d);
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_ws[dev].push_back({p, bytes, true});
+  return p;
+}
+
+void ws_release(int dev, void* p) {
+  if (!p) return;
+  void* to_free = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto& v = g_ws[dev];
+    size_t idle_bytes = 0;
+    int idle = 0;
+    for (auto& b : v)
+      if (!b.busy) {
+        ++idle;
+        idle_bytes += b.bytes;
+      }
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i].p == p) {
+        // keep at most 8 idle buffers / 8 GiB cached
+        if (idle >= 8 || idle_bytes + v[i].bytes > (size_t(8) << 30)) {
+          to_free = p;
+          v.erase(v.begin() + i);
+        } else {
+          v[i].busy = false;
+        }
+        break;
+      }
+  }
+  if (to_free) cudaFree(to_free);
+}
+
+int flag_acquire(int dev, FlagSlot* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  FlagPool& fp = g_flags[dev];
+  if (!fp.dev) {
+    if (cudaMalloc(&fp.dev, kFlagSlots * sizeof(long long)) != cudaSuccess ||
+        cudaHostAlloc(&fp.host, kFlagSlots * sizeof(long long), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(FASTCHEB_ENOMEM, "cannot allocate status flags on device %d", dev);
+    }
+  }
+  for (int i = 0; i < kFlagSlots; ++i)
+    if (!(fp.used >> i & 1)) {
+      fp.used |= uint64_t(1) << i;
+      out->dev = fp.dev + i;
+      out->host = fp.host + i;
+      out->dev_id = dev;
+      out->slot = i;
+      return FASTCHEB_OK;
+    }
+  return fail(FASTCHEB_ENOMEM, "more than %d concurrent calls on device %d", kFlagSlots, dev);
+}
+
+void flag_release(const FlagSlot& s) {
+  if (s.slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_flags[s.dev_id].used &= ~(uint64_t(1) << s.slot);
+}
+
+}  // namespace fastcheb

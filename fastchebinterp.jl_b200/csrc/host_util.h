@@ -1,0 +1,80 @@
+// Host-side plumbing shared by the C-ABI translation units: thread-local error state, device
+// bookkeeping, a small device-buffer cache and the per-call status-flag pool.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/fastcheb.h"
+
+namespace fastcheb {
+
+struct ErrState {
+  std::string msg;
+  int64_t index = -1;
+};
+ErrState& err_state();
+
+int fail(int code, const char* fmt, ...);
+
+#define FC_CUDA(x)                                                                              \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess)                                                                      \
+      return ::fastcheb::fail(e_ == cudaErrorMemoryAllocation ? FASTCHEB_ENOMEM : FASTCHEB_ECUDA, \
+                              "%s failed: %s", #x, cudaGetErrorString(e_));                     \
+  } while (0)
+#define FC_TRY(x)                   \
+  do {                              \
+    int rc_ = (x);                  \
+    if (rc_ != FASTCHEB_OK) return rc_; \
+  } while (0)
+
+struct DeviceInfo {
+  bool ok = false;
+  int sms = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t smem_optin = 0;
+};
+// cached per device; returns nullptr (and sets the error) if the device is unusable for this library
+const DeviceInfo* device_info(int dev);
+
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int dev);
+  ~DeviceGuard();
+  bool ok() const { return ok_; }
+
+ private:
+  int prev_ = -1;
+  bool switched_ = false, ok_ = true;
+};
+
+// grow-only cache of device scratch buffers (per device), so repeated host-memory calls do not pay
+// cudaMalloc each time.
+void* ws_acquire(int dev, size_t bytes);
+void ws_release(int dev, void* p);
+
+// one int64 device flag (+ pinned host mirror) per in-flight synchronous call
+struct FlagSlot {
+  long long* dev = nullptr;
+  long long* host = nullptr;  // pinned
+  int dev_id = -1;
+  int slot = -1;
+};
+int flag_acquire(int dev, FlagSlot* out);
+void flag_release(const FlagSlot& s);
+
+constexpr long long kNoBad = 0x7fffffffffffffffLL;
+cudaError_t set_flag_async(long long* dev_flag, long long value, cudaStream_t st);
+
+// process-wide count of kernels launched by this library (bench.py reports it as gpu_launches)
+void note_launch(int n = 1);
+long long launch_count();
+
+inline size_t real_size(int dtype) { return dtype == FASTCHEB_F64 ? 8 : 4; }
+
+}  // namespace fastcheb

@@ -1,0 +1,497 @@
+// C ABI: the ChebPoly handle and batched evaluation (include/fastcheb.h).
+#include "poly.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include "eval_clenshaw_launch.h"
+#include "eval_dmma_launch.h"
+
+using namespace fastcheb;
+
+namespace {
+
+// Julia layout -> planar-padded slabs of one component group.
+//   dst[((t*ec + c)*Ms + inner)*n1p + k1] = src[(e0+c) + E*(k1 + n1*(inner + Ms*t))], zero for k1 >= n1
+template <typename R>
+__global__ void __launch_bounds__(256) relayout_pp_kernel(const R* __restrict__ src, R* __restrict__ dst,
+                                                          long long total, int E, int e0, int ec, int n1, int n1p,
+                                                          long long Ms) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const int k1 = (int)(g % n1p);
+    long long rem = g / n1p;
+    const long long inner = rem % Ms;
+    rem /= Ms;
+    const int c = (int)(rem % ec);
+    const long long t = rem / ec;
+    dst[g] = k1 < n1 ? src[(e0 + c) + (long long)E * (k1 + (long long)n1 * (inner + Ms * t))] : R(0);
+  }
+}
+
+int grid_for(long long total, int threads, int sms) {
+  long long b = (total + threads - 1) / threads;
+  return (int)std::max<long long>(1, std::min<long long>(b, (long long)sms * 16));
+}
+
+int plan_clenshaw(fastcheb_poly* p, cudaStream_t st) {
+  const size_t rs = real_size(p->dtype);
+  const int V = 16 / (int)rs;
+  const int n1 = (int)p->dims[0];
+  const int n1p = (n1 + V - 1) / V * V;
+  const size_t budget = p->di->smem_optin - 1024 - 128;
+  for (int e0 = 0; e0 < p->E;) {
+    const int left = p->E - e0;
+    int ec = left <= kClenshawMaxEC ? left : (left == 5 ? 3 : (left % 4 == 0 ? 4 : (left % 3 == 0 ? 3 : 4)));
+    ClenshawGroup g;
+    g.e0 = e0;
+    g.ec = ec;
+    g.n1p = n1p;
+    g.nvec1 = n1p / V;
+    // the largest slab level that fits
+    int s = p->ndim;
+    for (; s >= 1; --s) {
+      double elems = (double)ec * n1p;
+      for (int d = 1; d < s; ++d) elems *= (double)p->dims[d];
+      long long T = 1;
+      for (int d = s; d < p->ndim; ++d) T *= p->dims[d];
+      const double bytes = elems * rs;
+      if (T == 1 ? bytes <= (double)budget : 2 * bytes <= (double)budget) break;
+    }
+    if (s < 1)
+      return fail(FASTCHEB_EUNSUPPORTED, "dimension 1 has %d coefficients: one line does not fit shared memory", n1);
+    long long Ms = 1, T = 1;
+    for (int d = 1; d < s; ++d) Ms *= p->dims[d];
+    for (int d = s; d < p->ndim; ++d) T *= p->dims[d];
+    if (T == 1) s = p->ndim;
+    g.s = s;
+    g.T = (int)T;
+    g.compStride = (int)(Ms * n1p);
+    g.slabElems = ec * g.compStride;
+    const size_t slabBytes = (size_t)g.slabElems * rs;
+    g.nstage = T == 1 ? 1 : (int)std::min<long long>(std::min<long long>(4, T), (long long)(budget / slabBytes));
+    g.smem = 128 + (size_t)g.nstage * slabBytes;
+    long long str = 1;
+    for (int d = 0; d < p->ndim; ++d) {
+      g.stride[d] = d < s ? (int)str : 0;
+      str *= (d == 0 ? n1p : p->dims[d]);
+    }
+    g.pp_bytes = slabBytes * (size_t)T;
+    FC_CUDA(cudaMalloc(&g.d_pp, g.pp_bytes));
+    const long long total = (long long)(g.pp_bytes / rs);
+    const int grid = grid_for(total, 256, p->di->sms);
+    if (p->dtype == FASTCHEB_F64)
+      relayout_pp_kernel<double><<<grid, 256, 0, st>>>((const double*)p->d_coefs, (double*)g.d_pp, total, p->E, e0, ec,
+                                                       n1, n1p, Ms);
+    else
+      relayout_pp_kernel<float><<<grid, 256, 0, st>>>((const float*)p->d_coefs, (float*)g.d_pp, total, p->E, e0, ec, n1,
+                                                      n1p, Ms);
+    FC_CUDA(cudaGetLastError());
+    note_launch();
+    p->groups.push_back(g);
+    e0 += ec;
+  }
+  return FASTCHEB_OK;
+}
+
+typedef cudaError_t (*ClenshawFn)(int, int, int, const EvalParams&, int, int, size_t, cudaStream_t, int*);
+ClenshawFn clenshaw_fn(int dtype, bool jac) {
+  if (dtype == FASTCHEB_F64) return jac ? clenshaw_f64_jac : clenshaw_f64_val;
+  return jac ? clenshaw_f32_jac : clenshaw_f32_val;
+}
+
+int eval_clenshaw(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+                  int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st) {
+  if (p->ndim > kMaxKernelNdim)
+    return fail(FASTCHEB_EUNSUPPORTED, "ndim = %d: evaluation kernels cover ndim <= %d", p->ndim, kMaxKernelNdim);
+  ClenshawFn fn = clenshaw_fn(p->dtype, jac);
+  const int P = jac ? kClenshawPtsJac : kClenshawPtsVal;
+  for (const ClenshawGroup& g : p->groups) {
+    EvalParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.coefs = g.d_pp;
+    prm.pts = pts;
+    prm.out_v = out_v;
+    prm.out_J = out_J;
+    prm.bad = (&g == &p->groups[0]) ? bad_dev : nullptr;  // the domain check is per point, not per group
+    prm.npts = npts;
+    prm.idx_base = idx_base;
+    prm.v_stride = v_stride;
+    prm.J_stride = J_stride;
+    prm.e0 = g.e0;
+    prm.Etot = p->E;
+    for (int d = 0; d < p->ndim; ++d) {
+      prm.n[d] = (int)p->dims[d];
+      prm.stride[d] = g.stride[d];
+      prm.lb[d] = p->lb[d];
+      prm.ub[d] = p->ub[d];
+    }
+    prm.nvec1 = g.nvec1;
+    prm.s = g.s;
+    prm.T = g.T;
+    prm.compStride = g.compStride;
+    prm.slabElems = g.slabElems;
+    prm.nstage = g.nstage;
+    // block size: the widest block the instantiation allows, narrowed for small batches so that the
+    // points spread over all SMs
+    const bool heavy = !jac && p->ndim * g.ec >= kClenshawHeavy;
+    int threads = jac ? kClenshawMaxThreadsJac : (heavy ? kClenshawMaxThreadsHeavy : kClenshawMaxThreadsVal);
+    const long long per_sm = (npts + (long long)p->di->sms * P - 1) / ((long long)p->di->sms * P);
+    if (per_sm < threads) threads = (int)std::max<long long>(32, (per_sm + 31) / 32 * 32);
+    int bps = 1;
+    cudaError_t e = fn(kOpOccupancy, p->ndim, g.ec, prm, threads, 0, g.smem, st, &bps);
+    if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+    if (bps < 1) return fail(FASTCHEB_ECUDA, "Clenshaw kernel does not fit an SM (smem %zu B)", g.smem);
+    const long long tile = (long long)threads * P;
+    const long long ntiles = (npts + tile - 1) / tile;
+    const int grid = (int)std::min<long long>(ntiles, (long long)p->di->sms * bps);
+    e = fn(kOpLaunch, p->ndim, g.ec, prm, threads, grid, g.smem, st, nullptr);
+    if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "Clenshaw kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  return FASTCHEB_OK;
+}
+
+bool use_dmma(const fastcheb_poly* p, bool jac) {
+  if (!p->dmma.ok) return false;
+  if (p->algo == FASTCHEB_ALGO_CLENSHAW) return false;
+  (void)jac;
+  return true;
+}
+
+}  // namespace
+
+namespace fastcheb {
+
+int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+                int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st) {
+  if (npts == 0) return FASTCHEB_OK;
+  if (use_dmma(p, jac))
+    return dmma_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st);
+  return eval_clenshaw(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st);
+}
+
+int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
+                       const void* d_src, const double* lb, const double* ub, int device, cudaStream_t st) {
+  fastcheb_poly* p = new (std::nothrow) fastcheb_poly();
+  if (!p) return fail(FASTCHEB_ENOMEM, "out of host memory");
+  p->ndim = ndim;
+  p->dtype = dtype;
+  p->cplx = is_complex ? 1 : 0;
+  p->K = ncomp;
+  p->E = ncomp * (is_complex ? 2 : 1);
+  p->device = device;
+  p->di = device_info(device);
+  p->nelems = 1;
+  for (int d = 0; d < ndim; ++d) {
+    p->dims[d] = dims[d];
+    p->lb[d] = lb[d];
+    p->ub[d] = ub[d];
+    p->nelems *= dims[d];
+  }
+  p->coef_bytes = (size_t)p->nelems * p->E * real_size(dtype);
+  int rc = FASTCHEB_OK;
+  do {
+    if (cudaMalloc(&p->d_coefs, p->coef_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      rc = fail(FASTCHEB_ENOMEM, "cudaMalloc of %zu coefficient bytes failed", p->coef_bytes);
+      break;
+    }
+    if (cudaMemcpyAsync(p->d_coefs, d_src, p->coef_bytes, cudaMemcpyDefault, st) != cudaSuccess) {
+      rc = fail(FASTCHEB_ECUDA, "coefficient upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    if (ndim <= kMaxKernelNdim) {
+      if ((rc = plan_clenshaw(p, st)) != FASTCHEB_OK) break;
+      if ((rc = dmma_plan(p, st)) != FASTCHEB_OK) break;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = fail(FASTCHEB_ECUDA, "handle creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+  } while (0);
+  if (rc != FASTCHEB_OK) {
+    fastcheb_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return FASTCHEB_OK;
+}
+
+}  // namespace fastcheb
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int fastcheb_version(void) { return FASTCHEB_VERSION; }
+
+int64_t fastcheb_launch_count(void) { return (int64_t)launch_count(); }
+
+int fastcheb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+size_t fastcheb_last_error(char* buf, size_t n) {
+  const std::string& m = err_state().msg;
+  if (buf && n) {
+    const size_t k = std::min(n - 1, m.size());
+    memcpy(buf, m.data(), k);
+    buf[k] = 0;
+  }
+  return m.size();
+}
+
+int fastcheb_error_index(int64_t* idx) {
+  if (!idx) return fail(FASTCHEB_EINVAL, "null idx");
+  *idx = err_state().index;
+  return FASTCHEB_OK;
+}
+
+int fastcheb_create(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
+                    const void* coefs, int coefs_mem, const double* lb, const double* ub, int device) {
+  if (!out || !dims || !coefs || !lb || !ub) return fail(FASTCHEB_EINVAL, "null argument");
+  *out = nullptr;
+  if (ndim < 1 || ndim > FASTCHEB_MAX_NDIM)
+    return fail(FASTCHEB_EINVAL, "ndim = %d outside 1..%d", ndim, FASTCHEB_MAX_NDIM);
+  if (dtype != FASTCHEB_F32 && dtype != FASTCHEB_F64) return fail(FASTCHEB_EINVAL, "bad dtype %d", dtype);
+  if (ncomp < 1) return fail(FASTCHEB_EINVAL, "ncomp = %d < 1", ncomp);
+  if (coefs_mem != FASTCHEB_MEM_HOST && coefs_mem != FASTCHEB_MEM_DEVICE)
+    return fail(FASTCHEB_EINVAL, "bad coefs_mem %d", coefs_mem);
+  double total = 1;
+  for (int d = 0; d < ndim; ++d) {
+    if (dims[d] < 1) return fail(FASTCHEB_EINVAL, "dims[%d] = %lld < 1", d, (long long)dims[d]);
+    total *= (double)dims[d];
+  }
+  if (total * ncomp * 2 > 2.0e9) return fail(FASTCHEB_EUNSUPPORTED, "coefficient tensor too large");
+  if (!device_info(device)) return FASTCHEB_ECUDA;
+  DeviceGuard dg(device);
+  if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", device);
+  return create_from_device(out, ndim, dims, dtype, is_complex, ncomp, coefs, lb, ub, device, 0);
+}
+
+int fastcheb_destroy(fastcheb_poly* p) {
+  if (!p) return FASTCHEB_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != p->device) cudaSetDevice(p->device);
+  if (p->d_coefs) cudaFree(p->d_coefs);
+  for (auto& g : p->groups)
+    if (g.d_pp) cudaFree(g.d_pp);
+  if (p->dmma.d_frag) cudaFree(p->dmma.d_frag);
+  if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
+  cudaGetLastError();
+  delete p;
+  return FASTCHEB_OK;
+}
+
+int fastcheb_ndim(const fastcheb_poly* p) { return p ? p->ndim : -1; }
+int fastcheb_dims(const fastcheb_poly* p, int64_t* dims_out) {
+  if (!p || !dims_out) return fail(FASTCHEB_EINVAL, "null argument");
+  for (int d = 0; d < p->ndim; ++d) dims_out[d] = p->dims[d];
+  return FASTCHEB_OK;
+}
+int fastcheb_dtype(const fastcheb_poly* p) { return p ? p->dtype : -1; }
+int fastcheb_is_complex(const fastcheb_poly* p) { return p ? p->cplx : -1; }
+int fastcheb_ncomp(const fastcheb_poly* p) { return p ? p->K : -1; }
+int fastcheb_device(const fastcheb_poly* p) { return p ? p->device : -1; }
+
+int fastcheb_get_coefs(const fastcheb_poly* p, void* dst, int dst_mem) {
+  if (!p || !dst) return fail(FASTCHEB_EINVAL, "null argument");
+  (void)dst_mem;
+  DeviceGuard dg(p->device);
+  FC_CUDA(cudaMemcpy(dst, p->d_coefs, p->coef_bytes, cudaMemcpyDefault));
+  return FASTCHEB_OK;
+}
+
+int fastcheb_set_algo(fastcheb_poly* p, int algo) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  if (algo == FASTCHEB_ALGO_DMMA && !p->dmma.ok)
+    return fail(FASTCHEB_EUNSUPPORTED, "the DMMA path needs Float64 coefficients, ndim >= 2 and n1 >= 5");
+  if (algo != FASTCHEB_ALGO_AUTO && algo != FASTCHEB_ALGO_CLENSHAW && algo != FASTCHEB_ALGO_DMMA)
+    return fail(FASTCHEB_EINVAL, "bad algo %d", algo);
+  p->algo = algo;
+  return FASTCHEB_OK;
+}
+
+int fastcheb_get_algo(const fastcheb_poly* p, int jac) {
+  if (!p) return -1;
+  return use_dmma(p, jac != 0) ? FASTCHEB_ALGO_DMMA : FASTCHEB_ALGO_CLENSHAW;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// synchronous evaluation entry points
+namespace {
+
+struct OutSpec {
+  // per point: `v_reals` reals at v, `J_reals` reals at J; strides in reals
+  void* v;
+  void* J;
+  int64_t v_stride, J_stride;
+  bool interleaved;  // v and J share one buffer (tuple layout)
+};
+
+int check_flag(long long flag, const fastcheb_poly* p) {
+  if (flag == kNoBad) return FASTCHEB_OK;
+  err_state().index = flag;
+  return fail(FASTCHEB_EDOMAIN, "point %lld not in domain (eval.jl:64)", flag);
+}
+
+int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSpec& o, bool jac, int mem,
+              void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  if (npts < 0) return fail(FASTCHEB_EINVAL, "npts < 0");
+  if (npts == 0) return FASTCHEB_OK;
+  if (!pts || !o.v || (jac && !o.J)) return fail(FASTCHEB_EINVAL, "null buffer");
+  if (mem != FASTCHEB_MEM_HOST && mem != FASTCHEB_MEM_DEVICE) return fail(FASTCHEB_EINVAL, "bad mem %d", mem);
+  DeviceGuard dg(p->device);
+  if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  FlagSlot fs;
+  FC_TRY(flag_acquire(p->device, &fs));
+  struct Rel {
+    FlagSlot& f;
+    ~Rel() { flag_release(f); }
+  } rel{fs};
+  const size_t rs = real_size(p->dtype);
+
+  if (mem == FASTCHEB_MEM_DEVICE) {
+    FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+    FC_TRY(eval_device(p, pts, npts, o.v, o.v_stride, o.J, o.J_stride, jac, fs.dev, 0, st));
+    FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(cudaStreamSynchronize(st));
+    return check_flag(*fs.host, p);
+  }
+
+  // host buffers: chunked H2D -> kernel -> D2H pipeline on two internal streams
+  const int N = p->ndim, E = p->E;
+  const size_t in_pp = (size_t)N * rs;
+  size_t out_pp;  // bytes per point of output, all buffers
+  if (o.interleaved)
+    out_pp = (size_t)o.v_stride * rs;
+  else
+    out_pp = (size_t)E * rs + (jac ? (size_t)E * N * rs : 0);
+  int64_t chunk = std::min<int64_t>(npts, std::max<int64_t>(1 << 16, (int64_t)((size_t(256) << 20) / (in_pp + out_pp))));
+  const int nbuf = npts > chunk ? 2 : 1;
+  cudaStream_t ss[2] = {nullptr, nullptr};
+  void* dbuf[2] = {nullptr, nullptr};
+  int rc = FASTCHEB_OK;
+  const size_t in_bytes = (size_t)chunk * in_pp;
+  const size_t v_bytes = o.interleaved ? (size_t)chunk * out_pp : (size_t)chunk * E * rs;
+  const size_t in_al = (in_bytes + 255) / 256 * 256, v_al = (v_bytes + 255) / 256 * 256;
+  const size_t J_bytes = (!o.interleaved && jac) ? (size_t)chunk * E * N * rs : 0;
+  auto cleanup = [&]() {
+    for (int i = 0; i < 2; ++i) {
+      if (ss[i]) cudaStreamDestroy(ss[i]);
+      if (dbuf[i]) ws_release(p->device, dbuf[i]);
+    }
+  };
+  for (int i = 0; i < nbuf; ++i) {
+    if (cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) != cudaSuccess) {
+      cleanup();
+      return fail(FASTCHEB_ECUDA, "cudaStreamCreate failed");
+    }
+    dbuf[i] = ws_acquire(p->device, in_al + v_al + J_bytes);
+    if (!dbuf[i]) {
+      cleanup();
+      return fail(FASTCHEB_ENOMEM, "device staging buffer of %zu bytes", in_al + v_al + J_bytes);
+    }
+  }
+  cudaError_t ce = set_flag_async(fs.dev, kNoBad, ss[0]);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ss[0]);
+  int64_t done = 0;
+  for (int it = 0; ce == cudaSuccess && rc == FASTCHEB_OK && done < npts; ++it) {
+    const int b = it % nbuf;
+    const int64_t m = std::min<int64_t>(chunk, npts - done);
+    char* d_in = (char*)dbuf[b];
+    char* d_v = d_in + in_al;
+    char* d_J = d_v + v_al;
+    ce = cudaMemcpyAsync(d_in, (const char*)pts + (size_t)done * in_pp, (size_t)m * in_pp, cudaMemcpyHostToDevice, ss[b]);
+    if (ce != cudaSuccess) break;
+    if (o.interleaved) {
+      rc = eval_device(p, d_in, m, d_v, o.v_stride, (char*)d_v + (size_t)E * rs, o.J_stride, jac, fs.dev, done, ss[b]);
+      if (rc != FASTCHEB_OK) break;
+      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * out_pp, d_v, (size_t)m * out_pp, cudaMemcpyDeviceToHost, ss[b]);
+    } else {
+      rc = eval_device(p, d_in, m, d_v, E, d_J, (int64_t)E * N, jac, fs.dev, done, ss[b]);
+      if (rc != FASTCHEB_OK) break;
+      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * E * rs, d_v, (size_t)m * E * rs, cudaMemcpyDeviceToHost, ss[b]);
+      if (ce == cudaSuccess && jac)
+        ce = cudaMemcpyAsync((char*)o.J + (size_t)done * E * N * rs, d_J, (size_t)m * E * N * rs,
+                             cudaMemcpyDeviceToHost, ss[b]);
+    }
+    done += m;
+  }
+  for (int i = 0; i < nbuf; ++i)
+    if (ss[i]) {
+      cudaError_t e2 = cudaStreamSynchronize(ss[i]);
+      if (ce == cudaSuccess) ce = e2;
+    }
+  if (ce == cudaSuccess) ce = cudaMemcpy(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (rc != FASTCHEB_OK) return rc;
+  if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged evaluation failed: %s", cudaGetErrorString(ce));
+  return check_flag(*fs.host, p);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fastcheb_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out, int mem, void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  OutSpec o{out, nullptr, p->E, 0, false};
+  return eval_sync(p, pts, npts, o, false, mem, stream);
+}
+
+int fastcheb_eval_jac(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_J, int mem,
+                      void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  OutSpec o{out_v, out_J, p->E, (int64_t)p->E * p->ndim, false};
+  return eval_sync(p, pts, npts, o, true, mem, stream);
+}
+
+int fastcheb_eval_grad(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_g, int mem,
+                       void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  if (p->K != 1)
+    return fail(FASTCHEB_EDIMMISMATCH, "chebgradient needs a scalar-valued polynomial, got %d components (eval.jl:170)",
+                p->K);
+  return fastcheb_eval_jac(p, pts, npts, out_v, out_g, mem, stream);
+}
+
+int fastcheb_eval_jac_tuple(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_vJ, int mem,
+                            void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  const int64_t rec = (int64_t)p->E * (1 + p->ndim);
+  OutSpec o{out_vJ, out_vJ ? (char*)out_vJ + (size_t)p->E * real_size(p->dtype) : nullptr, rec, rec, true};
+  return eval_sync(p, pts, npts, o, true, mem, stream);
+}
+
+int fastcheb_eval_async(const fastcheb_poly* p, const void* pts_dev, int64_t npts, void* out_dev, int64_t* status_dev,
+                        void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  if (npts < 0 || (npts > 0 && (!pts_dev || !out_dev))) return fail(FASTCHEB_EINVAL, "bad buffer");
+  DeviceGuard dg(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (status_dev) FC_CUDA(set_flag_async((long long*)status_dev, kNoBad, st));
+  return eval_device(p, pts_dev, npts, out_dev, p->E, nullptr, 0, false, (long long*)status_dev, 0, st);
+}
+
+int fastcheb_eval_jac_async(const fastcheb_poly* p, const void* pts_dev, int64_t npts, void* out_v_dev, void* out_J_dev,
+                            int64_t* status_dev, void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  if (npts < 0 || (npts > 0 && (!pts_dev || !out_v_dev || !out_J_dev))) return fail(FASTCHEB_EINVAL, "bad buffer");
+  DeviceGuard dg(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (status_dev) FC_CUDA(set_flag_async((long long*)status_dev, kNoBad, st));
+  return eval_device(p, pts_dev, npts, out_v_dev, p->E, out_J_dev, (int64_t)p->E * p->ndim, true,
+                     (long long*)status_dev, 0, st);
+}
+
+}  // extern "C"

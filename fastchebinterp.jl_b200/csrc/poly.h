@@ -1,0 +1,60 @@
+// The device-resident ChebPoly handle (mirrors struct ChebPoly{N,T,Td}, FastChebInterp.jl:37-41).
+#pragma once
+#include <vector>
+#include "host_util.h"
+
+namespace fastcheb {
+
+// Clenshaw-path plan for one group of <= 4 real components
+struct ClenshawGroup {
+  int e0 = 0, ec = 0;
+  void* d_pp = nullptr;  // planar-padded slabs
+  size_t pp_bytes = 0;
+  int n1p = 0, nvec1 = 0;
+  int s = 0, T = 1;
+  int compStride = 0, slabElems = 0, nstage = 1;
+  int stride[FASTCHEB_MAX_NDIM] = {0};
+  size_t smem = 0;
+};
+
+// DMMA-path plan (FP64, ndim >= 2); see eval_dmma.cuh
+struct DmmaGroup {
+  int e0 = 0, ec = 0;
+  size_t offset = 0;  // doubles into d_frag
+};
+struct DmmaPlan {
+  bool ok = false;
+  void* d_frag = nullptr;  // coefficients in B-fragment order, one stream per component group
+  size_t frag_bytes = 0;
+  int KS = 0;         // 4-wide k steps covering k1 = 1..n1-1
+  int M = 0;          // columns per component = prod(n2..nN)
+  int ntiles = 0;     // ceil(M / 8)
+  int tabStride = 0;  // doubles per point row of the weight tables
+  std::vector<DmmaGroup> groups;
+};
+
+}  // namespace fastcheb
+
+struct fastcheb_poly {
+  int ndim = 0;
+  int64_t dims[FASTCHEB_MAX_NDIM] = {0};
+  int dtype = FASTCHEB_F64, cplx = 0, K = 1, E = 1;
+  double lb[FASTCHEB_MAX_NDIM] = {0}, ub[FASTCHEB_MAX_NDIM] = {0};
+  int device = 0;
+  const fastcheb::DeviceInfo* di = nullptr;
+  void* d_coefs = nullptr;  // Julia layout copy (fastcheb_get_coefs, re-layouts)
+  size_t coef_bytes = 0;
+  int64_t nelems = 0;  // prod dims
+  std::vector<fastcheb::ClenshawGroup> groups;
+  fastcheb::DmmaPlan dmma;
+  int algo = FASTCHEB_ALGO_AUTO;
+};
+
+namespace fastcheb {
+// enqueue a batched evaluation on `st`; all pointers are device pointers on p->device.
+int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+                int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st);
+// build the handle from coefficients already on the device (Julia layout); takes no ownership of d_src
+int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
+                       const void* d_src, const double* lb, const double* ub, int device, cudaStream_t st);
+}  // namespace fastcheb

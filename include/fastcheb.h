@@ -1,0 +1,156 @@
+/* libfastcheb_cuda — C ABI of the B200 (sm_100a) hot path of FastChebInterp.jl.
+ *
+ * This is the drop-in boundary: what a Julia `src/cuda.jl` would `ccall` (INTEGRATION.md shows the
+ * binding).  The reference has no FFI layer of its own — its boundary is Julia's method table — so
+ * every entry point below names the reference method it replaces (file:line under the reference
+ * tree, FastChebInterp.jl v1.3.1).
+ *
+ * Conventions
+ *  - All functions return an `int` status (FASTCHEB_OK == 0).  A message for the last failure on the
+ *    calling thread is available from fastcheb_last_error(); the index of the first offending point
+ *    (EDOMAIN) or value (ENONFINITE) from fastcheb_error_index().
+ *  - Memory layouts are Julia's: coefficient arrays are column-major with
+ *    E = ncomp*(is_complex?2:1) reals stored inline per element (component index fastest, re/im
+ *    fastest of all); points are AoS `npts x ndim` reals (`Vector{SVector{N,T}}`); values are AoS
+ *    `npts x E` reals; Jacobians are `npts x (E x ndim)` with each E x ndim block column-major
+ *    (`SMatrix{K,N}` layout, J[i,j] at i + K*j).
+ *  - `dtype` selects the real scalar type of coefficients, points and outputs alike (promotion of
+ *    mixed precisions is the host wrapper's job, as it is Julia's in the reference).
+ *  - `mem` says where the caller's buffers live: FASTCHEB_MEM_HOST (pageable or pinned host memory;
+ *    the library stages through the GPU and returns after the results are back) or
+ *    FASTCHEB_MEM_DEVICE (device pointers on the handle's device; work is enqueued on `stream`).
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = the legacy default stream).
+ *  - The caller owns every buffer it passes; the library copies coefficients at create time and never
+ *    retains caller pointers after a call returns (for *_async: after the stream work completes).
+ *  - There is no CPU fallback: every compute entry point fails with FASTCHEB_ECUDA if no sm_100
+ *    device is usable.
+ */
+#ifndef FASTCHEB_H
+#define FASTCHEB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FASTCHEB_VERSION 100 /* 0.1.0 */
+
+/* real scalar type */
+#define FASTCHEB_F32 0
+#define FASTCHEB_F64 1
+
+/* where caller buffers live */
+#define FASTCHEB_MEM_HOST 0
+#define FASTCHEB_MEM_DEVICE 1
+
+/* status codes (-> the Julia exception the wrapper re-throws) */
+#define FASTCHEB_OK 0
+#define FASTCHEB_EDOMAIN 1      /* point outside [lb,ub] or NaN   -> ArgumentError  (eval.jl:64,148) */
+#define FASTCHEB_ENONFINITE 2   /* non-finite value in `vals`     -> DomainError    (interp.jl:40)   */
+#define FASTCHEB_EDIMMISMATCH 3 /* gradient of a vector-valued c  -> DimensionMismatch (eval.jl:170) */
+#define FASTCHEB_EINVAL 4       /* bad argument (null, rank, dtype, negative size) -> ArgumentError  */
+#define FASTCHEB_ECUDA 5        /* CUDA runtime failure / no usable device                          */
+#define FASTCHEB_ENOMEM 6       /* host or device allocation failed                                 */
+#define FASTCHEB_EUNSUPPORTED 7 /* a shape the kernels do not cover (ndim > FASTCHEB_MAX_NDIM ...)   */
+
+#define FASTCHEB_MAX_NDIM 6
+
+/* evaluation algorithm selector for fastcheb_set_algo (diagnostics / benchmarking only) */
+#define FASTCHEB_ALGO_AUTO 0
+#define FASTCHEB_ALGO_CLENSHAW 1 /* CUDA-core Clenshaw, one thread per point            */
+#define FASTCHEB_ALGO_DMMA 2     /* FP64 tensor-core first-dimension contraction (F64)   */
+
+typedef struct fastcheb_poly fastcheb_poly; /* device-resident ChebPoly{N,T,Td} (FastChebInterp.jl:37-41) */
+
+/* ---- library / device ------------------------------------------------------------------------ */
+int fastcheb_version(void);
+/* kernels launched by the library in this process so far (diagnostics; bench.py's gpu_launches) */
+int64_t fastcheb_launch_count(void);
+/* number of usable CUDA devices (0 if none; never fails) */
+int fastcheb_device_count(void);
+/* copy the calling thread's last error message (NUL-terminated, truncated to n) ; returns its length */
+size_t fastcheb_last_error(char* buf, size_t n);
+/* index (0-based) of the first offending point / value of the calling thread's last EDOMAIN / ENONFINITE */
+int fastcheb_error_index(int64_t* idx);
+
+/* ---- the ChebPoly handle ----------------------------------------------------------------------
+ * Mirrors `struct ChebPoly{N,T,Td}` (FastChebInterp.jl:37-41): coefs::Array{T,N}, lb, ub.
+ * dims[d] = size(coefs, d+1) >= 1.  `coefs` is read according to `coefs_mem`.  lb/ub travel as double
+ * (Td may be an integer type in the reference, runtests.jl:170).  The handle is immutable after
+ * creation; any number of host threads may evaluate it concurrently. */
+int fastcheb_create(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex,
+                    int ncomp, const void* coefs, int coefs_mem, const double* lb, const double* ub,
+                    int device);
+int fastcheb_destroy(fastcheb_poly* p); /* NULL is a no-op; safe from a finalizer thread */
+
+/* handle queries */
+int fastcheb_ndim(const fastcheb_poly* p);
+int fastcheb_dims(const fastcheb_poly* p, int64_t* dims_out);
+int fastcheb_dtype(const fastcheb_poly* p);
+int fastcheb_is_complex(const fastcheb_poly* p);
+int fastcheb_ncomp(const fastcheb_poly* p);
+int fastcheb_device(const fastcheb_poly* p);
+/* copy the coefficients back in Julia layout (dst on host or device per dst_mem) */
+int fastcheb_get_coefs(const fastcheb_poly* p, void* dst, int dst_mem);
+/* force an evaluation algorithm (default AUTO); returns EUNSUPPORTED if the handle cannot run it */
+int fastcheb_set_algo(fastcheb_poly* p, int algo);
+/* which algorithm AUTO resolves to for value (jac=0) / Jacobian (jac=1) calls */
+int fastcheb_get_algo(const fastcheb_poly* p, int jac);
+
+/* ---- batched evaluation -----------------------------------------------------------------------
+ * fastcheb_eval      : c.(ys)                       — (::ChebPoly{N})(x) eval.jl:63-70 per point
+ * fastcheb_eval_jac  : chebjacobian.(Ref(c), ys)    — eval.jl:147-155; out_v npts x E, out_J npts x E x ndim
+ * fastcheb_eval_grad : chebgradient.(Ref(c), ys)    — eval.jl:168-177; requires ncomp == 1 (else EDIMMISMATCH)
+ * The *_tuple variants write one interleaved record per point, `E` reals of v followed by `E*ndim`
+ * reals of J — byte-identical to Julia's `Vector{Tuple{V,SMatrix{K,N}}}` / `Vector{Tuple{T,SVector{N}}}`.
+ * These calls are synchronous with respect to the result status: they return after the domain check
+ * of every point is known (FASTCHEB_EDOMAIN + fastcheb_error_index on failure; outputs are then
+ * unspecified — the reference's broadcast aborts on the first throw). */
+int fastcheb_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out, int mem, void* stream);
+int fastcheb_eval_jac(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_J,
+                      int mem, void* stream);
+int fastcheb_eval_grad(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_g,
+                       int mem, void* stream);
+int fastcheb_eval_jac_tuple(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_vJ, int mem,
+                            void* stream);
+
+/* Asynchronous device-memory variants: enqueue on `stream` and return immediately.  `status_dev`
+ * (device pointer to one int64, may be NULL) receives the index of the first out-of-domain point, or
+ * INT64_MAX if all points were inside; the caller initialises nothing and reads it after syncing. */
+int fastcheb_eval_async(const fastcheb_poly* p, const void* pts_dev, int64_t npts, void* out_dev,
+                        int64_t* status_dev, void* stream);
+int fastcheb_eval_jac_async(const fastcheb_poly* p, const void* pts_dev, int64_t npts, void* out_v_dev,
+                            void* out_J_dev, int64_t* status_dev, void* stream);
+
+/* ---- the fit ----------------------------------------------------------------------------------
+ * fastcheb_fit : chebcoefs(vals) (interp.jl:39-71) for `howmany` independent arrays stored back to
+ * back, each `dims[0] x ... x dims[ndim-1]` elements of E inline reals (so `chebinterp_v1`'s
+ * K x n1 x ... input, interp.jl:155-156, is ncomp = K).  Computes the N-d DCT-I (FFTW REDFT00 along
+ * every dim with n > 1, identity along n == 1, interp.jl:43-44), the 1/prod 2(n-1) scaling (:49) and the
+ * interior doubling (:50-54), every real component independently.  `vals` and `coefs` may alias.
+ * maxabs (may be NULL; `howmany` doubles, same memory kind as coefs): max_k infnorm(C_k) of each fit
+ * (interp.jl:74-78; complex modulus for complex elements), the quantity droptol scales `tol` by.
+ * Non-finite input -> FASTCHEB_ENONFINITE (+ flat real index via fastcheb_error_index). */
+int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp, int64_t howmany,
+                 const void* vals, void* coefs, double* maxabs, int mem, int device, void* stream);
+
+/* droptol(coefs, tol) shape decision (interp.jl:77-93) for one coefficient array: writes the trimmed
+ * sizes to newdims (== dims when nothing is dropped, including tol == 0).  The caller copies the
+ * leading block (interp.jl:92). */
+int fastcheb_droptol_shape(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
+                           const void* coefs, double tol, int64_t* newdims, int mem, int device,
+                           void* stream);
+
+/* chebinterp(vals, lb, ub; tol) (interp.jl:95-99,140-141) end to end on the device: fit, droptol,
+ * and creation of the handle holding the trimmed coefficients.  tol < 0 selects the reference's
+ * default eps(real type of vals) (interp.jl:102). */
+int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex,
+                    int ncomp, const void* vals, int mem, const double* lb, const double* ub, double tol,
+                    int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTCHEB_H */

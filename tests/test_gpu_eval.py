@@ -1,0 +1,210 @@
+"""GPU parity: batched evaluation / Jacobian through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): |dv| <= 16 eps sum|c| per evaluated value.  The Clenshaw kernels execute the
+oracle's exact IEEE operation sequence, so they are additionally required to be BIT-IDENTICAL to it.
+Jacobian entries of the tensor-core (basis-form) path are held to the same bound applied to the
+differentiated series: 16 eps sum|c| * max(1, (n_d-1)^2) * 2/(ub_d-lb_d)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # dims, K, complex, dtype
+    ((201,), None, False, np.float64),
+    ((65,), None, False, np.float32),
+    ((65,), 2, True, np.float64),
+    ((65, 65), None, False, np.float64),
+    ((49, 40), None, False, np.float32),
+    ((33, 33, 33), 3, False, np.float64),
+    ((17, 17, 17, 17), None, True, np.float64),
+    ((9, 8, 7), 5, False, np.float64),       # E = 5: two component groups
+    ((6, 5, 4), 4, True, np.float32),        # E = 8
+    ((1,), None, False, np.float64),         # n == 1 (eval.jl:22)
+    ((2,), None, False, np.float64),         # n == 2 (eval.jl:23)
+    ((2, 1), None, False, np.float64),       # mixed orders (1, 0) (runtests.jl:160-165)
+    ((1, 1, 1), 2, False, np.float64),
+    ((3, 1, 4), None, False, np.float64),
+    ((34, 3), None, False, np.float64),
+    ((5, 70), 3, False, np.float64),
+]
+
+
+def make(dims, K, cplx, dt, seed):
+    rng = np.random.default_rng(seed)
+    shape = dims + ((K,) if K else ())
+    c = rng.uniform(-1, 1, shape)
+    if cplx:
+        c = c + 1j * rng.uniform(-1, 1, shape)
+        c = c.astype(np.complex64 if dt == np.float32 else np.complex128)
+    else:
+        c = c.astype(dt)
+    N = len(dims)
+    lb = (-1.0 - 0.25 * np.arange(N)).astype(dt)
+    ub = (0.5 + 0.75 * np.arange(N)).astype(dt)
+    return rng, c, lb, ub
+
+
+def points(rng, lb, ub, npts, dt):
+    N = len(lb)
+    pts = (lb + (ub - lb) * rng.random((npts, N))).astype(dt)
+    pts = np.clip(pts, lb, ub)
+    pts[0], pts[1] = lb, ub                      # closed box: faces are inside (runtests.jl:174-179)
+    if npts > 4:
+        pts[2] = lb
+        pts[2, -1] = ub[-1]
+    return pts
+
+
+def ids(case):
+    dims, K, cplx, dt = case
+    return f"{'x'.join(map(str, dims))}-K{K}-{'c' if cplx else 'r'}-{np.dtype(dt).name}"
+
+
+@pytest.mark.parametrize("case", CASES, ids=ids)
+def test_value_parity(fc, orc, case):
+    dims, K, cplx, dt = case
+    rng, c, lb, ub = make(*case, seed=11)
+    pts = points(rng, lb, ub, 3001, dt)
+    ref = orc.OracleChebPoly(c, lb, ub)(pts)
+    poly = fc.ChebPoly(c, lb, ub)
+    tol = 16 * np.finfo(dt).eps * np.abs(c).sum()
+    poly.set_algo(fc.ALGO_CLENSHAW, dt)
+    got = poly(pts)
+    assert got.dtype == ref.dtype and got.shape == ref.shape
+    assert np.array_equal(got, ref), f"Clenshaw kernel not bit-identical: max diff {np.abs(got - ref).max():.3e} (tol {tol:.3e})"
+    if dt == np.float64 and len(dims) >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8:
+        poly.set_algo(fc.ALGO_DMMA, dt)
+        assert poly.get_algo(False) == fc.ALGO_DMMA
+        got2 = poly(pts)
+        assert np.abs(got2 - ref).max() <= tol, f"DMMA: {np.abs(got2 - ref).max():.3e} > {tol:.3e}"
+    # single-point call == the batched entry (runtests.jl:176-178)
+    one = poly(pts[5] if len(dims) > 1 else pts[5, 0])
+    poly.set_algo(fc.ALGO_AUTO, dt)
+    auto = poly(pts)
+    assert np.abs(auto - ref).max() <= tol
+    assert np.abs(np.asarray(one) - ref[5]).max() <= tol
+
+
+@pytest.mark.parametrize("case", CASES, ids=ids)
+def test_jacobian_parity(fc, orc, case):
+    dims, K, cplx, dt = case
+    rng, c, lb, ub = make(*case, seed=12)
+    pts = points(rng, lb, ub, 1501, dt)
+    v0, J0 = orc.OracleChebPoly(c, lb, ub).jacobian(pts)
+    poly = fc.ChebPoly(c, lb, ub)
+    poly.set_algo(fc.ALGO_CLENSHAW, dt)
+    v, J = fc.chebjacobian(poly, pts)
+    assert J.shape == J0.shape == (len(pts), K or 1, len(dims))
+    assert np.array_equal(v, v0) and np.array_equal(J, J0), "Clenshaw Jacobian kernel not bit-identical to the oracle"
+    for d, n in enumerate(dims):
+        if n == 1:
+            assert np.all(J[:, :, d] == 0)       # exactly zero (runtests.jl:152,158,165)
+    if dt == np.float64 and len(dims) >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8:
+        poly.set_algo(fc.ALGO_DMMA, dt)
+        v2, J2 = fc.chebjacobian(poly, pts)
+        tol = 16 * np.finfo(dt).eps * np.abs(c).sum()
+        assert np.abs(v2 - v0).max() <= tol
+        for d, n in enumerate(dims):
+            told = tol * max(1, (n - 1) ** 2) * 2 / (ub[d] - lb[d])
+            assert np.abs(J2[:, :, d] - J0[:, :, d]).max() <= told, (d, np.abs(J2[:, :, d] - J0[:, :, d]).max(), told)
+
+
+def test_gradient_shapes_and_errors(fc, orc):
+    rng = np.random.default_rng(3)
+    c = rng.uniform(-1, 1, (9, 7))
+    lb, ub = np.array([0.0, 1.0]), np.array([2.0, 4.0])
+    p = fc.ChebPoly(c, lb, ub)
+    ref = orc.OracleChebPoly(c, lb, ub)
+    x = np.array([0.3, 2.5])
+    v, g = fc.chebgradient(p, x)
+    v0, g0 = ref.gradient(x)
+    assert g.shape == (2,) and v == v0 and np.array_equal(g, g0)
+    pv = fc.ChebPoly(rng.uniform(-1, 1, (9, 7, 2)), lb, ub)
+    with pytest.raises(fc.DimensionMismatch):
+        fc.chebgradient(pv, x)                    # eval.jl:170
+    p1 = fc.ChebPoly(rng.uniform(-1, 1, 12), [0.0], [1.0])
+    v, dv = fc.chebgradient(p1, 0.25)             # 1-D scalar form returns a scalar derivative (eval.jl:174-177)
+    assert np.ndim(v) == 0 and np.ndim(dv) == 0
+
+
+def test_domain_errors(fc):
+    rng = np.random.default_rng(4)
+    p = fc.ChebPoly(rng.uniform(-1, 1, (8, 8)), [0.0, 0.0], [1.0, 1.0])
+    pts = rng.random((1000, 2))
+    p(pts)
+    bad = pts.copy()
+    bad[637, 1] = 1.0000001
+    bad[900, 0] = -0.1
+    with pytest.raises(fc.ArgumentError) as ei:
+        p(bad)                                    # eval.jl:64; first offending point is reported
+    assert "1.0000001" in str(ei.value)
+    nan = pts.copy()
+    nan[10, 0] = np.nan
+    with pytest.raises(fc.ArgumentError):
+        p(nan)                                    # NaN fails the closed-box test
+    with pytest.raises(fc.ArgumentError):
+        fc.chebjacobian(p, bad)                   # eval.jl:148
+    with pytest.raises(fc.ArgumentError):
+        p(np.array([0.5, 2.0]))
+    assert p(np.empty((0, 2))).shape == (0,)      # empty batch
+
+
+def test_promotion_rules(fc, orc):
+    """Float32 polynomial at Float32 points stays Float32; at Float64 points it promotes (eval.jl:25,65)."""
+    rng = np.random.default_rng(6)
+    c32 = rng.uniform(-1, 1, (10, 6)).astype(np.float32)
+    lb, ub = np.array([0, 0], dtype=np.float32), np.array([1, 2], dtype=np.float32)
+    p = fc.ChebPoly(c32, lb, ub)
+    x32 = (rng.random((50, 2)) * [1, 2]).astype(np.float32)
+    assert p(x32).dtype == np.float32
+    r = p(x32.astype(np.float64))
+    assert r.dtype == np.float64
+    assert np.array_equal(r, orc.OracleChebPoly(c32, lb, ub)(x32.astype(np.float64)))
+    pint = fc.ChebPoly(c32.astype(np.float64), np.array([0, 0]), np.array([1, 2]))   # Td = Int (runtests.jl:170)
+    assert np.array_equal(pint(x32.astype(np.float64)), orc.OracleChebPoly(c32.astype(np.float64), np.array([0, 0]), np.array([1, 2]))(x32.astype(np.float64)))
+
+
+def test_device_resident_batches(fc, orc):
+    """torch CUDA tensors in, torch CUDA tensors out, on torch's current stream (no host round trip)."""
+    import torch
+
+    rng = np.random.default_rng(7)
+    c = rng.uniform(-1, 1, (12, 11, 10, 3))
+    lb, ub = -np.ones(3), np.ones(3)
+    pts = rng.uniform(-1, 1, (100_003, 3))
+    p = fc.ChebPoly(c, lb, ub)
+    ref = orc.OracleChebPoly(c, lb, ub)(pts)
+    tol = 16 * np.finfo(float).eps * np.abs(c).sum()
+    t = torch.from_numpy(pts).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = p(t)
+        v, J = fc.chebjacobian(p, t)
+    s.synchronize()
+    assert out.is_cuda and out.shape == (len(pts), 3)
+    assert np.abs(out.cpu().numpy() - ref).max() <= tol
+    assert np.abs(v.cpu().numpy() - ref).max() <= tol
+    assert J.shape == (len(pts), 3, 3)
+    bad = t.clone()
+    bad[77777, 2] = 1.5
+    with pytest.raises(fc.ArgumentError):
+        p(bad)
+
+
+def test_tuple_layout(fc, orc):
+    """fastcheb_eval_jac_tuple writes Julia's Vector{Tuple{SVector{K},SMatrix{K,N}}} records."""
+    import ctypes
+
+    rng = np.random.default_rng(8)
+    c = rng.uniform(-1, 1, (7, 6, 2))
+    lb, ub = np.zeros(2), np.ones(2)
+    pts = rng.random((500, 2))
+    p = fc.ChebPoly(c, lb, ub)
+    p.set_algo(fc.ALGO_CLENSHAW)
+    v0, J0 = orc.OracleChebPoly(c, lb, ub).jacobian(pts)
+    rec = np.empty((500, 2 + 4))
+    rc = fc._capi.lib().fastcheb_eval_jac_tuple(p._handle(np.float64), pts.ctypes.data, 500, rec.ctypes.data, fc._capi.MEM_HOST, None)
+    assert rc == 0
+    assert np.array_equal(rec[:, :2], v0)
+    assert np.array_equal(rec[:, 2:].reshape(500, 2, 2), np.swapaxes(J0, 1, 2))   # column-major K x N
