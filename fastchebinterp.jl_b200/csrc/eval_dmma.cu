@@ -6,32 +6,6 @@
 namespace fastcheb {
 
 namespace {
-// Julia layout -> fragment stream of one component group (see the header comment).
-__global__ void __launch_bounds__(256) relayout_frag_kernel(const double* __restrict__ src, double* __restrict__ dst,
-                                                            long long total, int E, int e0, int ec, int n1, int M,
-                                                            int KS) {
-  const int U = KS * 32 + 8;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-       g += (long long)gridDim.x * blockDim.x) {
-    const int u = (int)(g % U);
-    long long rem = g / U;
-    const int e = (int)(rem % ec);
-    const long long tile = rem / ec;
-    int k1;
-    long long m;
-    if (u < 8) {
-      k1 = 0;
-      m = tile * 8 + u;
-    } else {
-      const int l = (u - 8) & 31, ks = (u - 8) >> 5;
-      k1 = 1 + 4 * ks + (l & 3);
-      m = tile * 8 + (l >> 2);
-    }
-    dst[g] = (k1 < n1 && m < M) ? src[(e0 + e) + (long long)E * (k1 + (long long)n1 * m)] : 0.0;
-  }
-}
-
-
 typedef cudaError_t (*DmmaFn)(int, int, int, const DmmaParams&, int, int, size_t, cudaStream_t, int*);
 DmmaFn dmma_fn(int ks, bool jac) {
   switch (ks) {
@@ -70,17 +44,25 @@ int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
     g.e0 = e0;
     g.ec = ec;
     g.offset = off;
-    off += (size_t)pl.ntiles * ec * U;
+    off += (size_t)pl.ntiles * (kDmmaMeta + ec * U);
     pl.groups.push_back(g);
     e0 += ec;
   }
   pl.frag_bytes = off * sizeof(double);
   FC_CUDA(cudaMalloc(&pl.d_frag, pl.frag_bytes));
+  FragDims fd;
+  memset(&fd, 0, sizeof fd);
+  fd.nd = p->ndim - 1;
+  for (int d = 0, o = 0; d < fd.nd; ++d) {
+    fd.n[d] = (int)p->dims[d + 1];
+    fd.toff[d] = o;
+    o += fd.n[d];
+  }
   for (const DmmaGroup& g : pl.groups) {
-    const long long total = (long long)pl.ntiles * g.ec * U;
+    const long long total = (long long)pl.ntiles * (kDmmaMeta + g.ec * U);
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)p->di->sms * 16));
-    relayout_frag_kernel<<<grid, 256, 0, st>>>((const double*)p->d_coefs, (double*)pl.d_frag + g.offset, total, p->E,
-                                               g.e0, g.ec, n1, pl.M, pl.KS);
+    relayout_frag_kernel<0><<<grid, 256, 0, st>>>((const double*)p->d_coefs, (double*)pl.d_frag + g.offset, total, p->E,
+                                               g.e0, g.ec, n1, pl.M, pl.KS, fd);
     FC_CUDA(cudaGetLastError());
     note_launch();
   }
@@ -121,14 +103,17 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
     int warps = dmma_max_warps(jac);
     const long long per_sm = (npts + (long long)p->di->sms * rows - 1) / ((long long)p->di->sms * rows);
     if (per_sm < warps) warps = (int)std::max<long long>(1, per_sm);
-    const size_t unitBytes = (size_t)g.ec * U * 8;
+    const size_t unitBytes = (size_t)(kDmmaMeta + g.ec * U) * 8;  // one tile record
     const size_t budget = p->di->smem_optin - 1024 - 128;
+    // Stage geometry (measured on B200, profiles/r01_dmma_variants.jsonl): crossing a stage costs a ring
+    // hand-off, so stages of 4 tile records beat 1-2 by 10+ points of FP64 peak; 3 stages of look-ahead
+    // are enough once a stage holds 4 tiles.
     int tps = 0, nstage = 0;
     for (;; --warps) {
       const size_t tabBytes = (size_t)warps * rows * pl.tabStride * 8 * (jac ? 2 : 1);
       if (tabBytes + 3 * unitBytes <= budget) {
         const size_t room = budget - tabBytes;
-        tps = (int)std::max<size_t>(1, std::min<size_t>(16384 / unitBytes, room / (4 * unitBytes)));
+        tps = (int)std::max<size_t>(1, std::min<size_t>(4, room / (3 * unitBytes)));
         tps = std::min(tps, pl.ntiles);
         nstage = (int)std::min<size_t>(4, room / (tps * unitBytes));
         if (nstage >= 3) break;

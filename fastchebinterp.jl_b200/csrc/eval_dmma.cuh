@@ -15,12 +15,17 @@
 // per 8 DMMA.  Everything is linear, so each lane keeps partial sums over the columns it owns and a
 // quad shuffle-reduction finishes a point.
 //
-// Layout: the handle stores the coefficients in B-fragment order — per 8-column tile and component
-// a "unit" of 8 + 32*KS doubles: the 8 k1=0 coefficients, then for each k-step the 32 lane values
-// B[k = lane%4][col = lane/4] = C[1 + 4*ks + lane%4, 8*tile + lane/4, e] — so a warp's B load is one
-// conflict-free LDS.64 and a stage of tiles is one contiguous bulk copy.  One elected thread streams
-// stages from L2 into a shared-memory ring with cp.async.bulk + full/empty mbarriers; all warps
-// (16 points each) consume the same stage.
+// Layout: the handle stores the coefficients as a stream of 8-column tile records
+//     [ 16 doubles of metadata | EC units of (8 + 32*KS) doubles ]
+// metadata: for each weighted dimension d and tile column j the int32 offset (into a point's weight-table
+// row) of T_{k_d}(z_d) for that column — so a lane finds the weights of its two columns with ND 8-byte
+// loads and no index arithmetic; unit: the 8 k1=0 coefficients of the tile, then per k-step the 32 lane
+// values B[k = lane%4][col = lane/4] = C[1 + 4*ks + lane%4, 8*tile + lane/4, e], so a warp's B load is one
+// conflict-free LDS.64 and a stage of tiles is one contiguous bulk copy (cp.async.bulk -> UBLKCP) from L2
+// into a shared-memory ring, signalled by mbarriers.  Every warp of the CTA consumes the same stage
+// (16 points per warp); the last warp to release a stage buffer refills it, so no warp ever waits for
+// another warp's progress, only for data.  The weights of tile t+1 are computed in the same basic block
+// as the DMMAs of tile t, which lets ptxas hide them in the DMMA issue gaps.
 #pragma once
 #include <cstdint>
 #include "ptx_util.cuh"
@@ -28,7 +33,7 @@
 namespace fastcheb {
 
 struct DmmaParams {
-  const double* frag;  // [tile][ec][U] fragment stream of this component group
+  const double* frag;  // tile-record stream of this component group
   const double* pts;
   double* out_v;
   double* out_J;
@@ -39,28 +44,38 @@ struct DmmaParams {
   int n[kMaxNdim];
   int ntiles;         // 8-column tiles per pass
   int M;              // prod n2..nN (valid columns)
-  int tilesPerStage;  // tiles per shared-memory stage
+  int tilesPerStage;  // tile records per shared-memory stage
   int nstage;
   int tabStride;  // doubles per point row of the weight tables
   double lb[kMaxNdim], ub[kMaxNdim];
+#ifdef FC_PROFILE
+  long long* prof;  // experiment: per-warp cycle counters
+#endif
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
+#ifndef FC_DMMA_MT
+#define FC_DMMA_MT 2
+#endif
+constexpr int kDmmaMT = FC_DMMA_MT;  // 8-point M tiles per warp
+constexpr int kDmmaMeta = 16;  // doubles of metadata per tile record (8 columns x up to 3 dims x int32, padded)
 
-constexpr int kDmmaMT = 2;  // 8-point M tiles per consumer warp
-
+#ifndef FC_DMMA_MAXT
+#define FC_DMMA_MAXT 512
+#endif
 template <int N, int EC, int KS, bool JAC>
-__global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_constant__ DmmaParams prm) {
+__global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __grid_constant__ DmmaParams prm) {
   constexpr int MT = kDmmaMT;
   constexpr int U = KS * 32 + 8;
+  constexpr int TR = kDmmaMeta + EC * U;  // doubles per tile record
   constexpr int ROWS = MT * 8;
+  constexpr int ND = N - 1;  // weighted dimensions 2..N
+  constexpr int NTAB = JAC ? 2 : 1;
   extern __shared__ __align__(128) unsigned char fastcheb_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(fastcheb_smem);
-  uint64_t* empty = full + 8;
+  unsigned int* released = reinterpret_cast<unsigned int*>(full + 8);  // warps done with each stage buffer
+  unsigned int* ready = released + 8;  // low 32 bits of (visit + 1) whose data is known to be in each buffer
   double* stages = reinterpret_cast<double*>(fastcheb_smem + 128);
-  const int stageDoubles = prm.tilesPerStage * EC * U;
+  const int stageDoubles = prm.tilesPerStage * TR;
   double* tables = stages + (size_t)prm.nstage * stageDoubles;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,27 +85,28 @@ __global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_cons
   if ((long long)blockIdx.x >= npass) return;
   const long long my_pass = (npass - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const int S = (prm.ntiles + prm.tilesPerStage - 1) / prm.tilesPerStage;  // stages per pass
+  const int ns = prm.nstage;
 
   if (threadIdx.x == 0) {
-    for (int b = 0; b < prm.nstage; ++b) {
+    for (int b = 0; b < ns; ++b) {
       mbar_init(&full[b], 1);
-      mbar_init(&empty[b], ncw);
+      released[b] = 0;
+      ready[b] = 0;
     }
     fence_mbar_init();
   }
   __syncthreads();
 
-  // The producer role is folded into lane 0 of warp 0 (all warps compute): visits 0..nstage-1 are
-  // issued here; the refill for visit u (>= nstage) is issued at the start of iteration u-nstage+2,
-  // after every warp has released visit u-nstage (two iterations of slack, so the wait rarely spins).
+  // No producer warp and no warp that others wait on: visits 0..nstage-1 are issued in the prologue, and
+  // the LAST warp to release a stage buffer (shared-memory counter) refills it with visit v + nstage.
   const long long total_visits = my_pass * S;
   auto issue = [&](long long u) {
-    const int b = (int)(u % prm.nstage);
+    const int b = (int)(u % ns);
     const int s = (int)(u % S);
     const int t0 = s * prm.tilesPerStage;
     const int nt = prm.ntiles - t0 < prm.tilesPerStage ? prm.ntiles - t0 : prm.tilesPerStage;
-    const uint32_t bytes = (uint32_t)nt * EC * U * 8u;
-    const char* src = reinterpret_cast<const char*>(prm.frag) + (size_t)t0 * EC * U * 8u;
+    const uint32_t bytes = (uint32_t)nt * TR * 8u;
+    const char* src = reinterpret_cast<const char*>(prm.frag) + (size_t)t0 * TR * 8u;
     char* dst = reinterpret_cast<char*>(stages + (size_t)b * stageDoubles);
     mbar_arrive_expect_tx(&full[b], bytes);
     for (uint32_t o = 0; o < bytes; o += 32768u) {
@@ -99,26 +115,89 @@ __global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_cons
     }
   };
   if (threadIdx.x == 0)
-    for (long long u = 0; u < prm.nstage && u < total_visits; ++u) issue(u);
+    for (long long u = 0; u < ns && u < total_visits; ++u) issue(u);
+  // Wait until visit `u` has landed in buffer `bb`.  All warps ask at about the same time and 16 mbarrier
+  // try_waits serialise in the sync unit, so the first warp through publishes a plain shared-memory flag
+  // and the others take a one-LDS fast path.
+#ifdef FC_PROFILE
+  long long prof_wait = 0, prof_slow = 0, prof_issue = 0, prof_t0 = clock64();
+#endif
+  auto wait_stage = [&](long long u, int bb, uint32_t parity) {
+    const unsigned tag = (unsigned)(u + 1);
+    unsigned seen;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&ready[bb])) : "memory");
+    if (seen != tag) {
+#ifdef FC_PROFILE
+      const long long t0 = clock64();
+      mbar_wait(&full[bb], parity);
+      prof_wait += clock64() - t0;
+      prof_slow += 1;
+#else
+      mbar_wait(&full[bb], parity);
+#endif
+      asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&ready[bb])), "r"(tag) : "memory");
+    }
+  };
 
-  // ---------------- consumers ----------------
-  const int c = lane & 3;     // column pair inside a tile / k index inside a k-step
-  const int r = lane >> 2;    // point row inside an M tile
-  constexpr int ND = N - 1;   // weighted dimensions 2..N
-  constexpr int NTAB = JAC ? 2 : 1;
+  const int c = lane & 3;   // column pair inside a tile / k index inside a k-step
+  const int r = lane >> 2;  // point row inside an M tile
   double* tab = tables + (size_t)warp * ROWS * prm.tabStride * NTAB;  // [row][tabStride] (+ derivative copy)
   double* dtab = tab + (size_t)ROWS * prm.tabStride;
-  int toff[ND];
-  {
-    int o = 0;
+  const double* trow[MT];
+  const double* drow[MT];
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      toff[d] = o;
-      o += prm.n[d + 1];
-    }
+  for (int mt = 0; mt < MT; ++mt) {
+    trow[mt] = tab + (size_t)(mt * 8 + r) * prm.tabStride;
+    drow[mt] = dtab + (size_t)(mt * 8 + r) * prm.tabStride;
   }
 
-  long long v = 0;  // stage visit counter (same sequence as the producer's)
+  // weights of the two columns this lane owns in the tile whose record starts at `rec`
+  struct Weights {
+    double w[MT][2];
+    double wd[JAC ? MT : 1][2][JAC ? N : 1];  // [..][d]: T' in dimension d+1 (d >= 1)
+  };
+  auto weights = [&](const double* rec, Weights& W) {
+    const int2* meta = reinterpret_cast<const int2*>(rec);
+    int2 ix[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) ix[d] = meta[d * 4 + c];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      double t0[ND], t1[ND];
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        t0[d] = trow[mt][ix[d].x];
+        t1[d] = trow[mt][ix[d].y];
+      }
+      double w0 = t0[0], w1 = t1[0];
+#pragma unroll
+      for (int d = 1; d < ND; ++d) {
+        w0 *= t0[d];
+        w1 *= t1[d];
+      }
+      W.w[mt][0] = w0;
+      W.w[mt][1] = w1;
+      if constexpr (JAC) {
+#pragma unroll
+        for (int dd = 0; dd < ND; ++dd) {
+          double x0 = drow[mt][ix[dd].x], x1 = drow[mt][ix[dd].y];
+#pragma unroll
+          for (int d = 0; d < ND; ++d)
+            if (d != dd) {
+              x0 *= t0[d];
+              x1 *= t1[d];
+            }
+          W.wd[mt][0][dd + 1] = x0;
+          W.wd[mt][1][dd + 1] = x1;
+        }
+      }
+    }
+  };
+
+  // ring position of the stage being consumed (same sequence in every warp)
+  long long v = 0;
+  int b = 0;
+  uint32_t ph = 0;
   for (long long pass = blockIdx.x; pass < npass; pass += gridDim.x) {
     // ---- points of this warp: row r of M tile mt is point base + mt*8 + r ----
     const long long base = pass * pass_pts + (long long)warp * ROWS;
@@ -149,8 +228,8 @@ __global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_cons
       // A fragments: T_k(z1), k = 1 + 4*ks + c  (and T'_k)
       {
         const double z2 = 2.0 * z[0];
-        double tkm = 1.0, tk = z[0];     // T_0, T_1
-        double dkm = 0.0, dk = 1.0;      // T'_0, T'_1
+        double tkm = 1.0, tk = z[0];  // T_0, T_1
+        double dkm = 0.0, dk = 1.0;   // T'_0, T'_1
 #pragma unroll
         for (int k = 1; k <= 4 * KS; ++k) {
           if (((k - 1) & 3) == c) {
@@ -168,21 +247,23 @@ __global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_cons
         }
       }
       // weight tables of dims 2..N: every lane of the quad runs the recurrence, lane c stores k % 4 == c
+      int o = 0;
 #pragma unroll
       for (int d = 0; d < ND; ++d) {
         const double zz = z[d + 1], z2 = 2.0 * zz;
         double tkm = 1.0, tk = zz, dkm = 0.0, dk = 1.0;
-        double* trow = tab + (size_t)(mt * 8 + r) * prm.tabStride + toff[d];
-        double* drow = dtab + (size_t)(mt * 8 + r) * prm.tabStride + toff[d];
+        double* tr = tab + (size_t)(mt * 8 + r) * prm.tabStride + o;
+        double* dr = dtab + (size_t)(mt * 8 + r) * prm.tabStride + o;
         const int nd = prm.n[d + 1];
+        o += nd;
         if (c == 0) {
-          trow[0] = 1.0;
-          if constexpr (JAC) drow[0] = 0.0;
+          tr[0] = 1.0;
+          if constexpr (JAC) dr[0] = 0.0;
         }
         for (int k = 1; k < nd; ++k) {
           if ((k & 3) == c) {
-            trow[k] = tk;
-            if constexpr (JAC) drow[k] = dk;
+            tr[k] = tk;
+            if constexpr (JAC) dr[k] = dk;
           }
           const double tn = fma(z2, tk, -tkm);
           if constexpr (JAC) {
@@ -211,123 +292,104 @@ __global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_cons
         }
       }
 
-    // column counters of the two slots this lane owns: m = 8*tile + 2*c + slot
-    int kk[2][ND];
-#pragma unroll
-    for (int sl = 0; sl < 2; ++sl) {
-      int m = 2 * c + sl;
-#pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        const int nd = prm.n[d + 1];
-        if (d < ND - 1) {
-          kk[sl][d] = m % nd;
-          m /= nd;
+    // first stage of the pass
+    wait_stage(v, b, ph);
+    const double* rec = stages + (size_t)b * stageDoubles;
+    Weights W;
+    weights(rec, W);
+    int tin = 0;  // tile index inside the current stage
+    int nt = prm.ntiles < prm.tilesPerStage ? prm.ntiles : prm.tilesPerStage;
+    for (int tile = 0; tile < prm.ntiles; ++tile) {
+      // ---- where is the next tile's record?  (crossing into the next stage waits for it one tile early)
+      const bool last_in_stage = tin + 1 == nt;
+      const bool has_next = tile + 1 < prm.ntiles;
+      const double* rec_next = rec + TR;
+      int nb = b;
+      uint32_t nph = ph;
+      if (last_in_stage) {
+        nb = b + 1 == ns ? 0 : b + 1;
+        nph = nb == 0 ? ph ^ 1u : ph;
+        if (has_next) {
+          wait_stage(v + 1, nb, nph);
+          rec_next = stages + (size_t)nb * stageDoubles;
         } else {
-          kk[sl][d] = m;  // last dimension keeps the overflow (padding columns)
+          rec_next = rec;  // harmless recomputation of this tile's weights
         }
       }
-    }
-
-    int tile = 0;
-    for (int s = 0; s < S; ++s, ++v) {
-      const int b = (int)(v % prm.nstage);
-      if (threadIdx.x == 0 && v >= 2) {
-        const long long u = v - 2 + prm.nstage;
-        if (u < total_visits) {
-          const int bb = (int)((v - 2) % prm.nstage);
-          mbar_wait(&empty[bb], (uint32_t)(((v - 2) / prm.nstage) & 1));
-          issue(u);
+      // ---- one basic block: weights of the next tile + the DMMAs of this tile
+      Weights Wn;
+      weights(rec_next, Wn);
+#pragma unroll
+      for (int e = 0; e < EC; ++e) {
+        const double* u = rec + kDmmaMeta + e * U;
+        const double2 c0 = *reinterpret_cast<const double2*>(u + 2 * c);
+        double g0[MT], g1[MT];
+        double h0[JAC ? MT : 1], h1[JAC ? MT : 1];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          g0[mt] = c0.x;  // k1 = 0 term: T_0 = 1
+          g1[mt] = c0.y;
+          if constexpr (JAC) h0[mt] = h1[mt] = 0.0;
         }
-      }
-      __syncwarp();
-      mbar_wait(&full[b], (uint32_t)((v / prm.nstage) & 1));
-      const double* sb = stages + (size_t)b * stageDoubles;
-      const int nt = prm.ntiles - tile < prm.tilesPerStage ? prm.ntiles - tile : prm.tilesPerStage;
-      for (int t = 0; t < nt; ++t, ++tile) {
-        // weights of this tile's two columns for each M tile
-        double w[MT][2];
-        double wd[JAC ? MT : 1][2][JAC ? N : 1];  // [..][d]: weight with T' in dimension d+1 (d >= 1)
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
-          int ki[ND];
-#pragma unroll
-          for (int d = 0; d < ND; ++d) {
-            const int nd = prm.n[d + 1];
-            ki[d] = kk[sl][d] < nd ? kk[sl][d] : nd - 1;  // clamp padding columns (their coefficients are 0)
-          }
+        for (int ks = 0; ks < KS; ++ks) {
+          const double bf = u[8 + ks * 32 + lane];
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            const double* trow = tab + (size_t)(mt * 8 + r) * prm.tabStride;
-            double tv[ND];
-#pragma unroll
-            for (int d = 0; d < ND; ++d) tv[d] = trow[toff[d] + ki[d]];
-            double ww = tv[0];
-#pragma unroll
-            for (int d = 1; d < ND; ++d) ww *= tv[d];
-            w[mt][sl] = ww;
-            if constexpr (JAC) {
-              const double* drow = dtab + (size_t)(mt * 8 + r) * prm.tabStride;
-#pragma unroll
-              for (int dd = 0; dd < ND; ++dd) {
-                double x = drow[toff[dd] + ki[dd]];
-#pragma unroll
-                for (int d = 0; d < ND; ++d)
-                  if (d != dd) x *= tv[d];
-                wd[mt][sl][dd + 1] = x;
-              }
-            }
-          }
-          // advance this slot's column counters by 8
-          kk[sl][0] += 8;
-#pragma unroll
-          for (int d = 0; d < ND - 1; ++d) {
-            const int nd = prm.n[d + 1];
-            while (kk[sl][d] >= nd) {
-              kk[sl][d] -= nd;
-              kk[sl][d + 1] += 1;
-            }
+            dmma884(g0[mt], g1[mt], A[mt][ks], bf);
+            if constexpr (JAC) dmma884(h0[mt], h1[mt], Ad[mt][ks], bf);
           }
         }
-        const double* tb = sb + (size_t)t * EC * U;
 #pragma unroll
-        for (int e = 0; e < EC; ++e) {
-          const double* u = tb + e * U;
-          const double2 c0 = *reinterpret_cast<const double2*>(u + 2 * c);
-          double g0[MT], g1[MT];
-          double h0[JAC ? MT : 1], h1[JAC ? MT : 1];
+        for (int mt = 0; mt < MT; ++mt) {
+#if defined(FC_VARIANT) && FC_VARIANT == 1  // experiment: no FP64 work between the DMMA chains
+          acc[mt][e] = __longlong_as_double(__double_as_longlong(acc[mt][e]) ^ __double_as_longlong(g0[mt]) ^
+                                            __double_as_longlong(g1[mt]) ^ __double_as_longlong(W.w[mt][0]));
+#else
+          acc[mt][e] = fma(g0[mt], W.w[mt][0], acc[mt][e]);
+          acc[mt][e] = fma(g1[mt], W.w[mt][1], acc[mt][e]);
+#endif
+          if constexpr (JAC) {
+            accJ[mt][e][0] = fma(h0[mt], W.w[mt][0], accJ[mt][e][0]);
+            accJ[mt][e][0] = fma(h1[mt], W.w[mt][1], accJ[mt][e][0]);
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            g0[mt] = c0.x;  // k1 = 0 term: T_0 = 1
-            g1[mt] = c0.y;
-            if constexpr (JAC) h0[mt] = h1[mt] = 0.0;
-          }
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const double bf = u[8 + ks * 32 + lane];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              dmma884(g0[mt], g1[mt], A[mt][ks], bf);
-              if constexpr (JAC) dmma884(h0[mt], h1[mt], Ad[mt][ks], bf);
-            }
-          }
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            acc[mt][e] = fma(g0[mt], w[mt][0], acc[mt][e]);
-            acc[mt][e] = fma(g1[mt], w[mt][1], acc[mt][e]);
-            if constexpr (JAC) {
-              accJ[mt][e][0] = fma(h0[mt], w[mt][0], accJ[mt][e][0]);
-              accJ[mt][e][0] = fma(h1[mt], w[mt][1], accJ[mt][e][0]);
-#pragma unroll
-              for (int d = 1; d < N; ++d) {
-                accJ[mt][e][d] = fma(g0[mt], wd[mt][0][d], accJ[mt][e][d]);
-                accJ[mt][e][d] = fma(g1[mt], wd[mt][1][d], accJ[mt][e][d]);
-              }
+            for (int d = 1; d < N; ++d) {
+              accJ[mt][e][d] = fma(g0[mt], W.wd[mt][0][d], accJ[mt][e][d]);
+              accJ[mt][e][d] = fma(g1[mt], W.wd[mt][1][d], accJ[mt][e][d]);
             }
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[b]);
+      W = Wn;
+      rec = rec_next;
+      // ---- release the stage after its last tile; the last warp out refills the buffer
+      if (last_in_stage) {
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          if (atomicAdd(&released[b], 1u) == (unsigned)ncw - 1u) {
+            released[b] = 0;
+            if (v + ns < total_visits) {
+#ifdef FC_PROFILE
+              const long long t0 = clock64();
+#endif
+              fence_proxy_async();
+              issue(v + ns);
+#ifdef FC_PROFILE
+              prof_issue += clock64() - t0;
+#endif
+            }
+          }
+        }
+        ++v;
+        b = nb;
+        ph = nph;
+        tin = 0;
+        const int left = prm.ntiles - (tile + 1);
+        nt = left < prm.tilesPerStage ? left : prm.tilesPerStage;
+      } else {
+        ++tin;
+      }
     }
 
     // ---- quad reduction and store ----
@@ -349,6 +411,15 @@ __global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_cons
           }
         }
       }
+#ifdef FC_PROFILE
+    if (lane == 0 && blockIdx.x == 0 && pass + gridDim.x >= npass) {
+      long long* q = prm.prof + warp * 4;
+      q[0] = clock64() - prof_t0;
+      q[1] = prof_wait;
+      q[2] = prof_slow;
+      q[3] = prof_issue;
+    }
+#endif
     if (c == 0) {
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
@@ -365,6 +436,54 @@ __global__ void __launch_bounds__(JAC ? 256 : 512) dmma_kernel(const __grid_cons
           }
         }
     }
+  }
+}
+
+// Julia layout -> tile-record stream of one component group (see eval_dmma.cuh).
+struct FragDims {
+  int nd;                 // weighted dims (ndim - 1)
+  int n[kMaxNdim];        // n2..nN
+  int toff[kMaxNdim];     // offset of each dim's table inside a weight-table row
+};
+template <int DUMMY>
+__global__ void __launch_bounds__(256) relayout_frag_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                                            long long total, int E, int e0, int ec, int n1, int M,
+                                                            int KS, const FragDims fd) {
+  const int U = KS * 32 + 8;
+  const int TR = kDmmaMeta + ec * U;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long tile = g / TR;
+    const int w = (int)(g - tile * TR);
+    if (w < kDmmaMeta) {
+      // two int32 per double slot: meta[d*8 + col]
+      int v2[2];
+      for (int h = 0; h < 2; ++h) {
+        const int i = 2 * w + h, d = i >> 3, col = i & 7;
+        int val = 0;
+        if (d < fd.nd) {
+          long long m = tile * 8 + col;
+          if (m >= M) m = M - 1;  // padding column: its coefficients are zero, any valid entry will do
+          for (int q = 0; q < d; ++q) m /= fd.n[q];
+          val = fd.toff[d] + (int)(d == fd.nd - 1 ? m : m % fd.n[d]);
+        }
+        v2[h] = val;
+      }
+      reinterpret_cast<int2*>(dst)[g] = make_int2(v2[0], v2[1]);
+      continue;
+    }
+    const int e = (w - kDmmaMeta) / U, u = (w - kDmmaMeta) % U;
+    int k1;
+    long long m;
+    if (u < 8) {
+      k1 = 0;
+      m = tile * 8 + u;
+    } else {
+      const int l = (u - 8) & 31, ks = (u - 8) >> 5;
+      k1 = 1 + 4 * ks + (l & 3);
+      m = tile * 8 + (l >> 2);
+    }
+    dst[g] = (k1 < n1 && m < M) ? src[(e0 + e) + (long long)E * (k1 + (long long)n1 * m)] : 0.0;
   }
 }
 
