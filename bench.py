@@ -176,6 +176,175 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured: MEASURED_PEAKS.json hbm_gbs (torch copy, read+write)"
+    except Exception:
+        return 6400.0, "fallback: B200_PROFILING.md measured-copy figure"
+
+
+def cpu_fit_rate(n, howmany, dt):
+    """The reference's fit on the host cores: FFTW.r2r(REDFT00) stand-in = scipy/pocketfft dct(type=1) with all
+    workers (libfftw3 is not in this image) + the normalisation passes of interp.jl:49-54.  Returns (fits/s, threads)."""
+    import scipy.fft as sf
+    rng = np.random.default_rng(8)
+    vals = rng.uniform(-1, 1, (howmany, n)).astype(dt)
+    th = os.cpu_count() or 1
+    best = 0.0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        c = sf.dct(vals, type=1, axis=1, workers=th)
+        c /= 2 * (n - 1)
+        c[:, 1:n - 1] *= 2
+        best = max(best, howmany / (time.perf_counter() - t0))
+    return best, th
+
+
+def run_fit(args):
+    """configs[4]: batches of independent 1-D order-64 fits (chebcoefs, interp.jl:39-57) — the HBM-bound leg.
+    A step = one batched DCT-I fit of `--howmany` lines per GPU; fits are sharded per GPU (no collective)."""
+    n = 65
+    dt = np.float64 if args.dtype == "f64" else np.float32
+    rs = np.dtype(dt).itemsize
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        hm = min(args.howmany, 200_000)
+        r = 0.0
+        for _ in range(max(1, args.steps)):
+            rr, th = cpu_fit_rate(n, hm, dt)
+            r = max(r, rr)
+        print(json.dumps({"impl": "reference", "metric": "1-D order-64 DCT-I fits/sec", "value": r, "unit": "fits/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                          "config": {"workload": f"configs[4]: {hm} independent 1-D order-64 fits per step"},
+                          "cpu_baseline": {"value": r, "unit": "fits/s", "cores": th, "kind": "port",
+                                           "sample": f"{hm} fits, scipy/pocketfft dct(type=1, workers={th}) + normalisation"},
+                          "e2e": {"value": r, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    from fastcheb import _capi
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _capi.lib()
+    M = int(args.howmany)
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    bytes_per_fit = 2 * rs * n
+    # rotate over enough buffer pairs that consecutive steps never find their lines in the 126 MB L2
+    nbuf = max(2, int(np.ceil(300e6 / (M * bytes_per_fit))) + 1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(8 + rank)
+    vals = [torch.rand((M, n), dtype=tdt, device=dev, generator=g) * 2 - 1 for _ in range(nbuf)]
+    outs = [torch.empty((M, n), dtype=tdt, device=dev) for _ in range(nbuf)]
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    dims = _capi.i64_array((n,))
+    code = _capi.F64 if dt == np.float64 else _capi.F32
+
+    def launch(i):
+        # device-resident, asynchronous: enqueue only (the finite-check flag is read back by the synchronous API)
+        rc = L.fastcheb_fit_async(1, dims, code, 0, 1, M, vals[i % nbuf].data_ptr(), outs[i % nbuf].data_ptr(), None, None,
+                                  local, sp)
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        launch(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l0 = L.fastcheb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        launch(i)
+    e1.record(stream)
+    barrier()
+    launches = L.fastcheb_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = M * world * args.steps / (ms_max * 1e-3)
+    kern_ms = ms / args.steps
+    peak, peak_src = hbm_peak_gbs()
+    achieved = M * bytes_per_fit / (kern_ms * 1e-3) / 1e9
+
+    # parity spot check against the oracle on the first lines (checker only)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cheb_oracle as orc
+    got = outs[0][:64].cpu().numpy().astype(np.float64)
+    want = np.stack([orc.chebcoefs(v, 1) for v in vals[0][:64].cpu().numpy().astype(np.float64)])
+    err = float(np.abs(got - want).max() / np.abs(want).max())
+
+    e2e = None
+    if not args.no_e2e:
+        Me = min(M, 1 << 20)
+        hv = torch.empty((Me, n), dtype=tdt).pin_memory()
+        hv.copy_(vals[0][:Me].cpu())
+        hc = torch.empty((Me, n), dtype=tdt).pin_memory()
+        hm = torch.empty(Me, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            rc = L.fastcheb_fit(1, dims, code, 0, 1, Me, hv.data_ptr(), hc.data_ptr(), hm.data_ptr(), _capi.MEM_HOST, local, None)
+            if rc != 0:
+                raise RuntimeError(_capi.last_error())
+            return float(hc[0, 0])
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        nst = max(3, min(args.steps, 10))
+        for _ in range(nst):
+            e2e_step()
+        dtw = time.perf_counter() - t0
+        tt = torch.tensor([dtw], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": Me * world * nst / float(tt.item()), "unit": "fits/s", "h2d_bytes_per_step": Me * n * rs,
+               "d2h_bytes_per_step": Me * n * rs + Me * 8, "fits_per_step_per_gpu": Me,
+               "timer": "host wall clock around the synchronous C-ABI call (finite check + per-fit max|c| included)"}
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu:
+            r, th = cpu_fit_rate(n, min(M, 200_000), dt)
+            cpu = {"value": r, "unit": "fits/s", "cores": th, "kind": "port",
+                   "sample": f"{min(M, 200_000)} fits, best of 3, scipy/pocketfft dct(type=1, workers={th}) + normalisation "
+                             "passes (stand-in for the reference's FFTW.r2r REDFT00; libfftw3 is not in this image)"}
+        print(json.dumps({
+            "metric": "1-D order-64 DCT-I fits/sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"configs[4]: {M} independent 1-D order-64 fits per GPU per step (chebcoefs)",
+                       "l2": f"{nbuf} rotating input/output buffer pairs of {M * bytes_per_fit / 1e6:.0f} MB: no step finds its lines in L2",
+                       "parallelism": f"fits sharded over {world} GPU(s), no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "bytes_per_fit": bytes_per_fit, "kernel_ms": kern_ms, "peak_source": peak_src},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "max_rel_err_vs_oracle": err}))
+    if distributed:
+        dist.destroy_process_group()
+
+
 def workload_name(mode):
     what = "value c.(ys)" if mode == "val" else "value + chebjacobian"
     return f"configs[2]: 3-D order (32,32,32) SVector{{3}} Float64 ChebPoly, {what}, uniform random points"
@@ -194,7 +363,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--workload", default="eval3d", choices=["eval3d", "fit1d"],
+                    help="eval3d = the headline (configs[2]); fit1d = configs[4] batched DCT-I fits (HBM-bound leg)")
+    ap.add_argument("--howmany", type=int, default=1 << 20, help="fit1d: fits per GPU per step")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="fit1d: element type")
     args = ap.parse_args()
+    if args.workload == "fit1d":
+        return run_fit(args)
     if args.warmup < 3:
         args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -224,12 +399,13 @@ def main():
     N, E = 3, K
 
     # ---- the polynomial: rank 0 owns the coefficients, NCCL broadcasts them (north_star: eval sharding)
-    ct = torch.empty(DIMS + (K,), dtype=torch.float64, device=dev)
-    if rank == 0:
-        ct.copy_(torch.from_numpy(coefficients()))
     if distributed:
-        dist.broadcast(ct, src=0)
-    poly = fastcheb.ChebPoly(ct.cpu().numpy(), LB, UB, device=local)
+        from fastcheb import sharded
+        carr, lb_, ub_ = sharded.broadcast_coefficients(coefficients() if rank == 0 else None, LB if rank == 0 else None,
+                                                        UB if rank == 0 else None, src=0)
+    else:
+        carr, lb_, ub_ = coefficients(), LB, UB
+    poly = fastcheb.ChebPoly(carr, lb_, ub_, device=local)
     poly.set_algo({"auto": fastcheb.ALGO_AUTO, "clenshaw": fastcheb.ALGO_CLENSHAW, "dmma": fastcheb.ALGO_DMMA}[args.algo])
     h = poly._handle(np.float64)
     algo_used = {1: "clenshaw", 2: "dmma"}[poly.get_algo(jac)]

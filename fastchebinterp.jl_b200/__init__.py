@@ -224,7 +224,9 @@ class ChebPoly:
             rc = L.fastcheb_eval(h, pts.ctypes.data, npts, out.ctypes.data, _capi.MEM_HOST, None)
         if rc == _capi.EDOMAIN:
             bad = _capi.error_index()
-            raise ArgumentError(f"{pts[bad]} not in domain {self.lb} to {self.ub}")  # eval.jl:64
+            err = ArgumentError(f"{pts[bad]} not in domain {self.lb} to {self.ub}")  # eval.jl:64
+            err.index = bad  # 0-based index of the first offending point (sharded.py needs it)
+            raise err
         _check(rc, "fastcheb_eval: ")
         cdt = np.complex64 if rdt == np.float32 else np.complex128
         v = out.view(cdt) if cplx else out
@@ -262,7 +264,9 @@ class ChebPoly:
             rc = L.fastcheb_eval(h, pts.data_ptr(), npts, out.data_ptr(), _capi.MEM_DEVICE, stream)
         if rc == _capi.EDOMAIN:
             bad = _capi.error_index()
-            raise ArgumentError(f"{pts[bad].tolist()} not in domain {self.lb} to {self.ub}")
+            err = ArgumentError(f"{pts[bad].tolist()} not in domain {self.lb} to {self.ub}")
+            err.index = bad
+            raise err
         _check(rc, "fastcheb_eval: ")
         v = torch.view_as_complex(out.reshape(npts, -1, 2)) if cplx else out
         v = v.reshape(npts) if K is None else v.reshape(npts, K)
@@ -325,9 +329,10 @@ def _bounds(lb, ub):
     return lbv, ubv
 
 
-def chebcoefs(vals, ndim: int | None = None, device: int = 0, howmany: int | None = None):
+def chebcoefs(vals, ndim: int | None = None, device: int = 0, howmany: int | None = None, return_maxabs: bool = False):
     """chebcoefs(vals) — interp.jl:39-71 (no droptol).  `howmany`: vals has a leading batch axis of independent
-    fits (the reference's way to spell this is a loop)."""
+    fits (the reference's way to spell this is a loop).  return_maxabs: also return max_k infnorm(C_k) of every
+    fit (interp.jl:74-78), the quantity droptol scales its tolerance by."""
     vals = _float_vals(vals)
     batched = howmany is not None
     body = vals[0] if batched else vals
@@ -338,19 +343,30 @@ def chebcoefs(vals, ndim: int | None = None, device: int = 0, howmany: int | Non
     dims = body.shape[:ndim]
     rdt = _real_dtype(vals.dtype)
     if batched:
-        flat = np.concatenate([_to_julia_flat(v, ndim) for v in vals])
         nfit = vals.shape[0]
+        if ndim == 1:  # (howmany, n[, K]) C-contiguous is already the Julia order of back-to-back 1-D fits
+            flat = np.ascontiguousarray(vals).reshape(-1)
+            flat = flat.view(rdt) if cplx else flat
+        else:
+            flat = np.concatenate([_to_julia_flat(v, ndim) for v in vals])
     else:
         flat = _to_julia_flat(vals, ndim)
         nfit = 1
     out = np.empty_like(flat)
+    mx = np.zeros(nfit, dtype=np.float64) if return_maxabs else None
     rc = _capi.lib().fastcheb_fit(ndim, _capi.i64_array(dims), _dtype_code(rdt), int(cplx), K or 1, nfit,
-                                  flat.ctypes.data, out.ctypes.data, None, _capi.MEM_HOST, device, None)
+                                  flat.ctypes.data, out.ctypes.data, mx.ctypes.data if return_maxabs else None,
+                                  _capi.MEM_HOST, device, None)
     _check(rc, "fastcheb_fit: ")
     if batched:
-        per = out.size // nfit
-        return np.stack([_from_julia_flat(out[i * per:(i + 1) * per], dims, K, cplx) for i in range(nfit)])
-    return _from_julia_flat(out, dims, K, cplx)
+        if ndim == 1:
+            res = (out.view(vals.dtype) if cplx else out).reshape(vals.shape)
+        else:
+            per = out.size // nfit
+            res = np.stack([_from_julia_flat(out[i * per:(i + 1) * per], dims, K, cplx) for i in range(nfit)])
+    else:
+        res = _from_julia_flat(out, dims, K, cplx)
+    return (res, mx) if return_maxabs else res
 
 
 def droptol(coefs, tol: float, ndim: int | None = None, device: int = 0):

@@ -17,6 +17,8 @@ using namespace fastcheb;
 
 namespace {
 
+constexpr long long kFitDmmaMinLines = 256;  // below this a batch is latency-bound: generic kernel
+
 std::mutex g_tab_mu;
 std::map<std::pair<int, int>, double2*> g_ctab;  // (device, n) -> cos(pi r/(n-1)) as (hi, lo), r in [0, 2(n-1))
 
@@ -70,11 +72,6 @@ int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int
       FC_CUDA(cudaMemcpyAsync(coefs, vals, (size_t)total * sizeof(R), cudaMemcpyDeviceToDevice, st));
     return FASTCHEB_OK;
   }
-  // the bandwidth-bound path: batched 1-D transforms of short lines on the FP64 tensor cores
-  if (ndim == 1 && fit_dmma_applicable((int)dims[0], E, howmany))
-    return fit_dmma_1d(di, dev, (int)dims[0], (long long)E * howmany, sizeof(R) == 8 ? FASTCHEB_F64 : FASTCHEB_F32, vals,
-                       coefs, E, st);
-
   // ping-pong so that the last pass lands in `coefs`; `vals` is never written
   R* tmp = nullptr;
   R* tmp2 = nullptr;
@@ -127,17 +124,34 @@ int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, i
   const int E = K * (cplx ? 2 : 1);
   long long elems = 1;
   for (int d = 0; d < ndim; ++d) elems *= dims[d];
-  const long long total = elems * E * howmany;
-  if (bad_dev) {
-    nonfinite_kernel<R><<<grid_for(total, 256, di->sms), 256, 0, st>>>(vals, total, bad_dev);  // interp.jl:40
+  const int dt = sizeof(R) == 8 ? FASTCHEB_F64 : FASTCHEB_F32;
+  if (maxabs_dev) FC_CUDA(cudaMemsetAsync(maxabs_dev, 0, (size_t)howmany * sizeof(double), st));
+  // The bandwidth-bound path: many short 1-D lines go through the tensor-core transform, which also
+  // does the finite check and (for real coefficients) the per-fit maximum on the way.
+  long long done = 0;
+  if (ndim == 1 && (long long)E * howmany >= kFitDmmaMinLines)
+    FC_TRY(fit_dmma_1d(di, dev, (int)dims[0], E, howmany, dt, vals, coefs, bad_dev, (maxabs_dev && !cplx) ? maxabs_dev : nullptr,
+                       st, &done));
+  if (done > 0 && maxabs_dev && cplx) {
+    const long long nchunks = ((elems + 1023) / 1024) * done;
+    coef_max_kernel<R><<<grid_for(nchunks * 32, 256, di->sms), 256, 0, st>>>(coefs, elems, done, K, cplx, maxabs_dev);
     FC_CUDA(cudaGetLastError());
     note_launch();
   }
-  FC_TRY(fit_passes<R>(di, dev, ndim, dims, E, howmany, vals, coefs, st));
+  const long long rest = howmany - done;
+  if (rest == 0) return FASTCHEB_OK;
+  const long long off = done * elems * E;  // reals handled by the tensor-core path
+  const R* rvals = vals + off;
+  R* rcoefs = coefs + off;
+  if (bad_dev) {
+    nonfinite_kernel<R><<<grid_for(rest * elems * E, 256, di->sms), 256, 0, st>>>(rvals, rest * elems * E, off, bad_dev);  // interp.jl:40
+    FC_CUDA(cudaGetLastError());
+    note_launch();
+  }
+  FC_TRY(fit_passes<R>(di, dev, ndim, dims, E, rest, rvals, rcoefs, st));
   if (maxabs_dev) {
-    FC_CUDA(cudaMemsetAsync(maxabs_dev, 0, (size_t)howmany * sizeof(double), st));
-    const long long nchunks = ((elems + 1023) / 1024) * howmany;
-    coef_max_kernel<R><<<grid_for(nchunks * 32, 256, di->sms), 256, 0, st>>>(coefs, elems, howmany, K, cplx, maxabs_dev);
+    const long long nchunks = ((elems + 1023) / 1024) * rest;
+    coef_max_kernel<R><<<grid_for(nchunks * 32, 256, di->sms), 256, 0, st>>>(rcoefs, elems, rest, K, cplx, maxabs_dev + done);
     FC_CUDA(cudaGetLastError());
     note_launch();
   }
@@ -277,6 +291,23 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
     return fail(FASTCHEB_ENONFINITE, "non-finite interpolant value at flat index %lld (interp.jl:40)", *fs.host);
   }
   return FASTCHEB_OK;
+}
+
+int fastcheb_fit_async(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp, int64_t howmany,
+                       const void* vals_dev, void* coefs_dev, double* maxabs_dev, int64_t* status_dev, int device,
+                       void* stream) {
+  FC_TRY(check_args(ndim, dims, dtype, ncomp, FASTCHEB_MEM_DEVICE));
+  if (howmany < 0) return fail(FASTCHEB_EINVAL, "howmany < 0");
+  if (howmany == 0) return FASTCHEB_OK;
+  if (!vals_dev || !coefs_dev) return fail(FASTCHEB_EINVAL, "null buffer");
+  const DeviceInfo* di = device_info(device);
+  if (!di) return FASTCHEB_ECUDA;
+  DeviceGuard dg(device);
+  if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (status_dev) FC_CUDA(set_flag_async((long long*)status_dev, kNoBad, st));
+  return fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, howmany, vals_dev, coefs_dev, maxabs_dev,
+                    (long long*)status_dev, st);
 }
 
 int fastcheb_droptol_shape(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp, const void* coefs,

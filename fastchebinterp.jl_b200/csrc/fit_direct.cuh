@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) dct1_direct_kernel(const R* __restrict__ 
 
 // first non-finite real of `vals` (interp.jl:40): atomicMin of the flat index
 template <typename R>
-__global__ void __launch_bounds__(256) nonfinite_kernel(const R* __restrict__ v, long long total,
+__global__ void __launch_bounds__(256) nonfinite_kernel(const R* __restrict__ v, long long total, long long base,
                                                         long long* __restrict__ bad) {
   long long first = 0x7fffffffffffffffLL;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) nonfinite_kernel(const R* __restrict__ v,
     const double a = (double)v[g];
     if (!(fabs(a) <= 1.79769313486231570815e308) && g < first) first = g;
   }
-  if (first != 0x7fffffffffffffffLL) atomicMin(bad, first);
+  if (first != 0x7fffffffffffffffLL) atomicMin(bad, first + base);
 }
 
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {

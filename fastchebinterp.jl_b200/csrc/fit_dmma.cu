@@ -1,7 +1,215 @@
+// Host side of the tensor-core DCT-I path: folded transform matrices in A-fragment order, launch.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "fit_dmma.cuh"
 #include "fit_dmma_launch.h"
+
 namespace fastcheb {
-bool fit_dmma_applicable(int, int, long long) { return false; }
-int fit_dmma_1d(const DeviceInfo*, int, int, long long, int, const void*, void*, int, cudaStream_t) {
-  return fail(FASTCHEB_EUNSUPPORTED, "fit_dmma not built");
+namespace {
+
+struct AFrag {
+  double* d = nullptr;
+  int kse = 0, kso = 0, mte = 0, mto = 0;
+};
+std::mutex g_mu;
+std::map<std::pair<int, int>, AFrag> g_afrag;  // (device, n)
+
+// cos(pi r / N) with r reduced exactly, so that the symmetries of the transform hold bit for bit
+long double cospi_ratio(long long r, int N) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  r %= 2LL * N;
+  if (r > N) r = 2LL * N - r;
+  if (2 * r == N) return 0.0L;
+  if (2 * r < N) return cosl(pi * (long double)r / (long double)N);
+  return -cosl(pi * (long double)(N - r) / (long double)N);
 }
+
+int get_afrag(int dev, int n, AFrag* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_pair(dev, n);
+  auto it = g_afrag.find(key);
+  if (it != g_afrag.end()) {
+    *out = it->second;
+    return FASTCHEB_OK;
+  }
+  const int N = n - 1;
+  const int Le = N / 2 + 1, Lo = (N + 1) / 2, Je = N / 2 + 1, Jo = (N + 1) / 2;
+  AFrag a;
+  a.mte = (Le + 7) / 8;
+  a.mto = (Lo + 7) / 8;
+  a.kse = (Je + 3) / 4;
+  a.kso = (Jo + 3) / 4;
+  std::vector<double> h((size_t)(a.mte * a.kse + a.mto * a.kso) * 32, 0.0);
+  // entry of the folded matrix for output k, folded input j (interp.jl:44 REDFT00, :49-54 scaling)
+  auto entry = [&](int k, int j) -> double {
+    const long double s = (k == 0 || k == N) ? 0.5L / (long double)N : 1.0L / (long double)N;
+    // REDFT00 weights: x_0 and x_N count once, the interior twice.  The kernel folds a_j = x_j + x_{N-j} for every
+    // j, so j = 0 carries weight 1 and the self-paired middle element (2j == N, a = 2 x_{N/2}) weight 2/2 = 1.
+    const long double w = (j == 0 || 2 * j == N) ? 1.0L : 2.0L;
+    return (double)(s * w * cospi_ratio((long long)j * k, N));
+  };
+  for (int mt = 0; mt < a.mte; ++mt)
+    for (int ks = 0; ks < a.kse; ++ks)
+      for (int l = 0; l < 32; ++l) {
+        const int row = 8 * mt + l / 4, j = 4 * ks + l % 4;
+        if (row < Le && j < Je) h[(size_t)(mt * a.kse + ks) * 32 + l] = entry(2 * row, j);
+      }
+  const size_t ooff = (size_t)a.mte * a.kse * 32;
+  for (int mt = 0; mt < a.mto; ++mt)
+    for (int ks = 0; ks < a.kso; ++ks)
+      for (int l = 0; l < 32; ++l) {
+        const int row = 8 * mt + l / 4, j = 4 * ks + l % 4;
+        if (row < Lo && j < Jo) h[ooff + (size_t)(mt * a.kso + ks) * 32 + l] = entry(2 * row + 1, j);
+      }
+  FC_CUDA(cudaMalloc(&a.d, h.size() * sizeof(double)));
+  FC_CUDA(cudaMemcpy(a.d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  g_afrag[key] = a;
+  *out = a;
+  return FASTCHEB_OK;
+}
+
+template <typename R, int KSE, int KSO, int NT, bool E1>
+cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
+  auto kern = fit_dmma_kernel<R, KSE, KSO, NT, E1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (bps) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
+  kern<<<grid, threads, smem, st>>>(prm);
+  note_launch();
+  return cudaGetLastError();
+}
+
+template <typename R, int NT>
+cudaError_t dispatch(int kse, int kso, bool e1, const FitDmmaParams& prm, int grid, int threads, size_t smem,
+                     cudaStream_t st, int* bps) {
+#define FC_CASE(A, B)                                                                       \
+  if (kse == A && kso == B)                                                                 \
+    return e1 ? launch<R, A, B, NT, true>(prm, grid, threads, smem, st, bps)                \
+              : launch<R, A, B, NT, false>(prm, grid, threads, smem, st, bps)
+  // kso is kse or kse - 1 (Jo = Je or Je - 1); n <= 65 gives kse <= 9
+  FC_CASE(1, 1);
+  FC_CASE(2, 1);
+  FC_CASE(2, 2);
+  FC_CASE(3, 2);
+  FC_CASE(3, 3);
+  FC_CASE(4, 3);
+  FC_CASE(4, 4);
+  FC_CASE(5, 4);
+  FC_CASE(5, 5);
+  FC_CASE(6, 5);
+  FC_CASE(6, 6);
+  FC_CASE(7, 6);
+  FC_CASE(7, 7);
+  FC_CASE(8, 7);
+  FC_CASE(8, 8);
+  FC_CASE(9, 8);
+#undef FC_CASE
+  return cudaErrorInvalidValue;
+}
+
+// maxabs[f] = max_e linemax[(f / U) * lines + (f % U) * E + e]
+__global__ void __launch_bounds__(256) fit_max_kernel(const double* __restrict__ linemax, double* __restrict__ fitmax,
+                                                      long long nfits, int U, int E, int lines) {
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < nfits; f += (long long)gridDim.x * blockDim.x) {
+    const double* p = linemax + (f / U) * lines + (f % U) * E;
+    double m = 0.0;
+    for (int e = 0; e < E; ++e) m = fmax(m, p[e]);
+    fitmax[f] = m;
+  }
+}
+
+}  // namespace
+
+int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, int dtype, const void* vals,
+                void* coefs, long long* bad_dev, double* fit_max_dev, cudaStream_t st, long long* done) {
+  *done = 0;
+  if (n < 2 || n > 65 || E < 1) return FASTCHEB_OK;
+  // launch shape: FASTCHEB_FIT_TUNE="warps,slots,nt" overrides the defaults (benchmark sweeps)
+  int warps = 16, S = 3, NT = 1;  // measured best on B200 (profiles/r01_fit_sweep.txt)
+  if (const char* t = getenv("FASTCHEB_FIT_TUNE")) {
+    int a = 0, b = 0, c = 0;
+    if (sscanf(t, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && a <= (c == 1 ? 24 : 8) && b >= 2 && a * b <= 64 && (c == 1 || c == 2)) {
+      warps = a;
+      S = b;
+      NT = c;
+    }
+  }
+  const int rs = (int)real_size(dtype);
+  const int lines = 8 * NT;
+  if (E > lines) return FASTCHEB_OK;
+  int U = lines / E;
+  while (U >= 1 && ((long long)U * n * E * rs) % 16 != 0) --U;
+  if (U < 1) return FASTCHEB_OK;
+  if (((uintptr_t)vals | (uintptr_t)coefs) & 15) return FASTCHEB_OK;
+  const long long nunits = howmany / U;
+  if (nunits < 1) return FASTCHEB_OK;
+  AFrag af;
+  FC_TRY(get_afrag(dev, n, &af));
+  FitDmmaParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.src = vals;
+  prm.dst = coefs;
+  prm.afrag = af.d;
+  prm.nunits = nunits;
+  prm.bad = bad_dev;
+  prm.n = n;
+  prm.E = E;
+  prm.U = U;
+  prm.LU = U * E;
+  prm.unitBytes = U * n * E * rs;
+  prm.slotBytes = (prm.unitBytes + 127) / 128 * 128;
+  const size_t afragBytes = ((size_t)(af.mte * af.kse + af.mto * af.kso) * 32 * 8 + 127) / 128 * 128;
+  const size_t budget = di->smem_optin - 1024;
+  while (512 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > 2) --S;
+  while (512 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && warps > 1) --warps;
+  prm.nslots = S;
+  const size_t smem = 512 + afragBytes + (size_t)warps * S * prm.slotBytes;
+  if (smem > budget) return FASTCHEB_OK;
+  double* linemax = nullptr;
+  if (fit_max_dev) {
+    linemax = (double*)ws_acquire(dev, (size_t)nunits * lines * sizeof(double));
+    if (!linemax) return fail(FASTCHEB_ENOMEM, "fit line-maximum scratch");
+  }
+  prm.linemax = linemax;
+  const int threads = warps * 32;
+  int bps = 0;
+  cudaError_t e;
+  auto go = [&](int* bp, int grid) {
+    if (dtype == FASTCHEB_F64)
+      return NT == 2 ? dispatch<double, 2>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp)
+                     : dispatch<double, 1>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp);
+    return NT == 2 ? dispatch<float, 2>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp)
+                   : dispatch<float, 1>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp);
+  };
+  e = go(&bps, 0);
+  if (e != cudaSuccess || bps < 1) {
+    cudaGetLastError();
+    if (linemax) ws_release(dev, linemax);
+    return FASTCHEB_OK;  // not covered: the caller falls back to the generic kernel
+  }
+  const long long want = (nunits + warps - 1) / warps;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)di->sms * bps));
+  e = go(nullptr, grid);
+  int rc = FASTCHEB_OK;
+  if (e != cudaSuccess) rc = fail(FASTCHEB_ECUDA, "DCT-I tensor-core kernel launch failed: %s", cudaGetErrorString(e));
+  if (rc == FASTCHEB_OK && fit_max_dev) {
+    const long long nf = nunits * U;
+    const int g2 = (int)std::max<long long>(1, std::min<long long>((nf + 255) / 256, (long long)di->sms * 8));
+    fit_max_kernel<<<g2, 256, 0, st>>>(linemax, fit_max_dev, nf, U, E, lines);
+    note_launch();
+    if (cudaGetLastError() != cudaSuccess) rc = fail(FASTCHEB_ECUDA, "fit maximum kernel launch failed");
+  }
+  if (linemax) {
+    cudaStreamSynchronize(st);  // scratch returns to the cache only once the work is done
+    ws_release(dev, linemax);
+  }
+  if (rc == FASTCHEB_OK) *done = nunits * U;
+  return rc;
+}
+
 }  // namespace fastcheb

@@ -3,9 +3,12 @@
 #include "host_util.h"
 
 namespace fastcheb {
-// true when `nlines` lines of length n are better served by the folded-matrix DMMA transform
-bool fit_dmma_applicable(int n, int E, long long howmany);
-// lines are the (howmany x E) real sequences of length n stored with element stride E inside each fit
-int fit_dmma_1d(const DeviceInfo* di, int dev, int n, long long nlines, int dtype, const void* vals, void* coefs, int E,
-                cudaStream_t st);
+// Transform as many whole units of fits as the tensor-core path can take: `howmany` fits of n elements
+// of E inline reals each, stored back to back (so line (f, e) has element stride E).  *done receives the
+// number of leading fits handled (0 when the shape is not covered or the buffers are not 16-byte
+// aligned); the caller sends the remaining fits through the generic kernel.  Non-finite inputs are
+// reported through bad_dev (flat real index, atomicMin).  fit_max_dev (optional, real coefficients
+// only): max |c| of every handled fit.
+int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, int dtype, const void* vals,
+                void* coefs, long long* bad_dev, double* fit_max_dev, cudaStream_t st, long long* done);
 }  // namespace fastcheb

@@ -1,0 +1,240 @@
+"""Multi-GPU host logic: one process per GPU over torch.distributed (NCCL on the B200 box, gloo in CPU tests).
+
+SURVEY.md §8e.  Only the two naturally sharding paths are partitioned:
+
+* batched evaluation — points are independent: the coefficients (<= 1.4 MB in every config) are broadcast from
+  rank `src` over NVLink once, every rank builds its own device handle and evaluates a contiguous block of the
+  points; results stay sharded or are gathered on `dst`.  No collective inside the kernel; the out-of-domain
+  status is an all-reduce(MIN) of the first offending *global* index (the reference's broadcast aborts on the
+  first throw, eval.jl:64).
+* batches of independent fits — fit i goes to rank block(i); no collective.  A single N-d fit stays on one GPU.
+
+The compute itself is always `fastcheb.ChebPoly` / `fastcheb.chebcoefs` on the rank's GPU.  `make_poly` /
+`fit_fn` exist so the partition/collective logic can be tested on CPU (gloo) with the oracle as the stand-in.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NO_BAD = np.iinfo(np.int64).max
+
+
+def block_range(n: int, world: int, rank: int):
+    """Contiguous block partition of range(n): the first n % world ranks get one extra item."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised (launch with torchrun, one process per GPU)")
+    return dist
+
+
+def _comm_device(dist):
+    import torch
+
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def broadcast_coefficients(coefs, lb, ub, src: int = 0):
+    """Rank `src` passes numpy arrays, the others None; every rank returns (coefs, lb, ub) as numpy arrays.
+    Shapes/dtypes travel as a small object broadcast, the coefficient payload as one tensor broadcast."""
+    import torch
+
+    dist = _dist()
+    rank = dist.get_rank()
+    meta = [None]
+    if rank == src:
+        coefs = np.ascontiguousarray(coefs)
+        meta = [(coefs.shape, coefs.dtype.str, np.asarray(lb).tolist(), np.asarray(ub).tolist(),
+                 np.asarray(lb).dtype.str, np.asarray(ub).dtype.str)]
+    dist.broadcast_object_list(meta, src=src)
+    shape, dts, lbl, ubl, lbd, ubd = meta[0]
+    dt = np.dtype(dts)
+    dev = _comm_device(dist)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    if rank == src:
+        payload = torch.from_numpy(coefs.reshape(-1).view(np.uint8).copy()).to(dev)
+    else:
+        payload = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dist.broadcast(payload, src=src)
+    out = payload.cpu().numpy().view(dt).reshape(shape)
+    return out, np.asarray(lbl, dtype=np.dtype(lbd)), np.asarray(ubl, dtype=np.dtype(ubd))
+
+
+class ShardedChebPoly:
+    """A ChebPoly replicated on every rank's GPU; evaluation is sharded over points."""
+
+    def __init__(self, coefs=None, lb=None, ub=None, src: int = 0, device: int | None = None, make_poly=None):
+        dist = _dist()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        c, l, u = broadcast_coefficients(coefs, lb, ub, src)
+        if make_poly is None:
+            import torch
+
+            from . import ChebPoly
+
+            dev = torch.cuda.current_device() if device is None else device
+            make_poly = lambda c_, l_, u_: ChebPoly(c_, l_, u_, device=dev)  # noqa: E731
+        self.poly = make_poly(c, l, u)
+        self.ndim = len(l)
+
+    # -- partition helpers
+    def my_range(self, npts: int):
+        return block_range(npts, self.world, self.rank)
+
+    def scatter_points(self, pts, npts: int | None = None, src: int = 0):
+        """Rank `src` holds all points (npts x N array); every rank receives its block (numpy)."""
+        import torch
+
+        dist = _dist()
+        dev = _comm_device(dist)
+        meta = [None]
+        if self.rank == src:
+            pts = np.ascontiguousarray(pts)
+            meta = [(pts.shape[0], pts.dtype.str)]
+        dist.broadcast_object_list(meta, src=src)
+        n, dts = meta[0]
+        dt = np.dtype(dts)
+        lo, hi = block_range(n, self.world, self.rank)
+        mine = torch.empty((hi - lo, self.ndim), dtype=torch.from_numpy(np.empty(0, dt)).dtype, device=dev)
+        if self.rank == src:
+            chunks = []
+            for r in range(self.world):
+                a, b = block_range(n, self.world, r)
+                chunks.append(torch.from_numpy(pts[a:b].reshape(b - a, self.ndim)).to(dev))
+            # ragged blocks: point-to-point sends (scatter needs equal sizes)
+            reqs = [dist.isend(chunks[r], dst=r) for r in range(self.world) if r != src]
+            mine.copy_(chunks[src])
+            for q in reqs:
+                q.wait()
+        else:
+            dist.recv(mine, src=src)
+        return mine.cpu().numpy() if dev.type == "cpu" else mine
+
+    # -- sharded evaluation
+    def eval_local(self, pts_local, jac: bool = False):
+        """Evaluate this rank's block.  Raises the reference's ArgumentError on *every* rank if any rank saw an
+        out-of-domain point (first offending global index, as the serial broadcast would report)."""
+        import torch
+
+        dist = _dist()
+        err, local_bad = None, NO_BAD
+        res = None
+        try:
+            if jac:
+                from . import chebjacobian
+
+                res = chebjacobian(self.poly, pts_local) if hasattr(self.poly, "_eval") else self.poly.jacobian(pts_local)
+            else:
+                res = self.poly(pts_local)
+        except ValueError as e:  # ArgumentError (domain) is a ValueError in both the product and the oracle
+            err = e
+            local_bad = getattr(e, "index", 0)
+        dev = _comm_device(dist)
+        n_local = len(pts_local)
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        counts[self.rank] = n_local
+        dist.all_reduce(counts)
+        offset = int(counts[: self.rank].sum().item())
+        flag = torch.tensor([NO_BAD if err is None else offset + int(local_bad)], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        first = int(flag.item())
+        if first != NO_BAD:
+            from . import ArgumentError
+
+            raise ArgumentError(f"point {first} not in domain {self.poly.lb} to {self.poly.ub}") from err
+        return res
+
+    def eval_gather(self, pts_local, dst: int = 0):
+        """c.(ys) with ys block-partitioned over the ranks; the values are gathered on `dst` in global point order
+        (None on the other ranks)."""
+        import torch
+
+        dist = _dist()
+        v = self.eval_local(pts_local)
+        dev = _comm_device(dist)
+        t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+        cplx = t.is_complex()
+        if cplx:
+            t = torch.view_as_real(t.contiguous())
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        counts[self.rank] = t.shape[0]
+        dist.all_reduce(counts)
+        counts = [int(x) for x in counts.tolist()]
+        out = None
+        if self.rank == dst:
+            bufs = [torch.empty((counts[r],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for r in range(self.world)]
+            reqs = [dist.irecv(bufs[r], src=r) for r in range(self.world) if r != dst]
+            bufs[dst].copy_(t)
+            for q in reqs:
+                q.wait()
+            out = torch.cat(bufs, dim=0)
+            if cplx:
+                out = torch.view_as_complex(out)
+        else:
+            dist.send(t.contiguous(), dst=dst)
+        return out
+
+
+def sharded_fit(vals_all, ndim: int = 1, src: int = 0, fit_fn=None):
+    """`howmany` independent fits (leading batch axis) sharded per rank: rank `src` holds `vals_all`
+    (howmany x n1.. [x K]); every rank fits its block on its GPU; rank `src` returns all coefficients in order.
+    No collective inside the transform; a single fit is never split."""
+    import torch
+
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = _comm_device(dist)
+    meta = [None]
+    if rank == src:
+        vals_all = np.ascontiguousarray(vals_all)
+        meta = [(vals_all.shape, vals_all.dtype.str)]
+    dist.broadcast_object_list(meta, src=src)
+    shape, dts = meta[0]
+    dt = np.dtype(dts)
+    howmany = shape[0]
+    lo, hi = block_range(howmany, world, rank)
+    tdt = torch.from_numpy(np.empty(0, dt)).dtype
+    mine = torch.empty((hi - lo,) + tuple(shape[1:]), dtype=tdt, device=dev)
+    if rank == src:
+        reqs = []
+        for r in range(world):
+            a, b = block_range(howmany, world, r)
+            chunk = torch.from_numpy(vals_all[a:b]).to(dev)
+            if r == src:
+                mine.copy_(chunk)
+            else:
+                reqs.append(dist.isend(chunk, dst=r))
+        for q in reqs:
+            q.wait()
+    else:
+        dist.recv(mine, src=src)
+    if fit_fn is None:
+        from . import chebcoefs
+
+        fit_fn = lambda v: chebcoefs(v, ndim=ndim, howmany=v.shape[0], device=torch.cuda.current_device())  # noqa: E731
+    local = np.asarray(fit_fn(mine.cpu().numpy())) if hi > lo else np.empty((0,) + tuple(shape[1:]), dt)
+    lt = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    if rank == src:
+        outs = []
+        reqs = []
+        for r in range(world):
+            a, b = block_range(howmany, world, r)
+            buf = torch.empty((b - a,) + tuple(shape[1:]), dtype=tdt, device=dev)
+            outs.append(buf)
+            if r == src:
+                buf.copy_(lt)
+            else:
+                reqs.append(dist.irecv(buf, src=r))
+        for q in reqs:
+            q.wait()
+        return torch.cat(outs, dim=0).cpu().numpy()
+    dist.send(lt, dst=src)
+    return None

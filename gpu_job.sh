@@ -1,11 +1,16 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -15
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_val.json 2> gpurun_out/bench_val.err; tail -3 gpurun_out/bench_val.err; cat gpurun_out/bench_val.json
-python bench.py --steps 5 --warmup 3 --mode jac --no-cpu > gpurun_out/bench_jac.json 2> gpurun_out/bench_jac.err; tail -3 gpurun_out/bench_jac.err; cat gpurun_out/bench_jac.json
-CMD="python bench.py --steps 2 --warmup 3 --batch 1048576 --no-cpu --no-e2e"
-$CMD > gpurun_out/ncu_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv $CMD > gpurun_out/ncu_l.log 2>&1
-$CMD > gpurun_out/ncu_plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:dmma_kernel -s 3 -c 1 -o gpurun_out/r01_dmma_val_v4 -f $CMD > gpurun_out/ncu_f.log 2>&1
-tail -n 2 gpurun_out/ncu_f.log
+timeout 900 python -m pytest tests/test_gpu_fit.py -m gpu -q -x 2>&1 | tail -5
+for tune in 16,3,1 16,4,1 24,2,1 20,2,1 12,4,1 8,3,2; do
+  FASTCHEB_FIT_TUNE=$tune python bench.py --workload fit1d --steps 20 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()); continue
+    print('TUNE $tune', d['value'], d['roofline']['achieved'], d['roofline']['frac'], d['max_rel_err_vs_oracle'])
+"
+done
+python bench.py --workload fit1d --steps 20 --warmup 3 --no-cpu --no-e2e --dtype f32 | cut -c1-900
+CMD="python bench.py --workload fit1d --steps 2 --warmup 3 --no-cpu --no-e2e"
+ncu --set full --clock-control none --import-source on -k regex:fit_dmma_kernel -s 3 -c 1 -o gpurun_out/r01_fit_dmma_v3 -f $CMD > gpurun_out/ncu_fit2.log 2>&1
+tail -n 2 gpurun_out/ncu_fit2.log

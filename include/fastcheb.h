@@ -136,6 +136,13 @@ int fastcheb_eval_jac_async(const fastcheb_poly* p, const void* pts_dev, int64_t
 int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp, int64_t howmany,
                  const void* vals, void* coefs, double* maxabs, int mem, int device, void* stream);
 
+/* Asynchronous device-memory variant: enqueue on `stream` and return.  maxabs_dev (device, `howmany`
+ * doubles) and status_dev (device, one int64: flat index of the first non-finite real of `vals`, or
+ * INT64_MAX) may each be NULL; the caller reads them after synchronising. */
+int fastcheb_fit_async(int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp, int64_t howmany,
+                       const void* vals_dev, void* coefs_dev, double* maxabs_dev, int64_t* status_dev, int device,
+                       void* stream);
+
 /* droptol(coefs, tol) shape decision (interp.jl:77-93) for one coefficient array: writes the trimmed
  * sizes to newdims (== dims when nothing is dropped, including tol == 0).  The caller copies the
  * leading block (interp.jl:92). */

@@ -1,0 +1,190 @@
+# src/cuda.jl — the Julia side of the B200 hot path: thin `ccall` bindings to libfastcheb_cuda
+# (C ABI: include/fastcheb.h).  Drop this file into FastChebInterp.jl's src/ and add
+# `include("cuda.jl")` after `include("eval.jl")` in src/FastChebInterp.jl (line 62).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain.  Every entry point
+# used here is exercised through the identical C ABI from Python (fastchebinterp.jl_b200/_capi.py,
+# tests/test_gpu_*.py).  Memory layouts are those of SURVEY.md Appendix A and were chosen so that no
+# copy or permutation is needed on the Julia side: `Array{SVector{K,T},N}` coefficients,
+# `Vector{SVector{N,T}}` points, `Vector{Tuple{V,SMatrix{K,N}}}` Jacobian results are passed as is.
+#
+# Public API (unchanged names; methods are added for the device-resident type):
+#   cu = CuChebPoly(c::ChebPoly)            upload (FastChebInterp.jl:37-41 -> fastcheb_create)
+#   cu(ys::AbstractVector{<:SVector{N}})    == c.(ys)                      (eval.jl:63-70)
+#   cu.(ys)                                 same, through Base.broadcasted
+#   chebjacobian(cu, ys), chebgradient(cu, ys)                             (eval.jl:147-177)
+#   chebinterp(vals, lb, ub; tol, device=0) -> CuChebPoly                  (interp.jl:95-99,140-141)
+#   chebcoefs_batched(vals::Matrix)         10^5 independent 1-D fits      (interp.jl:39-57 per column)
+#   ChebPoly(cu)                            download
+
+using StaticArrays
+
+const libfastcheb = get(ENV, "FASTCHEB_CUDA_LIB", "libfastcheb_cuda")
+
+const FASTCHEB_F32, FASTCHEB_F64 = Cint(0), Cint(1)
+const FASTCHEB_MEM_HOST, FASTCHEB_MEM_DEVICE = Cint(0), Cint(1)
+const FASTCHEB_OK, FASTCHEB_EDOMAIN, FASTCHEB_ENONFINITE, FASTCHEB_EDIMMISMATCH, FASTCHEB_EINVAL =
+    Cint(0), Cint(1), Cint(2), Cint(3), Cint(4)
+
+_dtype(::Type{Float32}) = FASTCHEB_F32
+_dtype(::Type{Float64}) = FASTCHEB_F64
+# (real scalar type, is_complex, components) of a coefficient element type
+_elt(::Type{T}) where {T<:Union{Float32,Float64}} = (T, false, 1)
+_elt(::Type{Complex{T}}) where {T<:Union{Float32,Float64}} = (T, true, 1)
+_elt(::Type{SVector{K,T}}) where {K,T} = (_elt(T)[1], _elt(T)[2], K)
+
+function _last_error()
+    buf = Vector{UInt8}(undef, 512)
+    n = ccall((:fastcheb_last_error, libfastcheb), Csize_t, (Ptr{UInt8}, Csize_t), buf, length(buf))
+    String(buf[1:min(n, length(buf) - 1)])
+end
+function _error_index()
+    idx = Ref{Int64}(0)
+    ccall((:fastcheb_error_index, libfastcheb), Cint, (Ref{Int64},), idx)
+    idx[]
+end
+
+# status code -> the exception the reference throws at the same place
+function _check(rc::Cint, c=nothing, xs=nothing)
+    rc == FASTCHEB_OK && return
+    if rc == FASTCHEB_EDOMAIN                      # eval.jl:64, :148
+        i = _error_index() + 1
+        x = xs === nothing ? "point $i" : xs[i]
+        throw(ArgumentError("$x not in domain" * (c === nothing ? "" : " $(c.lb) to $(c.ub)")))
+    elseif rc == FASTCHEB_ENONFINITE               # interp.jl:40
+        throw(DomainError(_error_index() + 1, "non-finite interpolant value"))
+    elseif rc == FASTCHEB_EDIMMISMATCH             # eval.jl:170
+        throw(DimensionMismatch(_last_error()))
+    elseif rc == FASTCHEB_EINVAL
+        throw(ArgumentError(_last_error()))
+    else
+        error("libfastcheb_cuda: ", _last_error(), " (status $rc)")
+    end
+end
+
+"""
+Device-resident `ChebPoly{N,T,Td}`: an opaque handle owned by libfastcheb_cuda (coefficients in the
+kernels' own layouts, `lb`, `ub`, sizes).  Immutable after creation; safe to evaluate from several
+tasks at once.
+"""
+mutable struct CuChebPoly{N,T,Td<:Real} <: Function
+    handle::Ptr{Cvoid}
+    lb::SVector{N,Td}
+    ub::SVector{N,Td}
+    dims::NTuple{N,Int}
+    device::Int
+    function CuChebPoly{N,T,Td}(h, lb, ub, dims, device) where {N,T,Td}
+        c = new{N,T,Td}(h, lb, ub, dims, device)
+        finalizer(c) do x   # fastcheb_destroy is finalizer-safe: no exceptions, any thread
+            ccall((:fastcheb_destroy, libfastcheb), Cint, (Ptr{Cvoid},), x.handle)
+        end
+        c
+    end
+end
+Base.ndims(::CuChebPoly{N}) where {N} = N
+
+function CuChebPoly(c::ChebPoly{N,T,Td}; device::Integer=0) where {N,T,Td}
+    R, cplx, K = _elt(T)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    dims = collect(Int64, size(c.coefs))
+    lb, ub = collect(Float64, c.lb), collect(Float64, c.ub)   # Td may be Int (runtests.jl:170)
+    GC.@preserve c begin
+        rc = ccall((:fastcheb_create, libfastcheb), Cint,
+                   (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Cint),
+                   h, N, dims, _dtype(R), cplx, K, pointer(c.coefs), FASTCHEB_MEM_HOST, lb, ub, device)
+    end
+    _check(rc)
+    CuChebPoly{N,T,Td}(h[], c.lb, c.ub, size(c.coefs), device)
+end
+
+function ChebPoly(cu::CuChebPoly{N,T,Td}) where {N,T,Td}
+    coefs = Array{T,N}(undef, cu.dims)
+    _check(ccall((:fastcheb_get_coefs, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), cu.handle, coefs, FASTCHEB_MEM_HOST))
+    ChebPoly{N,T,Td}(coefs, cu.lb, cu.ub)
+end
+
+# result element types — the same promotion as eval.jl:25 (`muladd(x, c, c)`)
+_valtype(::Type{T}, ::Type{Tx}) where {T,Tx} = typeof(zero(T) * zero(Tx))
+
+# ---- c.(ys): batched evaluation (eval.jl:63-70 per point)
+function (cu::CuChebPoly{N,T})(ys::AbstractVector{SVector{N,R}}) where {N,T,R<:Union{Float32,Float64}}
+    _elt(T)[1] === R || throw(ArgumentError("promote points and coefficients to one precision first"))
+    ys = ys isa Vector ? ys : collect(ys)
+    out = Vector{T}(undef, length(ys))
+    GC.@preserve ys out begin
+        rc = ccall((:fastcheb_eval, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                   cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
+    end
+    _check(rc, cu, ys)
+    out
+end
+(cu::CuChebPoly{1,T})(xs::AbstractVector{R}) where {T,R<:Union{Float32,Float64}} =
+    cu(reinterpret(SVector{1,R}, xs isa Vector ? xs : collect(xs)))
+(cu::CuChebPoly{N})(x::SVector{N,<:Real}) where {N} = cu([float.(x)])[1]       # single point: still the device path
+(cu::CuChebPoly{1})(x::Real) = cu(SVector(float(x)))
+# `cu.(ys)` lowers to broadcasted(cu, ys): route whole batches to one library call
+Base.Broadcast.broadcasted(cu::CuChebPoly{N}, ys::AbstractVector{<:SVector{N}}) where {N} = cu(ys)
+Base.Broadcast.broadcasted(cu::CuChebPoly{1}, xs::AbstractVector{<:Real}) = cu(xs)
+
+# ---- chebjacobian / chebgradient over batches (eval.jl:147-177).  The library writes Julia's own
+# Vector{Tuple{V,SMatrix{K,N}}} element layout (fastcheb_eval_jac_tuple), so the result needs no repacking.
+function chebjacobian(cu::CuChebPoly{N,T}, ys::AbstractVector{SVector{N,R}}) where {N,T,R<:Union{Float32,Float64}}
+    _, _, K = _elt(T)
+    S = T <: SVector ? eltype(T) : T
+    out = Vector{Tuple{T,SMatrix{K,N,S,K * N}}}(undef, length(ys))
+    ys = ys isa Vector ? ys : collect(ys)
+    GC.@preserve ys out begin
+        rc = ccall((:fastcheb_eval_jac_tuple, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                   cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
+    end
+    _check(rc, cu, ys)
+    out
+end
+function chebgradient(cu::CuChebPoly{N,T}, ys::AbstractVector{SVector{N,R}}) where {N,T,R<:Union{Float32,Float64}}
+    T <: SVector && length(T) != 1 && throw(DimensionMismatch())                 # eval.jl:170
+    out = Vector{Tuple{T,SVector{N,T}}}(undef, length(ys))                       # same bytes as (v, 1xN SMatrix)
+    ys = ys isa Vector ? ys : collect(ys)
+    GC.@preserve ys out begin
+        rc = ccall((:fastcheb_eval_jac_tuple, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                   cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
+    end
+    _check(rc, cu, ys)
+    out
+end
+chebjacobian(cu::CuChebPoly{N}, x::SVector{N,<:Real}) where {N} = chebjacobian(cu, [float.(x)])[1]
+chebgradient(cu::CuChebPoly{N}, x::SVector{N,<:Real}) where {N} = chebgradient(cu, [float.(x)])[1]
+chebgradient(cu::CuChebPoly{1}, x::Real) = (r = chebgradient(cu, SVector(float(x))); (r[1], r[2][1]))  # eval.jl:174-177
+
+# ---- chebinterp(vals, lb, ub; tol) on the device (interp.jl:95-99, 140-141): fit + droptol + handle
+function cuchebinterp(vals::AbstractArray{T,N}, lb, ub; tol::Real=-1, device::Integer=0) where {T,N}
+    R, cplx, K = _elt(T)
+    Td = promote_type(eltype(lb), eltype(ub))
+    vals = vals isa Array ? vals : collect(vals)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    dims = collect(Int64, size(vals))
+    GC.@preserve vals begin
+        rc = ccall((:fastcheb_interp, libfastcheb), Cint,
+                   (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Cdouble, Cint, Ptr{Cvoid}),
+                   h, N, dims, _dtype(R), cplx, K, pointer(vals), FASTCHEB_MEM_HOST,
+                   collect(Float64, lb), collect(Float64, ub), tol, device, C_NULL)    # tol < 0: eps(R), interp.jl:102
+    end
+    _check(rc)
+    nd = Vector{Int64}(undef, N)
+    _check(ccall((:fastcheb_dims, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Int64}), h[], nd))
+    CuChebPoly{N,T,Td}(h[], SVector{N,Td}(lb), SVector{N,Td}(ub), Tuple(nd), device)
+end
+
+# ---- many independent 1-D fits at once (BASELINE configs[4]): column j of `vals` is one line
+function chebcoefs_batched(vals::Matrix{R}; device::Integer=0) where {R<:Union{Float32,Float64}}
+    n, howmany = size(vals)
+    coefs = similar(vals)
+    maxabs = Vector{Float64}(undef, howmany)
+    GC.@preserve vals coefs maxabs begin
+        rc = ccall((:fastcheb_fit, libfastcheb), Cint,
+                   (Cint, Ptr{Int64}, Cint, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Cvoid}),
+                   1, Int64[n], _dtype(R), 0, 1, howmany, pointer(vals), pointer(coefs), pointer(maxabs),
+                   FASTCHEB_MEM_HOST, device, C_NULL)
+    end
+    _check(rc)
+    coefs, maxabs      # droptol per column: trailing |c| < tol*maxabs[j] (interp.jl:77-93)
+end

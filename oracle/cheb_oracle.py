@@ -219,7 +219,9 @@ class OracleChebPoly:
             rc = getattr(lib(), f"oracle_eval_{sfx}")(N, _dims_ptr(dims), E, flat.ctypes.data, lb.ctypes.data, ub.ctypes.data,
                                                       pts.ctypes.data, npts, out.ctypes.data, ctypes.byref(bad))
         if rc == 1:
-            raise ValueError(f"{pts[bad.value]} not in domain {self.lb} to {self.ub}")   # ArgumentError eval.jl:64
+            err = ValueError(f"{pts[bad.value]} not in domain {self.lb} to {self.ub}")   # ArgumentError eval.jl:64
+            err.index = int(bad.value)
+            raise err
         v = out.reshape(npts, E)
         if cplx:
             v = v.view(np.complex64 if rdt == np.float32 else np.complex128)

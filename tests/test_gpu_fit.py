@@ -80,3 +80,61 @@ def test_fit_then_eval_roundtrip(fc):
     c = fc.chebinterp(f, lb, ub, tol=0.0)
     got = c(np.clip(x.reshape(-1, 3), lb, ub))
     assert np.abs(got - f.reshape(-1, 2)).max() <= 1e-12
+
+
+def _oracle_batch(orc, vals, K):
+    return np.stack([orc.chebcoefs(np.asarray(v, dtype=np.complex128 if np.iscomplexobj(v) else np.float64), 1) for v in vals])
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 9, 17, 33, 40, 49, 64, 65])
+def test_batched_tensor_core_fit(fc, orc, n, dt):
+    """configs[4]: many independent short 1-D fits (fit_dmma.cuh) incl. a ragged tail that the generic
+    kernel finishes; scalar, K-vector and complex elements."""
+    rng = np.random.default_rng(100 + n)
+    for K, cplx, howmany in ((None, False, 531), (3, False, 203), (2, True, 150), (None, True, 300)):
+        shape = (howmany, n) + ((K,) if K else ())
+        vals = rng.uniform(-1, 1, shape)
+        if cplx:
+            vals = vals + 1j * rng.uniform(-1, 1, shape)
+            vals = vals.astype(np.complex128 if dt == np.float64 else np.complex64)
+        else:
+            vals = vals.astype(dt)
+        got, mx = fc.chebcoefs(vals, ndim=1, howmany=howmany, return_maxabs=True)
+        want = _oracle_batch(orc, vals, K)
+        assert got.shape == want.shape and got.dtype == vals.dtype
+        assert np.abs(got - want).max() <= tol_for(dt) * np.abs(want).max(), (K, cplx)
+        wmx = np.abs(got.reshape(howmany, -1)).max(axis=1)
+        assert np.allclose(mx, wmx, rtol=1e-6 if dt == np.float32 else 1e-14, atol=0)
+
+
+def test_batched_fit_nonfinite_index(fc):
+    vals = np.ones((4096, 65))
+    vals[1234, 17] = np.nan
+    vals[3000, 2] = np.inf
+    with pytest.raises(fc.DomainError) as ei:
+        fc.chebcoefs(vals, ndim=1, howmany=4096)
+    assert str(1234 * 65 + 17) in str(ei.value)          # first offending flat index (interp.jl:40)
+    vals = np.ones((4099, 65))                              # ... and in the ragged tail
+    vals[4098, 64] = np.nan
+    with pytest.raises(fc.DomainError) as ei:
+        fc.chebcoefs(vals, ndim=1, howmany=4099)
+    assert str(4098 * 65 + 64) in str(ei.value)
+
+
+def test_batched_fit_linearity_and_constants(fc):
+    """Size-independent properties at the full configs[4] size: DCT-I is linear; a constant line has the single
+    coefficient c0 = value; T_k sampled on the grid gives the unit vector e_k."""
+    rng = np.random.default_rng(7)
+    M, n = 100_000, 65
+    a, b = rng.uniform(-1, 1, (M, n)), rng.uniform(-1, 1, (M, n))
+    ca, cb, cab = (fc.chebcoefs(v, ndim=1, howmany=M) for v in (a, b, 2.0 * a - 0.5 * b))
+    assert np.abs(cab - (2.0 * ca - 0.5 * cb)).max() <= 1e-13 * np.abs(cab).max()
+    k = rng.integers(0, n, M)
+    j = np.arange(n)
+    grid = np.cos(np.pi * j / (n - 1))                      # interp.jl:6: index 0 is the upper bound
+    tk = np.cos(k[:, None] * np.arccos(grid)[None, :])
+    ck = fc.chebcoefs(tk, ndim=1, howmany=M)
+    want = np.zeros((M, n))
+    want[np.arange(M), k] = 1.0
+    assert np.abs(ck - want).max() <= 1e-13
