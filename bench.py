@@ -132,6 +132,7 @@ def cpu_reference_rate(mode: str, sample_pts: int, reps: int = 3):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     import cheb_oracle as orc
 
+    orc.set_num_threads()  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     poly = orc.OracleChebPoly(coefficients(), LB, UB)
     rng = np.random.default_rng(PTS_SEED)
     pts = rng.uniform(-1.0, 1.0, (sample_pts, 3))
@@ -190,7 +191,7 @@ def cpu_fit_rate(n, howmany, dt):
     import scipy.fft as sf
     rng = np.random.default_rng(8)
     vals = rng.uniform(-1, 1, (howmany, n)).astype(dt)
-    th = os.cpu_count() or 1
+    th = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     best = 0.0
     for _ in range(3):
         t0 = time.perf_counter()

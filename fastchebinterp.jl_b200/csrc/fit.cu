@@ -120,7 +120,7 @@ int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int
 
 template <typename R>
 int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int cplx, int K, int64_t howmany,
-                 const R* vals, R* coefs, double* maxabs_dev, long long* bad_dev, cudaStream_t st) {
+                 const R* vals, R* coefs, double* maxabs_dev, long long* bad_dev, long long idx_base, cudaStream_t st) {
   const int E = K * (cplx ? 2 : 1);
   long long elems = 1;
   for (int d = 0; d < ndim; ++d) elems *= dims[d];
@@ -130,7 +130,7 @@ int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, i
   // does the finite check and (for real coefficients) the per-fit maximum on the way.
   long long done = 0;
   if (ndim == 1 && (long long)E * howmany >= kFitDmmaMinLines)
-    FC_TRY(fit_dmma_1d(di, dev, (int)dims[0], E, howmany, dt, vals, coefs, bad_dev, (maxabs_dev && !cplx) ? maxabs_dev : nullptr,
+    FC_TRY(fit_dmma_1d(di, dev, (int)dims[0], E, howmany, dt, vals, coefs, bad_dev, idx_base, (maxabs_dev && !cplx) ? maxabs_dev : nullptr,
                        st, &done));
   if (done > 0 && maxabs_dev && cplx) {
     const long long nchunks = ((elems + 1023) / 1024) * done;
@@ -144,7 +144,7 @@ int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, i
   const R* rvals = vals + off;
   R* rcoefs = coefs + off;
   if (bad_dev) {
-    nonfinite_kernel<R><<<grid_for(rest * elems * E, 256, di->sms), 256, 0, st>>>(rvals, rest * elems * E, off, bad_dev);  // interp.jl:40
+    nonfinite_kernel<R><<<grid_for(rest * elems * E, 256, di->sms), 256, 0, st>>>(rvals, rest * elems * E, idx_base + off, bad_dev);  // interp.jl:40
     FC_CUDA(cudaGetLastError());
     note_launch();
   }
@@ -159,12 +159,13 @@ int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, i
 }
 
 int fit_device(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int dtype, int cplx, int K, int64_t howmany,
-               const void* vals, void* coefs, double* maxabs_dev, long long* bad_dev, cudaStream_t st) {
+               const void* vals, void* coefs, double* maxabs_dev, long long* bad_dev, cudaStream_t st,
+               long long idx_base = 0) {
   if (dtype == FASTCHEB_F64)
     return fit_device_t<double>(di, dev, ndim, dims, cplx, K, howmany, (const double*)vals, (double*)coefs, maxabs_dev,
-                                bad_dev, st);
+                                bad_dev, idx_base, st);
   return fit_device_t<float>(di, dev, ndim, dims, cplx, K, howmany, (const float*)vals, (float*)coefs, maxabs_dev,
-                             bad_dev, st);
+                             bad_dev, idx_base, st);
 }
 
 int check_args(int ndim, const int64_t* dims, int dtype, int ncomp, int mem) {
@@ -273,16 +274,65 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
   if (mem == FASTCHEB_MEM_DEVICE) {
     FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, howmany, vals, coefs, maxabs, fs.dev, st));
   } else {
-    HostStage in(device), out(device), mx(device);
-    in.d = ws_acquire(device, bytes);
-    out.d = ws_acquire(device, bytes);
-    if (maxabs) mx.d = ws_acquire(device, (size_t)howmany * sizeof(double));
-    if (!in.d || !out.d || (maxabs && !mx.d)) return fail(FASTCHEB_ENOMEM, "device staging of %zu bytes", bytes);
-    FC_CUDA(cudaMemcpyAsync(in.d, vals, bytes, cudaMemcpyHostToDevice, st));
-    FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, howmany, in.d, out.d, (double*)mx.d, fs.dev, st));
-    FC_CUDA(cudaMemcpyAsync(coefs, out.d, bytes, cudaMemcpyDeviceToHost, st));
-    if (maxabs) FC_CUDA(cudaMemcpyAsync(maxabs, mx.d, (size_t)howmany * sizeof(double), cudaMemcpyDeviceToHost, st));
-    FC_CUDA(cudaStreamSynchronize(st));
+    // Host buffers: the fits are independent, so a large batch is cut into chunks that flow through two
+    // internal streams — the D2H copy of chunk i overlaps the H2D copy and the transform of chunk i+1 (PCIe is
+    // full duplex).  A single fit is never split.
+    const size_t fit_bytes = (size_t)elems * E * rs;
+    int64_t chunk = howmany;
+    if (bytes > (size_t(64) << 20) && howmany >= 4)
+      chunk = std::max<int64_t>(1, std::min<int64_t>((howmany + 3) / 4, (int64_t)((size_t(128) << 20) / fit_bytes)));
+    const int nbuf = howmany > chunk ? 2 : 1;
+    FC_CUDA(cudaStreamSynchronize(st));  // the flag initialisation above is ordered before the internal streams
+    cudaStream_t ss[2] = {nullptr, nullptr};
+    void* dbuf[2] = {nullptr, nullptr};
+    const size_t cb = (size_t)chunk * fit_bytes, cb_al = (cb + 255) / 256 * 256;
+    const size_t mxb = maxabs ? (size_t)chunk * sizeof(double) : 0;
+    auto cleanup = [&]() {
+      for (int i = 0; i < 2; ++i) {
+        if (ss[i]) cudaStreamDestroy(ss[i]);
+        if (dbuf[i]) ws_release(device, dbuf[i]);
+      }
+    };
+    for (int i = 0; i < nbuf; ++i) {
+      if (nbuf == 1) {
+        ss[i] = nullptr;
+      } else if (cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) != cudaSuccess) {
+        cleanup();
+        return fail(FASTCHEB_ECUDA, "cudaStreamCreate failed");
+      }
+      dbuf[i] = ws_acquire(device, 2 * cb_al + mxb);
+      if (!dbuf[i]) {
+        cleanup();
+        return fail(FASTCHEB_ENOMEM, "device staging of %zu bytes", 2 * cb_al + mxb);
+      }
+    }
+    int rc = FASTCHEB_OK;
+    cudaError_t ce = cudaSuccess;
+    int64_t done = 0;
+    for (int it = 0; rc == FASTCHEB_OK && ce == cudaSuccess && done < howmany; ++it) {
+      const int b = it % nbuf;
+      cudaStream_t s2 = nbuf == 1 ? st : ss[b];
+      const int64_t m = std::min<int64_t>(chunk, howmany - done);
+      char* d_in = (char*)dbuf[b];
+      char* d_out = d_in + cb_al;
+      double* d_mx = maxabs ? (double*)(d_out + cb_al) : nullptr;
+      ce = cudaMemcpyAsync(d_in, (const char*)vals + (size_t)done * fit_bytes, (size_t)m * fit_bytes, cudaMemcpyHostToDevice, s2);
+      if (ce != cudaSuccess) break;
+      rc = fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, m, d_in, d_out, d_mx, fs.dev, s2,
+                      (long long)done * elems * E);
+      if (rc != FASTCHEB_OK) break;
+      ce = cudaMemcpyAsync((char*)coefs + (size_t)done * fit_bytes, d_out, (size_t)m * fit_bytes, cudaMemcpyDeviceToHost, s2);
+      if (ce == cudaSuccess && maxabs)
+        ce = cudaMemcpyAsync(maxabs + done, d_mx, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s2);
+      done += m;
+    }
+    for (int i = 0; i < nbuf; ++i) {
+      cudaError_t e2 = cudaStreamSynchronize(nbuf == 1 ? st : ss[i]);
+      if (ce == cudaSuccess) ce = e2;
+    }
+    cleanup();
+    if (rc != FASTCHEB_OK) return rc;
+    if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged fit failed: %s", cudaGetErrorString(ce));
   }
   FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
   FC_CUDA(cudaStreamSynchronize(st));

@@ -14,7 +14,8 @@ namespace {
 
 struct AFrag {
   double* d = nullptr;
-  int kse = 0, kso = 0, mte = 0, mto = 0;
+  int ko = 0, kb = 0, kc = 0;  // k-steps of parts O, B, C (fit_dmma.cuh); kc == 0: one fold only
+  size_t doubles = 0;
 };
 std::mutex g_mu;
 std::map<std::pair<int, int>, AFrag> g_afrag;  // (device, n)
@@ -37,35 +38,43 @@ int get_afrag(int dev, int n, AFrag* out) {
     *out = it->second;
     return FASTCHEB_OK;
   }
-  const int N = n - 1;
-  const int Le = N / 2 + 1, Lo = (N + 1) / 2, Je = N / 2 + 1, Jo = (N + 1) / 2;
+  const int N = n - 1, H = N / 2;
+  const bool two = N >= 4 && N % 4 == 0;  // the even half folds once more
+  // folded inputs (= outputs) of each part
+  const int Jo = (N + 1) / 2;
+  const int Jb = two ? H / 2 + 1 : N / 2 + 1;
+  const int Jc = two ? H / 2 : 0;
   AFrag a;
-  a.mte = (Le + 7) / 8;
-  a.mto = (Lo + 7) / 8;
-  a.kse = (Je + 3) / 4;
-  a.kso = (Jo + 3) / 4;
-  std::vector<double> h((size_t)(a.mte * a.kse + a.mto * a.kso) * 32, 0.0);
-  // entry of the folded matrix for output k, folded input j (interp.jl:44 REDFT00, :49-54 scaling)
-  auto entry = [&](int k, int j) -> double {
+  a.ko = (Jo + 3) / 4;
+  a.kb = (Jb + 3) / 4;
+  a.kc = (Jc + 3) / 4;
+  const int mo = (a.ko + 1) / 2, mb = (a.kb + 1) / 2, mc = (a.kc + 1) / 2;
+  a.doubles = (size_t)(mo * a.ko + mb * a.kb + mc * a.kc) * 32;
+  std::vector<double> h(a.doubles, 0.0);
+  // REDFT00 (interp.jl:44) with the scaling of interp.jl:49-54 folded in: output k, folded input j carrying REDFT00
+  // weight w (end points and self-paired middle elements count once, everything else twice)
+  auto entry = [&](int k, int j, bool once) -> double {
     const long double s = (k == 0 || k == N) ? 0.5L / (long double)N : 1.0L / (long double)N;
-    // REDFT00 weights: x_0 and x_N count once, the interior twice.  The kernel folds a_j = x_j + x_{N-j} for every
-    // j, so j = 0 carries weight 1 and the self-paired middle element (2j == N, a = 2 x_{N/2}) weight 2/2 = 1.
-    const long double w = (j == 0 || 2 * j == N) ? 1.0L : 2.0L;
-    return (double)(s * w * cospi_ratio((long long)j * k, N));
+    return (double)(s * (once ? 1.0L : 2.0L) * cospi_ratio((long long)j * k, N));
   };
-  for (int mt = 0; mt < a.mte; ++mt)
-    for (int ks = 0; ks < a.kse; ++ks)
-      for (int l = 0; l < 32; ++l) {
-        const int row = 8 * mt + l / 4, j = 4 * ks + l % 4;
-        if (row < Le && j < Je) h[(size_t)(mt * a.kse + ks) * 32 + l] = entry(2 * row, j);
-      }
-  const size_t ooff = (size_t)a.mte * a.kse * 32;
-  for (int mt = 0; mt < a.mto; ++mt)
-    for (int ks = 0; ks < a.kso; ++ks)
-      for (int l = 0; l < 32; ++l) {
-        const int row = 8 * mt + l / 4, j = 4 * ks + l % 4;
-        if (row < Lo && j < Jo) h[ooff + (size_t)(mt * a.kso + ks) * 32 + l] = entry(2 * row + 1, j);
-      }
+  auto fill = [&](size_t off, int K, int M, int J, int kstride, int koff, int selfpair) {
+    for (int mt = 0; mt < M; ++mt)
+      for (int ks = 0; ks < K; ++ks)
+        for (int l = 0; l < 32; ++l) {
+          const int row = 8 * mt + l / 4, j = 4 * ks + l % 4, k = kstride * row + koff;
+          if (row < J && j < J && k <= N) h[off + (size_t)(mt * K + ks) * 32 + l] = entry(k, j, j == 0 || j == selfpair);
+        }
+  };
+  size_t off = 0;
+  fill(off, a.ko, mo, Jo, 2, 1, -1);                                  // part O: k = 2l+1, b_j
+  off += (size_t)mo * a.ko * 32;
+  if (two) {
+    fill(off, a.kb, mb, Jb, 4, 0, H / 2);                               // part B: k = 4l, aa_j (self-paired at j = N/4)
+    off += (size_t)mb * a.kb * 32;
+    fill(off, a.kc, mc, Jc, 4, 2, -1);                                  // part C: k = 4l+2, ab_j
+  } else {
+    fill(off, a.kb, mb, Jb, 2, 0, N % 2 == 0 ? H : -1);                 // part B: k = 2l, a_j (self-paired at j = N/2)
+  }
   FC_CUDA(cudaMalloc(&a.d, h.size() * sizeof(double)));
   FC_CUDA(cudaMemcpy(a.d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
   g_afrag[key] = a;
@@ -73,9 +82,9 @@ int get_afrag(int dev, int n, AFrag* out) {
   return FASTCHEB_OK;
 }
 
-template <typename R, int KSE, int KSO, int NT, bool E1>
+template <typename R, int KO, int KB, int KC, int NT, bool E1>
 cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
-  auto kern = fit_dmma_kernel<R, KSE, KSO, NT, E1>;
+  auto kern = fit_dmma_kernel<R, KO, KB, KC, NT, E1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (bps) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
@@ -84,30 +93,43 @@ cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem,
   return cudaGetLastError();
 }
 
-template <typename R, int NT>
-cudaError_t dispatch(int kse, int kso, bool e1, const FitDmmaParams& prm, int grid, int threads, size_t smem,
+template <typename R>
+cudaError_t dispatch(int ko, int kb, int kc, bool e1, const FitDmmaParams& prm, int grid, int threads, size_t smem,
                      cudaStream_t st, int* bps) {
-#define FC_CASE(A, B)                                                                       \
-  if (kse == A && kso == B)                                                                 \
-    return e1 ? launch<R, A, B, NT, true>(prm, grid, threads, smem, st, bps)                \
-              : launch<R, A, B, NT, false>(prm, grid, threads, smem, st, bps)
-  // kso is kse or kse - 1 (Jo = Je or Je - 1); n <= 65 gives kse <= 9
-  FC_CASE(1, 1);
-  FC_CASE(2, 1);
-  FC_CASE(2, 2);
-  FC_CASE(3, 2);
-  FC_CASE(3, 3);
-  FC_CASE(4, 3);
-  FC_CASE(4, 4);
-  FC_CASE(5, 4);
-  FC_CASE(5, 5);
-  FC_CASE(6, 5);
-  FC_CASE(6, 6);
-  FC_CASE(7, 6);
-  FC_CASE(7, 7);
-  FC_CASE(8, 7);
-  FC_CASE(8, 8);
-  FC_CASE(9, 8);
+#define FC_CASE(A, B, C)                                                                   \
+  if (ko == A && kb == B && kc == C)                                                       \
+    return e1 ? launch<R, A, B, C, 1, true>(prm, grid, threads, smem, st, bps)             \
+              : launch<R, A, B, C, 1, false>(prm, grid, threads, smem, st, bps)
+  // one fold (4 does not divide n-1): kb is ko or ko + 1; n <= 65 gives kb <= 9
+  FC_CASE(1, 1, 0);
+  FC_CASE(1, 2, 0);
+  FC_CASE(2, 2, 0);
+  FC_CASE(2, 3, 0);
+  FC_CASE(3, 3, 0);
+  FC_CASE(3, 4, 0);
+  FC_CASE(4, 4, 0);
+  FC_CASE(4, 5, 0);
+  FC_CASE(5, 5, 0);
+  FC_CASE(5, 6, 0);
+  FC_CASE(6, 6, 0);
+  FC_CASE(6, 7, 0);
+  FC_CASE(7, 7, 0);
+  FC_CASE(7, 8, 0);
+  FC_CASE(8, 8, 0);
+  FC_CASE(8, 9, 0);
+  // two folds (n - 1 = 4t, t = 1..16): (ceil(t/2), ceil((t+1)/4), ceil(t/4))
+  FC_CASE(1, 1, 1);
+  FC_CASE(2, 1, 1);
+  FC_CASE(2, 2, 1);
+  FC_CASE(3, 2, 2);
+  FC_CASE(4, 2, 2);
+  FC_CASE(4, 3, 2);
+  FC_CASE(5, 3, 3);
+  FC_CASE(6, 3, 3);
+  FC_CASE(6, 4, 3);
+  FC_CASE(7, 4, 4);
+  FC_CASE(8, 4, 4);
+  FC_CASE(8, 5, 4);
 #undef FC_CASE
   return cudaErrorInvalidValue;
 }
@@ -126,14 +148,14 @@ __global__ void __launch_bounds__(256) fit_max_kernel(const double* __restrict__
 }  // namespace
 
 int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, int dtype, const void* vals,
-                void* coefs, long long* bad_dev, double* fit_max_dev, cudaStream_t st, long long* done) {
+                void* coefs, long long* bad_dev, long long idx_base, double* fit_max_dev, cudaStream_t st, long long* done) {
   *done = 0;
   if (n < 2 || n > 65 || E < 1) return FASTCHEB_OK;
   // launch shape: FASTCHEB_FIT_TUNE="warps,slots,nt" overrides the defaults (benchmark sweeps)
-  int warps = 16, S = 3, NT = 1;  // measured best on B200 (profiles/r01_fit_sweep.txt)
+  int warps = 16, S = 3, NT = 1;  // measured best on B200 (profiles/r01_fit_sweep.txt); NT = 2 is not instantiated
   if (const char* t = getenv("FASTCHEB_FIT_TUNE")) {
     int a = 0, b = 0, c = 0;
-    if (sscanf(t, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && a <= (c == 1 ? 24 : 8) && b >= 2 && a * b <= 64 && (c == 1 || c == 2)) {
+    if (sscanf(t, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && a <= 24 && b >= 2 && a * b <= 64 && c == 1) {
       warps = a;
       S = b;
       NT = c;
@@ -157,13 +179,14 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   prm.afrag = af.d;
   prm.nunits = nunits;
   prm.bad = bad_dev;
+  prm.idx_base = idx_base;
   prm.n = n;
   prm.E = E;
   prm.U = U;
   prm.LU = U * E;
   prm.unitBytes = U * n * E * rs;
   prm.slotBytes = (prm.unitBytes + 127) / 128 * 128;
-  const size_t afragBytes = ((size_t)(af.mte * af.kse + af.mto * af.kso) * 32 * 8 + 127) / 128 * 128;
+  const size_t afragBytes = (af.doubles * 8 + 127) / 128 * 128;
   const size_t budget = di->smem_optin - 1024;
   while (512 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > 2) --S;
   while (512 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && warps > 1) --warps;
@@ -180,11 +203,8 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   int bps = 0;
   cudaError_t e;
   auto go = [&](int* bp, int grid) {
-    if (dtype == FASTCHEB_F64)
-      return NT == 2 ? dispatch<double, 2>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp)
-                     : dispatch<double, 1>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp);
-    return NT == 2 ? dispatch<float, 2>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp)
-                   : dispatch<float, 1>(af.kse, af.kso, E == 1, prm, grid, threads, smem, st, bp);
+    if (dtype == FASTCHEB_F64) return dispatch<double>(af.ko, af.kb, af.kc, E == 1, prm, grid, threads, smem, st, bp);
+    return dispatch<float>(af.ko, af.kb, af.kc, E == 1, prm, grid, threads, smem, st, bp);
   };
   e = go(&bps, 0);
   if (e != cudaSuccess || bps < 1) {

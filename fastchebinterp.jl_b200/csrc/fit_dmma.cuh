@@ -9,8 +9,10 @@
 // Transform: with N = n-1 and REDFT00  X_k = x_0 + (-1)^k x_N + 2 sum_{0<j<N} x_j cos(pi j k/N),
 // cos(pi k (N-j)/N) = (-1)^k cos(pi k j/N), so the even-k outputs depend only on a_j = x_j + x_{N-j}
 // and the odd-k outputs only on b_j = x_j - x_{N-j} (j <= N/2): two half-size dense transforms
-//     C[2l]   = sum_j Me[l][j] a_j ,   C[2l+1] = sum_j Mo[l][j] b_j
-// whose matrices (built on the host from exactly reduced long-double cosines, normalisation folded in)
+//     C[2l]   = sum_j Me[l][j] a_j ,   C[2l+1] = sum_j Mo[l][j] b_j .
+// The even half is itself a REDFT00 of the sequence a_0..a_{N/2}, so when 4 | N it is folded once more
+// (k = 0 mod 4 from a_j + a_{N/2-j}, k = 2 mod 4 from a_j - a_{N/2-j}): 55 instead of 77 DMMAs per 8
+// lines at n = 65.  The matrices (built on the host from exactly reduced long-double cosines, normalisation folded in)
 // are the A operands of mma.sync m8n8k4 (SASS DMMA); 8 lines form the N extent of one MMA.  This works
 // for every n (no power-of-two requirement) and is a direct sum, so a coefficient carries ~sqrt(n) eps
 // of rounding, not an FFT's log n stages.
@@ -32,9 +34,10 @@ namespace fastcheb {
 struct FitDmmaParams {
   const void* src;
   void* dst;
-  const double* afrag;  // A fragments: even block [MTE][kse][32], then odd block [MTO][kso][32]
+  const double* afrag;  // A fragments of parts O, B, C back to back, each [m-tile][k-step][32 lanes]
   long long nunits;     // full units (the host sends the remainder through the generic kernel)
   long long* bad;       // first non-finite flat real index (atomicMin), may be null
+  long long idx_base;   // flat index of src[0] in the caller's array (chunked host calls)
   double* linemax;      // optional: max |c| of every line (nunits * 8*NT doubles, dead lines 0)
   int n, E;
   int U;   // fits per unit
@@ -56,17 +59,25 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// KSE / KSO: 4-wide k-steps of the even / odd half transform (compile-time, so the whole unit is one
-// straight-line block with immediate shared-memory offsets); E1: scalar elements (E == 1).
-template <typename R, int KSE, int KSO, int NT, bool E1>
+// Parts of the folded transform.  Every part is a small dense product on the tensor cores:
+//   part O  (KO k-steps): k = 2l+1          from b_j  = x_j - x_{N-j}
+//   part B  (KB k-steps): k = 2l            from a_j  = x_j + x_{N-j}                (one fold,  KC == 0)
+//                         k = 4l            from aa_j = a_j + a_{N/2-j}              (two folds, KC  > 0)
+//   part C  (KC k-steps): k = 4l+2          from ab_j = a_j - a_{N/2-j}              (two folds only)
+// K* are compile-time, so a unit is one straight-line block with immediate shared-memory offsets.
+// E1: scalar elements (E == 1).
+template <typename R, int KO, int KB, int KC, int NT, bool E1>
 __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __grid_constant__ FitDmmaParams prm) {
-  constexpr int MTE = (KSE + 1) / 2, MTO = (KSO + 1) / 2;  // 8-row m-tiles: ceil(4 KS / 8)
+  constexpr bool L2 = KC > 0;
+  constexpr int MO = (KO + 1) / 2, MB = (KB + 1) / 2, MC = (KC + 1) / 2;  // 8-row m-tiles: ceil(4 K / 8)
+  constexpr int KMAX = KO > KB ? KO : KB;
+  constexpr int SB = L2 ? 4 : 2, OB = 0;  // output stride / offset of part B; part C: stride 4, offset 2
   extern __shared__ __align__(128) unsigned char fastcheb_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int S = prm.nslots;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fastcheb_smem);  // [nwarps][S], <= 64 entries
-  constexpr int afragDoubles = (MTE * KSE + MTO * KSO) * 32;
+  constexpr int afragDoubles = (MO * KO + MB * KB + MC * KC) * 32;
   double* afrag = reinterpret_cast<double*>(fastcheb_smem + 512);
   unsigned char* ring = fastcheb_smem + 512 + ((afragDoubles * 8 + 127) / 128) * 128 + (size_t)warp * S * prm.slotBytes;
 
@@ -93,9 +104,8 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
   if (lane == 0)
     for (long long i = 0; i < S - 1 && i < my_units; ++i) issue(i);
 
-  const int n = prm.n, N = n - 1, E = E1 ? 1 : prm.E;
+  const int n = prm.n, N = n - 1, H = N / 2, E = E1 ? 1 : prm.E;
   const int c = lane & 3, q = lane >> 2;
-  const int Je = N / 2 + 1;  // folded inputs j = 0..Je-1 (the odd part's matrix has zero columns beyond (N+1)/2)
   // B-operand line of this lane in every line group, D-operand lines (columns 2c, 2c+1).  Dead lines (a unit
   // may hold fewer than 8*NT lines when E does not divide it) alias line 0: computed, never stored.
   auto line_of = [&](int t, int col) { return 2 * NT * (col & 3) + (col >> 2) + 2 * t; };
@@ -113,14 +123,17 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
     for (int h = 0; h < 2; ++h) {
       const int Ld = line_of(t, 2 * c + h);
       dlive[t][h] = Ld < prm.LU;
-      dbase[t][h] = line_base(dlive[t][h] ? Ld : 0) + 2 * q * E;  // element k = 2q of the line
+      dbase[t][h] = line_base(dlive[t][h] ? Ld : 0);
     }
   }
-  const double* aE = afrag + lane;
-  const double* aO = afrag + MTE * KSE * 32 + lane;
-  const int E4 = 4 * E, E16 = 16 * E;
-  // validity of the last m-tile's rows for this lane (all earlier m-tiles are full)
-  const bool lastE = 2 * (8 * (MTE - 1) + q) <= N, lastO = 2 * (8 * (MTO - 1) + q) + 1 <= N;
+  const double* aO = afrag + lane;
+  const double* aB = aO + MO * KO * 32;
+  const double* aC = aB + MB * KB * 32;
+  const int E4 = 4 * E;
+  // output element of row q in m-tile 0 of each part, and validity of the last m-tile's rows (earlier ones are full)
+  const int kO0 = 2 * q + 1, kB0 = SB * q + OB, kC0 = 4 * q + 2;
+  const bool lastO = 2 * (8 * (MO - 1) + q) + 1 <= N, lastB = SB * (8 * (MB - 1) + q) + OB <= N;
+  const bool lastC = L2 && 4 * (8 * (MC - 1) + q) + 2 <= N;
 
   for (long long i = 0; i < my_units; ++i) {
     const int s = (int)(i % S);
@@ -129,49 +142,74 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
     R* x = reinterpret_cast<R*>(ring + (size_t)s * prm.slotBytes);
     mbar_wait(&bars[warp * S + s], parity);
 
-    double accE[NT][MTE][2], accO[NT][MTO][2];
+    double accO[NT][MO][2], accB[NT][MB][2], accC[NT][L2 ? MC : 1][2];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
-      for (int mt = 0; mt < MTE; ++mt) accE[t][mt][0] = accE[t][mt][1] = 0.0;
+      for (int mt = 0; mt < MO; ++mt) accO[t][mt][0] = accO[t][mt][1] = 0.0;
 #pragma unroll
-      for (int mt = 0; mt < MTO; ++mt) accO[t][mt][0] = accO[t][mt][1] = 0.0;
+      for (int mt = 0; mt < MB; ++mt) accB[t][mt][0] = accB[t][mt][1] = 0.0;
+#pragma unroll
+      for (int mt = 0; mt < MC; ++mt) accC[t][mt][0] = accC[t][mt][1] = 0.0;
     }
-    // fold pointers: x_j walks up from j = c, x_{N-j} walks down; j is clamped to Je-1 in the last k-step
-    // (the matrix columns there are zero, the operand only has to be finite)
+    // fold pointers for j = 4 ks + c: x_j walks up and x_{N-j} down (and x_{H-j}, x_{H+j} for the second fold).
+    // Beyond j = N/2 (possible only in the last k-step) the matrix columns are zero; the operand only has to be
+    // finite, so those lanes read element 0.
     const R* p1[NT];
     const R* p2[NT];
+    const R* p3[NT];
+    const R* p4[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       p1[t] = x + bbase[t] + c * E;
       p2[t] = x + bbase[t] + (N - c) * E;
+      p3[t] = x + bbase[t] + (H - c) * E;
+      p4[t] = x + bbase[t] + (H + c) * E;
     }
 #pragma unroll
-    for (int ks = 0; ks < KSE; ++ks) {
-      const bool inr = ks < KSE - 1 || 4 * ks + c < Je;
-      double be[NT], bo[NT];
+    for (int ks = 0; ks < KMAX; ++ks) {
+      const bool inr = 4 * ks + c <= H;
+      double fo[NT], fb[NT], fc[NT];
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const R* q1 = inr ? p1[t] : x + bbase[t];
-        const R* q2 = inr ? p2[t] : x + bbase[t];
-        const double x1 = (double)*q1, x2 = (double)*q2;
-        be[t] = __dadd_rn(x1, x2);  // j == N/2 pairs x_{N/2} with itself: the matrix entry carries weight 1
-        bo[t] = __dsub_rn(x1, x2);
+        const R* z = x + bbase[t];
+        const double x1 = (double)*(inr ? p1[t] : z), x2 = (double)*(inr ? p2[t] : z);
+        fo[t] = __dsub_rn(x1, x2);
+        fb[t] = __dadd_rn(x1, x2);  // a self-paired element (2j == N) counts twice: its matrix entry carries weight 1
+        fc[t] = 0.0;
+        if (L2 && ks < KB) {
+          const double x3 = (double)*(inr ? p3[t] : z), x4 = (double)*(inr ? p4[t] : z);
+          const double a2 = __dadd_rn(x3, x4);
+          fc[t] = __dsub_rn(fb[t], a2);
+          fb[t] = __dadd_rn(fb[t], a2);
+        }
         p1[t] += E4;
         p2[t] -= E4;
+        p3[t] -= E4;
+        p4[t] += E4;
       }
+      if (ks < KB) {
 #pragma unroll
-      for (int mt = 0; mt < MTE; ++mt) {
-        const double a = aE[(mt * KSE + ks) * 32];
+        for (int mt = 0; mt < MB; ++mt) {
+          const double a = aB[(mt * KB + ks) * 32];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) dmma884(accE[t][mt][0], accE[t][mt][1], a, be[t]);
+          for (int t = 0; t < NT; ++t) dmma884(accB[t][mt][0], accB[t][mt][1], a, fb[t]);
+        }
       }
-      if (ks < KSO) {
+      if (ks < KC) {
 #pragma unroll
-        for (int mt = 0; mt < MTO; ++mt) {
-          const double a = aO[(mt * KSO + ks) * 32];
+        for (int mt = 0; mt < MC; ++mt) {
+          const double a = aC[(mt * KC + ks) * 32];
 #pragma unroll
-          for (int t = 0; t < NT; ++t) dmma884(accO[t][mt][0], accO[t][mt][1], a, bo[t]);
+          for (int t = 0; t < NT; ++t) dmma884(accC[t][mt][0], accC[t][mt][1], a, fc[t]);
+        }
+      }
+      if (ks < KO) {
+#pragma unroll
+        for (int mt = 0; mt < MO; ++mt) {
+          const double a = aO[(mt * KO + ks) * 32];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) dmma884(accO[t][mt][0], accO[t][mt][1], a, fo[t]);
         }
       }
     }
@@ -183,11 +221,11 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
       for (int t = 0; t < NT; ++t)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-          if (dlive[t][h] && !(fabs(accE[t][0][h]) <= 1.79769313486231570815e308)) {
-            const int lb0 = dbase[t][h];  // q == 0: the line's element 0
+          if (dlive[t][h] && !(fabs(accB[t][0][h]) <= 1.79769313486231570815e308)) {
+            const int lb0 = dbase[t][h];
             for (int j = 0; j <= N; ++j)
               if (!(fabs((double)x[lb0 + j * E]) <= 1.79769313486231570815e308)) {
-                atomicMin(prm.bad, u * (long long)(prm.unitBytes / (int)sizeof(R)) + lb0 + j * E);
+                atomicMin(prm.bad, prm.idx_base + u * (long long)(prm.unitBytes / (int)sizeof(R)) + lb0 + j * E);
                 break;
               }
           }
@@ -200,11 +238,14 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
         if (!dlive[t][h]) continue;
         R* y = x + dbase[t][h];
 #pragma unroll
-        for (int mt = 0; mt < MTE; ++mt)
-          if (mt < MTE - 1 || lastE) y[mt * E16] = (R)accE[t][mt][h];  // k = 2 (8 mt + q)
+        for (int mt = 0; mt < MB; ++mt)
+          if (mt < MB - 1 || lastB) y[(kB0 + 8 * SB * mt) * E] = (R)accB[t][mt][h];
 #pragma unroll
-        for (int mt = 0; mt < MTO; ++mt)
-          if (mt < MTO - 1 || lastO) y[mt * E16 + E] = (R)accO[t][mt][h];  // k = 2 (8 mt + q) + 1
+        for (int mt = 0; mt < MC; ++mt)
+          if (mt < MC - 1 || lastC) y[(kC0 + 32 * mt) * E] = (R)accC[t][mt][h];
+#pragma unroll
+        for (int mt = 0; mt < MO; ++mt)
+          if (mt < MO - 1 || lastO) y[(kO0 + 16 * mt) * E] = (R)accO[t][mt][h];
       }
     if (prm.linemax) {
 #pragma unroll
@@ -214,11 +255,14 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
           double m = 0.0;
           if (dlive[t][h]) {
 #pragma unroll
-            for (int mt = 0; mt < MTE; ++mt)
-              if (mt < MTE - 1 || lastE) m = fmax(m, fabs(accE[t][mt][h]));
+            for (int mt = 0; mt < MB; ++mt)
+              if (mt < MB - 1 || lastB) m = fmax(m, fabs(accB[t][mt][h]));
 #pragma unroll
-            for (int mt = 0; mt < MTO; ++mt)
-              if (mt < MTO - 1 || lastO) m = fmax(m, fabs(accO[t][mt][h]));
+            for (int mt = 0; mt < MC; ++mt)
+              if (mt < MC - 1 || lastC) m = fmax(m, fabs(accC[t][mt][h]));
+#pragma unroll
+            for (int mt = 0; mt < MO; ++mt)
+              if (mt < MO - 1 || lastO) m = fmax(m, fabs(accO[t][mt][h]));
           }
           m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
           m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));

@@ -7,8 +7,8 @@ namespace fastcheb {
 // of E inline reals each, stored back to back (so line (f, e) has element stride E).  *done receives the
 // number of leading fits handled (0 when the shape is not covered or the buffers are not 16-byte
 // aligned); the caller sends the remaining fits through the generic kernel.  Non-finite inputs are
-// reported through bad_dev (flat real index, atomicMin).  fit_max_dev (optional, real coefficients
+// reported through bad_dev (idx_base + flat real index, atomicMin).  fit_max_dev (optional, real coefficients
 // only): max |c| of every handled fit.
 int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, int dtype, const void* vals,
-                void* coefs, long long* bad_dev, double* fit_max_dev, cudaStream_t st, long long* done);
+                void* coefs, long long* bad_dev, long long idx_base, double* fit_max_dev, cudaStream_t st, long long* done);
 }  // namespace fastcheb

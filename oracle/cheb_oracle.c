@@ -143,6 +143,16 @@ int oracle_droptol_shape(int ndim, const int64_t* dims, int K, int cplx, const d
   return 1;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU baseline wants all host cores */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  extern void omp_set_num_threads(int);
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

@@ -312,3 +312,15 @@ def eval_truth(coefs: np.ndarray, lb, ub, pts: np.ndarray, z: np.ndarray | None 
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n: int | None = None) -> int:
+    """Use `n` OpenMP threads (default: every core this process may run on).  torchrun exports
+    OMP_NUM_THREADS=1 to its ranks, which would otherwise turn the timed CPU baseline into a 1-core run."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    L = lib()
+    L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+    L.oracle_set_num_threads.restype = None
+    L.oracle_set_num_threads(int(n))
+    return num_threads()

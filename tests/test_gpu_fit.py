@@ -87,7 +87,7 @@ def _oracle_batch(orc, vals, K):
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
-@pytest.mark.parametrize("n", [2, 3, 4, 5, 9, 17, 33, 40, 49, 64, 65])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 13, 17, 21, 33, 34, 35, 40, 49, 61, 64, 65])
 def test_batched_tensor_core_fit(fc, orc, n, dt):
     """configs[4]: many independent short 1-D fits (fit_dmma.cuh) incl. a ragged tail that the generic
     kernel finishes; scalar, K-vector and complex elements."""
