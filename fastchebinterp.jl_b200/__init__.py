@@ -14,6 +14,10 @@ Reference API mirrored (file:line under /root/reference/src):
   chebinterp(vals, lb, ub; tol) interp.jl:95-99, 140-141
   chebinterp_v1                 interp.jl:155-156
   chebpoints(order, lb, ub)     interp.jl:4-36   (host helper: grid generation is not on the device path)
+  chebinterp(f, order, lb, ub)  interp.jl:163-170 (host closure f on the host grid; a ChebPoly f stays on the device)
+  chebinterp(f, lb, ub)         interp.jl:174-203 (adaptive order doubling)
+  roots, colleague_matrix       roots.jl:55-59, 88-110 (re-interpolation on the device, <= 50x50
+                                eigenproblems on the host, as the reference leaves them to LAPACK)
 
 Array conventions (numpy): scalar-valued data has shape (n1..nN); vector-valued data carries a trailing
 component axis (n1..nN, K) — the flat buffer handed to C is Julia's `Array{SVector{K,T},N}` order.
@@ -31,7 +35,7 @@ from . import _capi
 from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA  # noqa: F401
 
 __all__ = ["ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
-           "droptol", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]
+           "droptol", "roots", "colleague_matrix", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]
 
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
 
@@ -388,9 +392,43 @@ def droptol(coefs, tol: float, ndim: int | None = None, device: int = 0):
     return np.ascontiguousarray(coefs[tuple(slice(0, n) for n in nd)])  # interp.jl:92
 
 
-def chebinterp(vals, lb, ub, tol: float | None = None, device: int = 0) -> ChebPoly:
-    """chebinterp(vals, lb, ub; tol=eps) — interp.jl:95-99,140-141.  Fit, trim and handle creation all
-    happen on the device (fastcheb_interp); the trimmed coefficients are copied back for `.coefs`."""
+def _handle_to_poly(h, lbv, ubv, rdt, K, cplx, device) -> ChebPoly:
+    L = _capi.lib()
+    N = len(lbv)
+    newdims = (ctypes.c_int64 * N)()
+    _check(L.fastcheb_dims(h, newdims))
+    nd = tuple(int(v) for v in newdims)
+    E = (K or 1) * (2 if cplx else 1)
+    out = np.empty(int(np.prod(nd)) * E, dtype=rdt)
+    _check(L.fastcheb_get_coefs(h, out.ctypes.data, _capi.MEM_HOST))
+    coefs = _from_julia_flat(out, nd, K, cplx)
+    return ChebPoly(coefs, lbv, ubv, device=device, _handle=h, _handle_dtype=rdt)
+
+
+def _eps_bounds(lbv, ubv):
+    """epsbounds (interp.jl:158-160): eps of the float type of the bounds."""
+    td = np.result_type(np.asarray(lbv).dtype, np.asarray(ubv).dtype)
+    return float(np.finfo(td if td.kind == "f" else np.float64).eps)
+
+
+def chebinterp(vals, *args, tol: float | None = None, device: int = 0, min_order=None, max_order=None) -> ChebPoly:
+    """chebinterp(vals, lb, ub; tol=eps)         — interp.jl:95-99,140-141: fit, trim and handle creation all happen
+                                                   on the device (fastcheb_interp).
+    chebinterp(f, order, lb, ub; tol=eps)        — interp.jl:163-170.  A host callable `f` is evaluated on the host grid
+                                                   (as in the reference); if `f` is a ChebPoly the grid, its evaluation
+                                                   and the fit stay on the device (fastcheb_reinterp).
+    chebinterp(f, lb, ub; tol=5eps, min_order, max_order) — interp.jl:174-203: order doubling until every dimension's
+                                                   fitted order is below the trial order."""
+    if callable(vals):
+        f = vals
+        if len(args) == 3:
+            return _chebinterp_f(f, args[0], args[1], args[2], tol, device)
+        if len(args) == 2:
+            return _chebinterp_adaptive(f, args[0], args[1], tol, device, min_order, max_order)
+        raise ArgumentError("chebinterp(f, [order,] lb, ub)")
+    if len(args) != 2:
+        raise ArgumentError("chebinterp(vals, lb, ub)")
+    lb, ub = args
     lbv, ubv = _bounds(lb, ub)
     N = len(lbv)
     vals = _float_vals(vals)
@@ -406,16 +444,141 @@ def chebinterp(vals, lb, ub, tol: float | None = None, device: int = 0) -> ChebP
                            flat.ctypes.data, _capi.MEM_HOST, _capi.dbl_array(lbv), _capi.dbl_array(ubv),
                            -1.0 if tol is None else float(tol), device, None)
     _check(rc, "fastcheb_interp: ")
-    newdims = (ctypes.c_int64 * N)()
-    _check(L.fastcheb_dims(h, newdims))
-    nd = tuple(int(v) for v in newdims)
-    E = (K or 1) * (2 if cplx else 1)
-    out = np.empty(int(np.prod(nd)) * E, dtype=rdt)
-    _check(L.fastcheb_get_coefs(h, out.ctypes.data, _capi.MEM_HOST))
-    coefs = _from_julia_flat(out, nd, K, cplx)
-    return ChebPoly(coefs, lbv, ubv, device=device, _handle=h, _handle_dtype=rdt)
+    return _handle_to_poly(h, lbv, ubv, rdt, K, cplx, device)
+
+
+def _chebinterp_f(f, order, lb, ub, tol, device) -> ChebPoly:
+    scalar = np.isscalar(order)
+    lbv, ubv = _bounds(lb, ub)
+    orders = (int(order),) * 1 if scalar else tuple(int(o) for o in order)
+    if any(o < 0 for o in orders):
+        raise ArgumentError(f"invalid negative order {orders}")  # interp.jl:10
+    if len(orders) != len(lbv):
+        raise DimensionMismatch("order, lb and ub must have the same length")
+    if tol is None:
+        tol = _eps_bounds(lbv, ubv)  # interp.jl:163: tol = epsbounds(lb, ub)
+    if isinstance(f, ChebPoly):
+        if f.ndim != len(lbv):
+            raise DimensionMismatch("the polynomial and the new box differ in dimension")
+        rdt = _real_dtype(f.coefs.dtype)
+        h = ctypes.c_void_p()
+        rc = _capi.lib().fastcheb_reinterp(ctypes.byref(h), f._handle(rdt), _capi.i64_array(orders), _capi.dbl_array(lbv),
+                                           _capi.dbl_array(ubv), float(tol), None)
+        _check(rc, "fastcheb_reinterp: ")
+        return _handle_to_poly(h, lbv, ubv, rdt, f.K, f.is_complex, f.device)
+    fdt = np.result_type(lbv.dtype, ubv.dtype)
+    fdt = fdt if fdt.kind == "f" else np.float64
+    x = chebpoints(orders[0] if scalar else orders, lbv[0] if scalar else lbv, ubv[0] if scalar else ubv, dtype=fdt)
+    if scalar:
+        vals = np.asarray([f(xi) for xi in x])
+    else:
+        flat = x.reshape(-1, len(orders))
+        vals = np.asarray([f(xi) for xi in flat])
+        vals = vals.reshape(x.shape[:-1] + vals.shape[1:])
+    return chebinterp(vals, lbv, ubv, tol=tol, device=device)
+
+
+def _chebinterp_adaptive(f, lb, ub, tol, device, min_order, max_order) -> ChebPoly:
+    lbv, ubv = _bounds(lb, ub)
+    N = len(lbv)
+    if tol is None:
+        tol = 5 * _eps_bounds(lbv, ubv)
+    if not tol > 0:
+        raise ArgumentError(f"tolerance {tol} must be > 0")  # interp.jl:178
+    big = np.iinfo(np.int64).max
+    mn = np.full(N, 8, dtype=np.int64) if min_order is None else np.atleast_1d(np.asarray(min_order, dtype=np.int64))
+    mx = np.full(N, big, dtype=np.int64) if max_order is None else np.atleast_1d(np.asarray(max_order, dtype=np.int64))
+    if not (len(mn) == len(mx) == N):
+        raise DimensionMismatch(f"dimensions must all == {N}")
+    if not np.all(mn > 0):
+        raise ArgumentError(f"minimum order {mn} must be > 0")
+    if not np.all(mx >= 0):
+        raise ArgumentError(f"maximum order {mx} must be >= 0")
+    order = np.minimum(mn, mx)
+    scalar = np.ndim(lb) == 0
+    while True:
+        c = _chebinterp_f(f, int(order[0]) if scalar else tuple(int(o) for o in order), lb, ub, tol, device)
+        size = np.asarray(c.dims)
+        done = (size - 1 < order) | (order == mx)                      # interp.jl:189
+        if np.all(done):
+            return c
+        nxt = np.array([1 << int(2 * o - 1).bit_length() if 2 * o > 1 else 1 for o in order], dtype=np.int64)  # nextpow(2, 2o)
+        order = np.where(done, order, np.minimum(mx, nxt))
 
 
 def chebinterp_v1(vals, lb, ub, tol: float | None = None, device: int = 0) -> ChebPoly:
     """interp.jl:155-156: the *first* axis of `vals` is the component axis."""
     return chebinterp(np.moveaxis(np.asarray(vals), 0, -1), lb, ub, tol=tol, device=device)
+
+
+
+# ------------------------------------------------------------------------------------------- roots (SURVEY §8f N1)
+def _colleague(coefs: np.ndarray) -> np.ndarray:
+    """Colleague matrix on [-1, 1] of a coefficient vector whose last entry is non-zero (roots.jl:13-33): the
+    upper-Hessenberg matrix with halves on both off-diagonals, a one at (2,1), and the last column corrected by
+    -c[:-1] / (2 c[-1])."""
+    n = len(coefs)
+    if n <= 1:
+        return np.zeros((0, 0))
+    if coefs[-1] == 0:
+        raise ArgumentError("trailing coefficient must be nonzero")
+    if n == 2:
+        return np.array([[-coefs[0] / coefs[1]]], dtype=float)
+    m = n - 1
+    C = np.zeros((m, m))
+    i = np.arange(m - 1)
+    C[i, i + 1] = 0.5
+    C[i + 1, i] = 0.5
+    C[1, 0] = 1.0
+    C[:, -1] -= coefs[:-1] / (2 * coefs[-1])
+    return C
+
+
+def colleague_matrix(c: ChebPoly, tol: float | None = None) -> np.ndarray:
+    """colleague_matrix(c; tol=5eps) — roots.jl:55-59: eigenvalues are the roots of the 1-D polynomial on [lb, ub];
+    trailing coefficients below tol * sum|c| are dropped."""
+    if c.ndim != 1 or c.K is not None:
+        raise ArgumentError("colleague_matrix needs a scalar-valued 1-D ChebPoly")
+    co = np.asarray(c.coefs)
+    if tol is None:
+        tol = 5 * float(np.finfo(_real_dtype(co.dtype)).eps)
+    abstol = np.abs(co).sum() * tol
+    big = np.nonzero(np.abs(co) >= abstol)[0]
+    n = int(big[-1]) + 1 if len(big) else 1
+    C = _colleague(co[:n].astype(float))
+    lb, ub = float(c.lb[0]), float(c.ub[0])
+    C = C * ((ub - lb) / 2)
+    C[np.diag_indices_from(C)] += (ub + lb) / 2
+    return C
+
+
+def roots(c: ChebPoly, tol: float | None = None, maxsize: int = 50) -> np.ndarray:
+    """roots(c; tol=5eps, maxsize=50) — roots.jl:88-110: sorted real roots of a real 1-D ChebPoly on [lb, ub].
+    Small problems are colleague-matrix eigenvalues (host LAPACK, like the reference); larger ones are split at the
+    chebfun point and *re-interpolated on the device* (fastcheb_reinterp: grid -> batched evaluation -> DCT-I fit ->
+    droptol), recursively, with the coefficients never leaving the GPU except for the <= maxsize eigenproblems."""
+    if c.ndim != 1 or c.K is not None or c.is_complex:
+        raise ArgumentError("roots needs a real scalar-valued 1-D ChebPoly")
+    co = np.asarray(c.coefs)
+    if tol is None:
+        tol = 5 * float(np.finfo(_real_dtype(co.dtype)).eps)
+    if not tol > 0:
+        raise ArgumentError(f"tolerance {tol} for truncating coefficients must be > 0")
+    if not maxsize > 0:
+        raise ArgumentError(f"maxsize {maxsize} must be > 0")
+    lb, ub = float(c.lb[0]), float(c.ub[0])
+    abstol = np.abs(co).max() * tol
+    big = np.nonzero(np.abs(co) >= abstol)[0]
+    n = int(big[-1]) + 1 if len(big) else 1
+    if n <= maxsize:
+        C = _colleague(co[:n].astype(float))
+        lam = np.linalg.eigvals(C) if C.size else np.zeros(0)
+        lam = (lam + 1) * ((ub - lb) / 2) + lb
+        htol = float(np.spacing(ub - lb)) * 100                         # roots.jl:63: eps(float(ub - lb)) * 100
+        keep = (np.abs(lam.imag) < htol) & (lam.real >= lb - htol) & (lam.real <= ub + htol)
+        return np.sort(np.clip(lam.real[keep], lb, ub))
+    split = 1.004849834917525 * ((ub - lb) / 2) + lb                  # roots.jl:102 (chebfun's split point)
+    order = 1 << int(n - 2).bit_length() if n > 2 else 1               # nextpow(2, n-1)
+    c1 = chebinterp(c, order, lb, split, tol=2 * tol)
+    c2 = chebinterp(c, order, split, ub, tol=2 * tol)
+    return np.concatenate([roots(c1, tol=2 * tol, maxsize=maxsize), roots(c2, tol=2 * tol, maxsize=maxsize)])

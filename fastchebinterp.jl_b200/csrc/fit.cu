@@ -234,6 +234,26 @@ int droptol_device(const DeviceInfo* di, int dev, int ndim, const int64_t* dims,
   return FASTCHEB_OK;
 }
 
+// points of a tensor-product grid, AoS: pts[g*N + d] = axis_d[index of g along d] (g column-major over the grid)
+struct GridParams {
+  int ndim;
+  int n[kMaxNdim];
+  int off[kMaxNdim];
+};
+template <typename R>
+__global__ void __launch_bounds__(256) grid_points_kernel(const double* __restrict__ axes, R* __restrict__ pts,
+                                                          long long total, const GridParams gp) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    long long rem = g;
+    for (int d = 0; d < gp.ndim; ++d) {
+      const int k = (int)(rem % gp.n[d]);
+      rem /= gp.n[d];
+      pts[g * gp.ndim + d] = (R)axes[gp.off[d] + k];
+    }
+  }
+}
+
 struct HostStage {
   int dev;
   void* d = nullptr;
@@ -454,6 +474,69 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
     d_final = blk.d;
   }
   return create_from_device(out, ndim, newdims, dtype, is_complex, ncomp, d_final, lb, ub, device, st);
+}
+
+// chebinterp(c, order, lb, ub; tol) for an interpolant that is itself a device-resident ChebPoly (the loop body of
+// roots, roots.jl:105-107, and of any re-expansion on a sub-box): Chebyshev points of the new box (interp.jl:4-36)
+// -> batched evaluation of `p` -> N-d DCT-I fit -> droptol -> new handle, without leaving the device.
+int fastcheb_reinterp(fastcheb_poly** out, const fastcheb_poly* p, const int64_t* order, const double* lb,
+                      const double* ub, double tol, void* stream) {
+  if (!out || !p || !order || !lb || !ub) return fail(FASTCHEB_EINVAL, "null argument");
+  *out = nullptr;
+  const int N = p->ndim, dev = p->device;
+  const DeviceInfo* di = device_info(dev);
+  if (!di) return FASTCHEB_ECUDA;
+  DeviceGuard dg(dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = real_size(p->dtype);
+  int64_t dims[FASTCHEB_MAX_NDIM];
+  GridParams gp;
+  memset(&gp, 0, sizeof gp);
+  gp.ndim = N;
+  long long total = 1;
+  int asum = 0;
+  for (int d = 0; d < N; ++d) {
+    if (order[d] < 0) return fail(FASTCHEB_EINVAL, "invalid negative order %lld (interp.jl:10)", (long long)order[d]);
+    if (!(lb[d] >= p->lb[d] && ub[d] <= p->ub[d]))
+      return fail(FASTCHEB_EDOMAIN, "new box [%g, %g] leaves the domain of the polynomial in dimension %d", lb[d], ub[d], d + 1);
+    dims[d] = order[d] + 1;
+    gp.n[d] = (int)dims[d];
+    gp.off[d] = asum;
+    asum += (int)dims[d];
+    total *= dims[d];
+    if (total > (1LL << 31)) return fail(FASTCHEB_EUNSUPPORTED, "grid too large");
+  }
+  // the grid coordinates, computed like interp.jl:4-7 in the working precision (index 0 is the upper bound; order 0
+  // gives the midpoint), clamped into the source box so that rounding at the faces never leaves the domain
+  std::vector<double> axes((size_t)asum);
+  for (int d = 0; d < N; ++d)
+    for (int i = 0; i < gp.n[d]; ++i) {
+      double x;
+      if (p->dtype == FASTCHEB_F64) {
+        const double cth = order[d] == 0 ? cos(1.0 * M_PI / 2.0) : cos((double)i * M_PI / (double)order[d]);
+        x = lb[d] + (1.0 + cth) * (ub[d] - lb[d]) * 0.5;
+      } else {
+        const float cth = order[d] == 0 ? cosf((float)(1.0 * M_PI / 2.0)) : cosf((float)((double)i * M_PI / (double)order[d]));
+        x = (double)((float)lb[d] + (1.0f + cth) * ((float)ub[d] - (float)lb[d]) * 0.5f);
+      }
+      axes[gp.off[d] + i] = std::min(std::max(x, p->lb[d]), p->ub[d]);
+    }
+  HostStage ax(dev), pts(dev), vals(dev);
+  ax.d = ws_acquire(dev, axes.size() * sizeof(double));
+  pts.d = ws_acquire(dev, (size_t)total * N * rs);
+  vals.d = ws_acquire(dev, (size_t)total * p->E * rs);
+  if (!ax.d || !pts.d || !vals.d) return fail(FASTCHEB_ENOMEM, "re-interpolation scratch");
+  FC_CUDA(cudaMemcpyAsync(ax.d, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  FC_CUDA(cudaStreamSynchronize(st));  // `axes` is pageable host memory
+  const int grid = grid_for(total, 256, di->sms);
+  if (p->dtype == FASTCHEB_F64)
+    grid_points_kernel<double><<<grid, 256, 0, st>>>((const double*)ax.d, (double*)pts.d, total, gp);
+  else
+    grid_points_kernel<float><<<grid, 256, 0, st>>>((const double*)ax.d, (float*)pts.d, total, gp);
+  FC_CUDA(cudaGetLastError());
+  note_launch();
+  FC_TRY(eval_device(p, pts.d, total, vals.d, p->E, nullptr, 0, false, nullptr, 0, st));
+  return fastcheb_interp(out, N, dims, p->dtype, p->cplx, p->K, vals.d, FASTCHEB_MEM_DEVICE, lb, ub, tol, dev, stream);
 }
 
 }  // extern "C"

@@ -152,10 +152,12 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   *done = 0;
   if (n < 2 || n > 65 || E < 1) return FASTCHEB_OK;
   // launch shape: FASTCHEB_FIT_TUNE="warps,slots,nt" overrides the defaults (benchmark sweeps)
-  int warps = 16, S = 3, NT = 1;  // measured best on B200 (profiles/r01_fit_sweep.txt); NT = 2 is not instantiated
+  // measured best on B200 (profiles/r01_fit_sweep.txt): Float64 is HBM-bound with 16 warps; Float32 units are half
+  // the bytes, so 24 warps fit and the (then DMMA-bound) kernel wants them.  NT = 2 is not instantiated.
+  int warps = dtype == FASTCHEB_F64 ? 16 : 24, S = 3, NT = 1;
   if (const char* t = getenv("FASTCHEB_FIT_TUNE")) {
     int a = 0, b = 0, c = 0;
-    if (sscanf(t, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && a <= 24 && b >= 2 && a * b <= 64 && c == 1) {
+    if (sscanf(t, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && a <= 24 && b >= 2 && a * b <= 128 && c == 1) {
       warps = a;
       S = b;
       NT = c;
@@ -188,10 +190,10 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   prm.slotBytes = (prm.unitBytes + 127) / 128 * 128;
   const size_t afragBytes = (af.doubles * 8 + 127) / 128 * 128;
   const size_t budget = di->smem_optin - 1024;
-  while (512 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > 2) --S;
-  while (512 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && warps > 1) --warps;
+  while (1024 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > 2) --S;
+  while (1024 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && warps > 1) --warps;
   prm.nslots = S;
-  const size_t smem = 512 + afragBytes + (size_t)warps * S * prm.slotBytes;
+  const size_t smem = 1024 + afragBytes + (size_t)warps * S * prm.slotBytes;
   if (smem > budget) return FASTCHEB_OK;
   double* linemax = nullptr;
   if (fit_max_dev) {

@@ -76,10 +76,10 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int S = prm.nslots;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fastcheb_smem);  // [nwarps][S], <= 64 entries
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fastcheb_smem);  // [nwarps][S], <= 128 entries
   constexpr int afragDoubles = (MO * KO + MB * KB + MC * KC) * 32;
-  double* afrag = reinterpret_cast<double*>(fastcheb_smem + 512);
-  unsigned char* ring = fastcheb_smem + 512 + ((afragDoubles * 8 + 127) / 128) * 128 + (size_t)warp * S * prm.slotBytes;
+  double* afrag = reinterpret_cast<double*>(fastcheb_smem + 1024);
+  unsigned char* ring = fastcheb_smem + 1024 + ((afragDoubles * 8 + 127) / 128) * 128 + (size_t)warp * S * prm.slotBytes;
 
   for (int i = threadIdx.x; i < afragDoubles; i += blockDim.x) afrag[i] = prm.afrag[i];
   if (lane == 0) {

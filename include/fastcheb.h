@@ -157,6 +157,27 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
                     int ncomp, const void* vals, int mem, const double* lb, const double* ub, double tol,
                     int device, void* stream);
 
+/* chebinterp(c, order, lb, ub; tol) where the interpolated function is itself a device-resident ChebPoly `p`
+ * (interp.jl:163-170 applied to a ChebPoly, the loop body of roots, roots.jl:105-107): Chebyshev points of the new
+ * box [lb,ub] (inside p's box; interp.jl:4-36) -> batched evaluation of p -> N-d fit -> droptol -> new handle, all
+ * on p's device.  order[d] >= 0 per dimension; tol < 0 selects eps of the real type. */
+int fastcheb_reinterp(fastcheb_poly** out, const fastcheb_poly* p, const int64_t* order, const double* lb,
+                      const double* ub, double tol, void* stream);
+
+/* ---- multi-GPU: fused evaluation + gather over NVLink ---------------------------------------------
+ * One process per GPU.  The reference has no counterpart (it has no parallelism at all); these
+ * entry points exist so that `c.(ys)` sharded over the GPUs of a node returns ONE result array: the gathering
+ * rank allocates the buffer (peer_alloc) and ships the 64-byte IPC handle; the other ranks map it (peer_open) and
+ * pass `mapped + slice offset` as the output pointer of fastcheb_eval_async / fastcheb_eval_jac_async — the
+ * kernel's result stores go over NVLink/NVSwitch directly into the gatherer's HBM, no separate collective. */
+#define FASTCHEB_IPC_HANDLE_BYTES 64
+int fastcheb_peer_alloc(void** dev_ptr, size_t bytes, void* ipc_handle_out, int device);
+int fastcheb_peer_free(void* dev_ptr, int device);
+int fastcheb_peer_open(void** mapped_ptr, const void* ipc_handle, int device);
+int fastcheb_peer_close(void* mapped_ptr, int device);
+/* synchronous device -> host copy of (part of) a peer buffer */
+int fastcheb_peer_read(void* host_dst, const void* dev_src, size_t bytes, int device);
+
 #ifdef __cplusplus
 }
 #endif
