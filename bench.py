@@ -364,6 +364,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how values reach rank 0")
     ap.add_argument("--workload", default="eval3d", choices=["eval3d", "fit1d"],
                     help="eval3d = the headline (configs[2]); fit1d = configs[4] batched DCT-I fits (HBM-bound leg)")
     ap.add_argument("--howmany", type=int, default=1 << 20, help="fit1d: fits per GPU per step")
@@ -418,21 +419,31 @@ def main():
     out_v = torch.empty((B, E), dtype=torch.float64, device=dev)
     out_J = torch.empty((B, N, E), dtype=torch.float64, device=dev) if jac else None
     status = torch.zeros(1, dtype=torch.int64, device=dev)
-    gathered = None
-    if distributed and not args.no_gather and not jac:
+    # N > 1: the values of all ranks land in ONE buffer on rank 0.  Default: fused eval + gather — every rank's kernel
+    # stores straight into rank 0's HBM through a CUDA-IPC mapping (NVLink peer stores, fastcheb.sharded.PeerGather);
+    # --gather nccl uses a torch.distributed gather after the kernel instead.
+    gathered, peer = None, None
+    do_gather = distributed and not args.no_gather and not jac
+    if do_gather and args.gather == "nccl":
         gathered = [torch.empty_like(out_v) for _ in range(world)] if rank == 0 else None
+    elif do_gather:
+        from fastcheb import sharded
+        peer = sharded.PeerGather(total_rows=B * world, row_reals=E, itemsize=8, dst=0, device=local)
+        out_ptr = peer.slice_ptr(rank * B)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
 
     def step():
         if jac:
             rc = L.fastcheb_eval_jac_async(h, pts.data_ptr(), B, out_v.data_ptr(), out_J.data_ptr(), status.data_ptr(), sp)
+        elif peer is not None:
+            rc = L.fastcheb_eval_async(h, pts.data_ptr(), B, out_ptr, status.data_ptr(), sp)  # stores go to rank 0's HBM
         else:
             rc = L.fastcheb_eval_async(h, pts.data_ptr(), B, out_v.data_ptr(), status.data_ptr(), sp)
         if rc != 0:
             raise RuntimeError(_capi.last_error())
-        if distributed and not args.no_gather and not jac:
-            dist.gather(out_v, gathered, dst=0)  # results gathered on rank 0 over NVLink
+        if gathered is not None or (do_gather and args.gather == "nccl" and rank != 0):
+            dist.gather(out_v, gathered, dst=0)  # results gathered on rank 0 over NVLink (NCCL)
 
     def barrier():
         if distributed:
@@ -467,7 +478,7 @@ def main():
     value = B * world * args.steps / (ms_max * 1e-3)
 
     # kernel-only time (no gather) for the roofline: one kernel per step
-    if distributed and not args.no_gather and not jac:
+    if do_gather:
         barrier()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record(stream)
@@ -519,6 +530,17 @@ def main():
         chk = float((hv[:1000] - out_v[:1000].cpu()).abs().max())
         e2e["max_abs_diff_vs_device_path"] = chk
 
+    gather_check = None
+    if peer is not None:
+        # every rank's slice of the gathered buffer equals what that rank computes locally
+        L.fastcheb_eval_async(h, pts.data_ptr(), B, out_v.data_ptr(), status.data_ptr(), sp)
+        torch.cuda.synchronize(dev)
+        mine = out_v[:4096].cpu()
+        lst = [None] * world
+        dist.all_gather_object(lst, mine.numpy())
+        if rank == 0:
+            gather_check = max(float(np.abs(peer.read(r * B, 4096).reshape(4096, E) - lst[r]).max()) for r in range(world))
+        peer.close()
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -534,8 +556,10 @@ def main():
                        "coef_bytes": int(np.prod(DIMS)) * K * 8, "algo": algo_used,
                        "l2": f"inputs {B * N * 8 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2",
                        "parallelism": f"points sharded over {world} GPU(s), coefficients NCCL-broadcast, "
-                                      + ("values gathered on rank 0 (NCCL gather) inside the timed region"
-                                         if (distributed and not args.no_gather and not jac) else "results stay sharded")},
+                                      + (("values gathered on rank 0 inside the timed region: "
+                                          + ("kernel stores straight into rank 0's HBM over NVLink (CUDA-IPC peer buffer, fused eval+gather)"
+                                             if peer is not None else "NCCL gather after the kernel"))
+                                         if do_gather else "results stay sharded")},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
                          "flops_per_point": W, "kernel_ms": kern_ms, "peak_source": peak_src,
@@ -545,6 +569,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if gather_check is not None:
+            line["gather_max_abs_diff_vs_local"] = gather_check
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()

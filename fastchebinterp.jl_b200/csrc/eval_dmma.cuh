@@ -28,6 +28,7 @@
 // as the DMMAs of tile t, which lets ptxas hide them in the DMMA issue gaps.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include "ptx_util.cuh"
 
 namespace fastcheb {
@@ -297,6 +298,35 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
     const double* rec = stages + (size_t)b * stageDoubles;
     Weights W;
     weights(rec, W);
+    // Software pipelining of the weighted reduction: the DFMAs that fold a finished G chain into the per-lane sums
+    // depend on the chain's last DMMA, and an in-order warp that waits for that latency cannot issue the next
+    // (independent) chain.  So chain e is folded only after chain e+1 has been issued; the last chain of a tile is
+    // folded after the first chain of the next tile, with the weights (Wp) of the tile it belongs to.
+    double pg0[MT], pg1[MT];
+    double ph0[JAC ? MT : 1], ph1[JAC ? MT : 1];
+    Weights Wp = W;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      pg0[mt] = pg1[mt] = 0.0;
+      if constexpr (JAC) ph0[mt] = ph1[mt] = 0.0;
+    }
+    auto fold = [&](auto ec, const Weights& Wf) {  // fold the pending chain of component `ec` with weights Wf
+      constexpr int e = decltype(ec)::value;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        acc[mt][e] = fma(pg0[mt], Wf.w[mt][0], acc[mt][e]);
+        acc[mt][e] = fma(pg1[mt], Wf.w[mt][1], acc[mt][e]);
+        if constexpr (JAC) {
+          accJ[mt][e][0] = fma(ph0[mt], Wf.w[mt][0], accJ[mt][e][0]);
+          accJ[mt][e][0] = fma(ph1[mt], Wf.w[mt][1], accJ[mt][e][0]);
+#pragma unroll
+          for (int d = 1; d < N; ++d) {
+            accJ[mt][e][d] = fma(pg0[mt], Wf.wd[mt][0][d], accJ[mt][e][d]);
+            accJ[mt][e][d] = fma(pg1[mt], Wf.wd[mt][1][d], accJ[mt][e][d]);
+          }
+        }
+      }
+    };
     int tin = 0;  // tile index inside the current stage
     int nt = prm.ntiles < prm.tilesPerStage ? prm.ntiles : prm.tilesPerStage;
     for (int tile = 0; tile < prm.ntiles; ++tile) {
@@ -316,15 +346,14 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
           rec_next = rec;  // harmless recomputation of this tile's weights
         }
       }
-      // ---- one basic block: weights of the next tile + the DMMAs of this tile
+      // ---- one basic block: the DMMA chains of this tile, the deferred folds, the weights of the next tile
       Weights Wn;
-      weights(rec_next, Wn);
-#pragma unroll
-      for (int e = 0; e < EC; ++e) {
+      auto chain = [&](auto ec) {
+        constexpr int e = decltype(ec)::value;
         const double* u = rec + kDmmaMeta + e * U;
         const double2 c0 = *reinterpret_cast<const double2*>(u + 2 * c);
         double g0[MT], g1[MT];
-        double h0[JAC ? MT : 1], h1[JAC ? MT : 1];
+        [[maybe_unused]] double h0[JAC ? MT : 1], h1[JAC ? MT : 1];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           g0[mt] = c0.x;  // k1 = 0 term: T_0 = 1
@@ -340,26 +369,26 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
             if constexpr (JAC) dmma884(h0[mt], h1[mt], Ad[mt][ks], bf);
           }
         }
+        // the previous chain has long finished: fold it now, then this chain becomes the pending one
+        if constexpr (e == 0)
+          fold(std::integral_constant<int, EC - 1>{}, Wp);
+        else
+          fold(std::integral_constant<int, (e > 0 ? e - 1 : 0)>{}, W);
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-#if defined(FC_VARIANT) && FC_VARIANT == 1  // experiment: no FP64 work between the DMMA chains
-          acc[mt][e] = __longlong_as_double(__double_as_longlong(acc[mt][e]) ^ __double_as_longlong(g0[mt]) ^
-                                            __double_as_longlong(g1[mt]) ^ __double_as_longlong(W.w[mt][0]));
-#else
-          acc[mt][e] = fma(g0[mt], W.w[mt][0], acc[mt][e]);
-          acc[mt][e] = fma(g1[mt], W.w[mt][1], acc[mt][e]);
-#endif
+          pg0[mt] = g0[mt];
+          pg1[mt] = g1[mt];
           if constexpr (JAC) {
-            accJ[mt][e][0] = fma(h0[mt], W.w[mt][0], accJ[mt][e][0]);
-            accJ[mt][e][0] = fma(h1[mt], W.w[mt][1], accJ[mt][e][0]);
-#pragma unroll
-            for (int d = 1; d < N; ++d) {
-              accJ[mt][e][d] = fma(g0[mt], W.wd[mt][0][d], accJ[mt][e][d]);
-              accJ[mt][e][d] = fma(g1[mt], W.wd[mt][1][d], accJ[mt][e][d]);
-            }
+            ph0[mt] = h0[mt];
+            ph1[mt] = h1[mt];
           }
         }
-      }
+      };
+      chain(std::integral_constant<int, 0>{});
+      weights(rec_next, Wn);
+      if constexpr (EC > 1) chain(std::integral_constant<int, 1>{});
+      if constexpr (EC > 2) chain(std::integral_constant<int, 2>{});
+      Wp = W;
       W = Wn;
       rec = rec_next;
       // ---- release the stage after its last tile; the last warp out refills the buffer
@@ -391,6 +420,7 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
         ++tin;
       }
     }
+    fold(std::integral_constant<int, EC - 1>{}, Wp);  // the last chain of the pass
 
     // ---- quad reduction and store ----
 #pragma unroll

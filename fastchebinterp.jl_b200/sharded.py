@@ -238,3 +238,63 @@ def sharded_fit(vals_all, ndim: int = 1, src: int = 0, fit_fn=None):
         return torch.cat(outs, dim=0).cpu().numpy()
     dist.send(lt, dst=src)
     return None
+
+
+class PeerGather:
+    """Fused evaluation + gather: rank `dst` owns one result buffer of `total_rows x row_reals` reals in its HBM
+    (fastcheb_peer_alloc); every other rank maps it through CUDA IPC and hands `mapped + its row offset` to the
+    evaluation kernel as the output pointer, so the kernel's own stores cross NVLink/NVSwitch — no staging buffer
+    and no collective kernel.  The only synchronisation is the caller's end-of-step stream sync + barrier."""
+
+    def __init__(self, total_rows: int, row_reals: int, itemsize: int = 8, dst: int = 0, device: int | None = None):
+        import ctypes
+
+        import torch
+
+        from . import _capi
+        from . import _check
+
+        dist = _dist()
+        self.rank, self.world, self.dst = dist.get_rank(), dist.get_world_size(), dst
+        self.device = torch.cuda.current_device() if device is None else device
+        self.row_bytes = int(row_reals) * int(itemsize)
+        self.total_rows = int(total_rows)
+        self._L = _capi.lib()
+        self._own = ctypes.c_void_p()
+        self._mapped = ctypes.c_void_p()
+        handle = [None]
+        if self.rank == dst:
+            buf = ctypes.create_string_buffer(64)
+            _check(self._L.fastcheb_peer_alloc(ctypes.byref(self._own), self.total_rows * self.row_bytes, buf, self.device),
+                   "fastcheb_peer_alloc: ")
+            handle = [buf.raw]
+        dist.broadcast_object_list(handle, src=dst)
+        if self.rank != dst:
+            hb = ctypes.create_string_buffer(handle[0], 64)
+            _check(self._L.fastcheb_peer_open(ctypes.byref(self._mapped), hb, self.device), "fastcheb_peer_open: ")
+        self.base = self._own.value if self.rank == dst else self._mapped.value
+
+    def slice_ptr(self, first_row: int) -> int:
+        """Device pointer (valid on THIS rank) of row `first_row` of the gathered buffer."""
+        return self.base + int(first_row) * self.row_bytes
+
+    def read(self, first_row: int, nrows: int, dtype=np.float64) -> np.ndarray:
+        """Copy rows of the gathered buffer to the host (dst rank only)."""
+        if self.rank != self.dst:
+            raise RuntimeError("only the gathering rank reads the buffer")
+        out = np.empty(int(nrows) * self.row_bytes // np.dtype(dtype).itemsize, dtype=dtype)
+        from . import _check
+
+        _check(self._L.fastcheb_peer_read(out.ctypes.data, self.slice_ptr(first_row), out.nbytes, self.device))
+        return out
+
+    def close(self):
+        dist = _dist()
+        dist.barrier()  # nobody unmaps while a peer may still be writing
+        if self.rank == self.dst:
+            if self._own.value:
+                self._L.fastcheb_peer_free(self._own, self.device)
+                self._own = type(self._own)()
+        elif self._mapped.value:
+            self._L.fastcheb_peer_close(self._mapped, self.device)
+            self._mapped = type(self._mapped)()
