@@ -177,6 +177,16 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measured_traffic(key, units_key, units):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json), when
+    the capture was taken at this launch size; else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
+        return int(t["dram_bytes"]) if int(t[units_key]) == int(units) else None
+    except Exception:
+        return None
+
+
 def hbm_peak_gbs():
     """Measured HBM copy bandwidth of this pool (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
     try:
@@ -339,7 +349,7 @@ def run_fit(args):
                        "l2": f"{nbuf} rotating input/output buffer pairs of {M * bytes_per_fit / 1e6:.0f} MB: no step finds its lines in L2",
                        "parallelism": f"fits sharded over {world} GPU(s), no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "bytes_per_fit": bytes_per_fit, "kernel_ms": kern_ms, "peak_source": peak_src},
+                         "traffic": measured_traffic("fit1d_" + args.dtype, "launch_fits", M), "bytes_per_fit": bytes_per_fit, "kernel_ms": kern_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "max_rel_err_vs_oracle": err}))
     if distributed:
@@ -561,7 +571,10 @@ def main():
                                              if peer is not None else "NCCL gather after the kernel"))
                                          if do_gather else "results stay sharded")},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         "traffic": measured_traffic("eval3d_jac" if jac else "eval3d_val", "launch_points", B),
+                         "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_traffic.json); algorithmic: "
+                                         f"{B * 8 * (N + E * (1 + (N if jac else 0)))} B of points in + results out",
                          "flops_per_point": W, "kernel_ms": kern_ms, "peak_source": peak_src,
                          "note": "FP64 tensor-core (DMMA) pipe; algorithmic flops, not executed flops"},
             "cpu_baseline": cpu,

@@ -34,7 +34,7 @@ import numpy as np
 from . import _capi
 from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA  # noqa: F401
 
-__all__ = ["ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
+__all__ = ["eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
            "droptol", "roots", "colleague_matrix", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]
 
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
@@ -300,6 +300,51 @@ def chebgradient(c: ChebPoly, x):
     if c.ndim == 1 and not _is_torch(x) and np.ndim(x) == 0:
         return v, g[..., 0]  # eval.jl:174-177
     return v, g
+
+
+def eval_many(coefs, lb, ub, pts, deriv: bool = False, device: int = 0):
+    """Many independent 1-D polynomials, each at its own points, in one launch: `[c.(xs) for (c, xs) in zip(cs, xss)]`
+    (eval.jl:63-70 per point; with deriv=True also chebgradient's derivative, eval.jl:174-177).
+
+    coefs: (howmany, n) or (howmany, n, K) real/complex — the layout chebcoefs(..., howmany=) returns;
+    lb, ub: scalars (shared box) or length-howmany arrays; pts: (howmany, M) reals.
+    Returns values (howmany, M[, K]) [and derivatives of the same shape]."""
+    coefs = _float_vals(coefs)
+    if coefs.ndim not in (2, 3):
+        raise DimensionMismatch("coefs must be (howmany, n) or (howmany, n, K)")
+    howmany, n = coefs.shape[:2]
+    K = coefs.shape[2] if coefs.ndim == 3 else None
+    cplx = np.iscomplexobj(coefs)
+    rdt = _real_dtype(coefs.dtype)
+    pts = np.ascontiguousarray(np.asarray(pts), dtype=rdt)
+    if pts.ndim != 2 or pts.shape[0] != howmany:
+        raise DimensionMismatch("pts must be (howmany, M)")
+    M = pts.shape[1]
+    lbv, ubv = np.atleast_1d(np.asarray(lb, dtype=np.float64)), np.atleast_1d(np.asarray(ub, dtype=np.float64))
+    per = int(lbv.size > 1 or ubv.size > 1)
+    if per:
+        lbv, ubv = np.broadcast_to(lbv, (howmany,)).copy(), np.broadcast_to(ubv, (howmany,)).copy()
+    flat = np.ascontiguousarray(coefs).reshape(-1)
+    flat = flat.view(rdt) if cplx else flat
+    E = (K or 1) * (2 if cplx else 1)
+    out = np.empty((howmany, M, E), dtype=rdt)
+    outd = np.empty((howmany, M, E), dtype=rdt) if deriv else None
+    rc = _capi.lib().fastcheb_eval_many(howmany, n, _dtype_code(rdt), int(cplx), K or 1, flat.ctypes.data,
+                                        lbv.ctypes.data, ubv.ctypes.data, per, pts.ctypes.data, M, out.ctypes.data,
+                                        outd.ctypes.data if deriv else None, None, _capi.MEM_HOST, device, None)
+    if rc == _capi.EDOMAIN:
+        bad = _capi.error_index()
+        f, i = divmod(bad, M)
+        err = ArgumentError(f"{pts[f, i]} not in domain {lbv[f if per else 0]} to {ubv[f if per else 0]} (polynomial {f})")
+        err.index = bad
+        raise err
+    _check(rc, "fastcheb_eval_many: ")
+
+    def shape(a):
+        a = a.view(np.complex64 if rdt == np.float32 else np.complex128) if cplx else a
+        return a.reshape(howmany, M) if K is None else a.reshape(howmany, M, K)
+
+    return (shape(out), shape(outd)) if deriv else shape(out)
 
 
 # ------------------------------------------------------------------------------------------- fit

@@ -1,0 +1,243 @@
+// C ABI: many independent 1-D ChebPolys evaluated at their own points in one launch (include/fastcheb.h,
+// fastcheb_eval_many) — the evaluation leg of BASELINE.json configs[4] (10^5 order-64 polynomials x 10^3 points).
+//
+// Reference: `[c.(xs) for (c, xs) in zip(cs, xss)]`, i.e. per polynomial (::ChebPoly{1})(x) eval.jl:63-70 and
+// chebgradient eval.jl:174-177 (1-D Clenshaw eval.jl:19-31, derivative recurrence :88-101, scale :151).
+//
+// One warp owns one polynomial at a time: its n*E coefficients go to the warp's shared-memory region (they are the
+// output of fastcheb_fit: back-to-back lines, element stride E), every lane runs the Clenshaw recurrence for P
+// points with the coefficient read as a warp-wide broadcast.  The operation sequence is the oracle's (explicit IEEE
+// fma / sub / mul / div), so results are bit-identical to it.
+#include <algorithm>
+#include <cstring>
+#include "host_util.h"
+#include "ptx_util.cuh"
+
+namespace fastcheb {
+namespace {
+
+__device__ __forceinline__ double rsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float rsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float rmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double rdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float rdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double rfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float rfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+struct ManyParams {
+  const void* coefs;   // [howmany][n][E]
+  const void* pts;     // [howmany][M]
+  void* out_v;         // [howmany][M][E]
+  void* out_d;         // [howmany][M][E] or null
+  const double* lb;    // per polynomial (bounds_per_poly) or one value
+  const double* ub;
+  long long* bad;      // first out-of-domain flat point index (atomicMin)
+  long long howmany, M;
+  int n, bounds_per_poly;
+};
+
+template <typename R, int E, int P, bool DER>
+__global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ ManyParams prm) {
+  extern __shared__ __align__(16) unsigned char fastcheb_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int n = prm.n, nE = n * E;
+  R* cs = reinterpret_cast<R*>(fastcheb_smem) + (size_t)warp * nE;
+  const R* coefs = reinterpret_cast<const R*>(prm.coefs);
+  const R* pts = reinterpret_cast<const R*>(prm.pts);
+  R* out_v = reinterpret_cast<R*>(prm.out_v);
+  R* out_d = reinterpret_cast<R*>(prm.out_d);
+  const long long gw = (long long)blockIdx.x * nwarps + warp, tw = (long long)gridDim.x * nwarps;
+  for (long long f = gw; f < prm.howmany; f += tw) {
+    __syncwarp();
+    for (int i = lane; i < nE; i += 32) cs[i] = coefs[f * nE + i];
+    __syncwarp();
+    const R lb = (R)prm.lb[prm.bounds_per_poly ? f : 0], ub = (R)prm.ub[prm.bounds_per_poly ? f : 0];
+    const R span = rsub(ub, lb);
+    for (long long p0 = lane; p0 < prm.M; p0 += 32 * P) {
+      R z[P], z2[P];
+      bool live[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const long long ip = p0 + 32 * p;
+        live[p] = ip < prm.M;
+        const R x = live[p] ? pts[f * prm.M + ip] : lb;
+        const bool ok = (lb <= x) && (x <= ub);                       // eval.jl:64 (closed box, NaN fails)
+        z[p] = ok ? rsub(rdiv(rmul(rsub(x, lb), R(2)), span), R(1)) : R(0);  // eval.jl:65
+        z2[p] = rmul(R(2), z[p]);
+        if (live[p] && !ok) {
+          live[p] = false;
+          if (prm.bad) atomicMin(prm.bad, f * prm.M + ip);
+        }
+      }
+      R b1[P][E], b2[P][E], d1[DER ? P : 1][E], d2[DER ? P : 1][E];
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          b1[p][e] = b2[p][e] = R(0);
+          if constexpr (DER) d1[p][e] = d2[p][e] = R(0);
+        }
+      for (int j = n - 1; j >= 1; --j) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const R cj = cs[j * E + e];
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            const R nb = rsub(rfma(z2[p], b1[p][e], cj), b2[p][e]);                    // eval.jl:28 / :96
+            if constexpr (DER) {
+              const R nd = rsub(rfma(z2[p], d1[p][e], rmul(R(2), b1[p][e])), d2[p][e]);  // eval.jl:97
+              d2[p][e] = d1[p][e];
+              d1[p][e] = nd;
+            }
+            b2[p][e] = b1[p][e];
+            b1[p][e] = nb;
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        if (!live[p]) continue;
+        const long long o = (f * prm.M + p0 + 32 * p) * E;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          out_v[o + e] = rsub(rfma(z[p], b1[p][e], cs[e]), b2[p][e]);  // eval.jl:31 / :101
+          if constexpr (DER)
+            out_d[o + e] = rdiv(rmul(rsub(rfma(z[p], d1[p][e], b1[p][e]), d2[p][e]), R(2)), span);  // eval.jl:101, :151
+        }
+      }
+    }
+  }
+}
+
+template <typename R, int E, bool DER>
+cudaError_t launch(const ManyParams& prm, int sms, cudaStream_t st) {
+  constexpr int P = sizeof(R) == 8 ? (E >= 3 ? 2 : 4) : (E >= 3 ? 2 : 4);
+  const int warps = 8;
+  const size_t smem = (size_t)warps * prm.n * E * sizeof(R);
+  auto kern = eval_many_kernel<R, E, P, DER>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int bps = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, warps * 32, smem);
+  if (e != cudaSuccess) return e;
+  const long long want = (prm.howmany + warps - 1) / warps;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * std::max(1, bps)));
+  kern<<<grid, warps * 32, smem, st>>>(prm);
+  note_launch();
+  return cudaGetLastError();
+}
+
+template <typename R, bool DER>
+cudaError_t dispatch(int E, const ManyParams& prm, int sms, cudaStream_t st) {
+  switch (E) {
+    case 1: return launch<R, 1, DER>(prm, sms, st);
+    case 2: return launch<R, 2, DER>(prm, sms, st);
+    case 3: return launch<R, 3, DER>(prm, sms, st);
+    case 4: return launch<R, 4, DER>(prm, sms, st);
+    case 6: return launch<R, 6, DER>(prm, sms, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+}  // namespace fastcheb
+
+using namespace fastcheb;
+
+extern "C" int fastcheb_eval_many(int64_t howmany, int64_t n, int dtype, int is_complex, int ncomp, const void* coefs,
+                                  const double* lb, const double* ub, int bounds_per_poly, const void* pts, int64_t M,
+                                  void* out_v, void* out_d, int64_t* status_dev, int mem, int device, void* stream) {
+  if (howmany < 0 || n < 1 || M < 0 || ncomp < 1) return fail(FASTCHEB_EINVAL, "bad size");
+  if (dtype != FASTCHEB_F32 && dtype != FASTCHEB_F64) return fail(FASTCHEB_EINVAL, "bad dtype %d", dtype);
+  if (mem != FASTCHEB_MEM_HOST && mem != FASTCHEB_MEM_DEVICE) return fail(FASTCHEB_EINVAL, "bad mem %d", mem);
+  if (howmany == 0 || M == 0) return FASTCHEB_OK;
+  if (!coefs || !lb || !ub || !pts || !out_v) return fail(FASTCHEB_EINVAL, "null buffer");
+  const int E = ncomp * (is_complex ? 2 : 1);
+  if (!(E == 1 || E == 2 || E == 3 || E == 4 || E == 6))
+    return fail(FASTCHEB_EUNSUPPORTED, "fastcheb_eval_many covers 1, 2, 3, 4 or 6 real components per element, got %d", E);
+  const size_t rs = real_size(dtype);
+  if ((size_t)n * E * rs * 8 > (size_t)96 * 1024)
+    return fail(FASTCHEB_EUNSUPPORTED, "n = %lld too large for the batched 1-D evaluator (use one handle per polynomial)", (long long)n);
+  const DeviceInfo* di = device_info(device);
+  if (!di) return FASTCHEB_ECUDA;
+  DeviceGuard dg(device);
+  if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t cbytes = (size_t)howmany * n * E * rs, pbytes = (size_t)howmany * M * rs, obytes = pbytes * E;
+  const size_t nb = bounds_per_poly ? (size_t)howmany : 1;
+  ManyParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.howmany = howmany;
+  prm.M = M;
+  prm.n = (int)n;
+  prm.bounds_per_poly = bounds_per_poly ? 1 : 0;
+  FlagSlot fs;
+  FC_TRY(flag_acquire(device, &fs));
+  struct Rel {
+    FlagSlot& f;
+    ~Rel() { flag_release(f); }
+  } rel{fs};
+  long long* flag = status_dev && mem == FASTCHEB_MEM_DEVICE ? (long long*)status_dev : fs.dev;
+  FC_CUDA(set_flag_async(flag, kNoBad, st));
+  prm.bad = flag;
+  void* scratch = nullptr;
+  struct Free {
+    int dev;
+    void*& p;
+    ~Free() {
+      if (p) ws_release(dev, p);
+    }
+  } fr{device, scratch};
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  if (mem == FASTCHEB_MEM_HOST) {
+    const size_t total = al(cbytes) + al(pbytes) + al(obytes) * (out_d ? 2 : 1) + 2 * al(nb * 8);
+    scratch = ws_acquire(device, total);
+    if (!scratch) return fail(FASTCHEB_ENOMEM, "device staging of %zu bytes", total);
+    char* q = (char*)scratch;
+    char* d_c = q;
+    q += al(cbytes);
+    char* d_p = q;
+    q += al(pbytes);
+    char* d_v = q;
+    q += al(obytes);
+    char* d_d = out_d ? q : nullptr;
+    if (out_d) q += al(obytes);
+    char* d_lb = q;
+    q += al(nb * 8);
+    char* d_ub = q;
+    FC_CUDA(cudaMemcpyAsync(d_c, coefs, cbytes, cudaMemcpyHostToDevice, st));
+    FC_CUDA(cudaMemcpyAsync(d_p, pts, pbytes, cudaMemcpyHostToDevice, st));
+    FC_CUDA(cudaMemcpyAsync(d_lb, lb, nb * 8, cudaMemcpyHostToDevice, st));
+    FC_CUDA(cudaMemcpyAsync(d_ub, ub, nb * 8, cudaMemcpyHostToDevice, st));
+    prm.coefs = d_c;
+    prm.pts = d_p;
+    prm.out_v = d_v;
+    prm.out_d = d_d;
+    prm.lb = (const double*)d_lb;
+    prm.ub = (const double*)d_ub;
+  } else {
+    prm.coefs = coefs;
+    prm.pts = pts;
+    prm.out_v = out_v;
+    prm.out_d = out_d;
+    prm.lb = lb;  // device pointers in device mode
+    prm.ub = ub;
+  }
+  cudaError_t e;
+  if (dtype == FASTCHEB_F64)
+    e = out_d ? dispatch<double, true>(E, prm, di->sms, st) : dispatch<double, false>(E, prm, di->sms, st);
+  else
+    e = out_d ? dispatch<float, true>(E, prm, di->sms, st) : dispatch<float, false>(E, prm, di->sms, st);
+  if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "batched 1-D evaluation launch failed: %s", cudaGetErrorString(e));
+  if (mem == FASTCHEB_MEM_DEVICE) return FASTCHEB_OK;  // asynchronous: the caller reads status_dev after syncing
+  FC_CUDA(cudaMemcpyAsync(out_v, prm.out_v, obytes, cudaMemcpyDeviceToHost, st));
+  if (out_d) FC_CUDA(cudaMemcpyAsync(out_d, prm.out_d, obytes, cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaStreamSynchronize(st));
+  if (*fs.host != kNoBad) {
+    err_state().index = *fs.host;
+    return fail(FASTCHEB_EDOMAIN, "point %lld not in domain (eval.jl:64)", *fs.host);
+  }
+  return FASTCHEB_OK;
+}

@@ -1,4 +1,9 @@
-set -x
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_val_p.json 2> gpurun_out/bench_val.err; tail -3 gpurun_out/bench_val.err; cat gpurun_out/bench_val_p.json
-python bench.py --steps 5 --warmup 3 --mode jac --no-cpu --no-e2e > gpurun_out/bench_jac_p.json 2> gpurun_out/bench_jac.err; tail -3 gpurun_out/bench_jac.err; cat gpurun_out/bench_jac_p.json
+timeout 1200 python -m pytest tests/test_gpu_eval.py -m gpu -q -x 2>&1 | tail -8
+python tools/bench_configs.py many > gpurun_out/configs_many.jsonl 2> gpurun_out/configs.err; tail -3 gpurun_out/configs.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/configs_many.jsonl'):
+    d=json.loads(l)
+    print(f"{d['config']:60s} {d['algo']:8s} {d['mode']} {d['points_per_s']:.3e} pts/s  fp {d['frac_of_fp_peak']*100:5.1f}%  hbm {d['frac_of_hbm']*100:5.1f}%")
+PY

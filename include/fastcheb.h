@@ -124,6 +124,18 @@ int fastcheb_eval_async(const fastcheb_poly* p, const void* pts_dev, int64_t npt
 int fastcheb_eval_jac_async(const fastcheb_poly* p, const void* pts_dev, int64_t npts, void* out_v_dev,
                             void* out_J_dev, int64_t* status_dev, void* stream);
 
+/* fastcheb_eval_many : many independent 1-D polynomials, each evaluated at its own points, in one launch — the
+ * reference spells this `[c.(xs) for (c, xs) in zip(cs, xss)]` with (::ChebPoly{1})(x) eval.jl:63-70 per point (and
+ * chebgradient eval.jl:174-177 when out_d != NULL: d/dx of every component).  `coefs` holds `howmany` coefficient
+ * lines of n elements (E inline reals each) back to back — exactly what fastcheb_fit writes for a batch of 1-D fits;
+ * pts is howmany x M reals, out_v / out_d are howmany x M x E.  lb/ub: one pair (bounds_per_poly = 0) or `howmany`
+ * pairs.  mem = HOST: synchronous, EDOMAIN + fastcheb_error_index (flat point index) on a point outside its box.
+ * mem = DEVICE: every pointer (lb/ub included) is a device pointer, the call only enqueues, and status_dev (may be
+ * NULL) receives the first offending flat point index or INT64_MAX. */
+int fastcheb_eval_many(int64_t howmany, int64_t n, int dtype, int is_complex, int ncomp, const void* coefs,
+                       const double* lb, const double* ub, int bounds_per_poly, const void* pts, int64_t M,
+                       void* out_v, void* out_d, int64_t* status_dev, int mem, int device, void* stream);
+
 /* ---- the fit ----------------------------------------------------------------------------------
  * fastcheb_fit : chebcoefs(vals) (interp.jl:39-71) for `howmany` independent arrays stored back to
  * back, each `dims[0] x ... x dims[ndim-1]` elements of E inline reals (so `chebinterp_v1`'s

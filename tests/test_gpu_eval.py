@@ -208,3 +208,54 @@ def test_tuple_layout(fc, orc):
     assert rc == 0
     assert np.array_equal(rec[:, :2], v0)
     assert np.array_equal(rec[:, 2:].reshape(500, 2, 2), np.swapaxes(J0, 1, 2))   # column-major K x N
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_eval_many_bit_identical_to_oracle(fc, orc, dt):
+    """configs[4] evaluation leg: many independent 1-D polynomials at their own points in one launch
+    (fastcheb_eval_many) == a loop of oracle evaluations, bit for bit (values and chebgradient derivative)."""
+    rng = np.random.default_rng(77)
+    for n, K, cplx, M in ((65, None, False, 1000), (1, None, False, 7), (2, None, False, 33), (17, 3, False, 130),
+                          (40, 2, True, 257), (9, None, True, 64)):
+        howmany = 37
+        shape = (howmany, n) + ((K,) if K else ())
+        c = rng.uniform(-1, 1, shape)
+        if cplx:
+            c = (c + 1j * rng.uniform(-1, 1, shape)).astype(np.complex128 if dt == np.float64 else np.complex64)
+        else:
+            c = c.astype(dt)
+        lb = rng.uniform(-2, 0, howmany).astype(dt)
+        ub = (lb + rng.uniform(0.5, 3, howmany)).astype(dt)
+        pts = (lb[:, None] + (ub - lb)[:, None] * rng.random((howmany, M))).astype(dt)
+        pts = np.clip(pts, lb[:, None], ub[:, None])
+        pts[:, 0], pts[:, -1] = lb, ub                                    # closed box
+        v, d = fc.eval_many(c, lb, ub, pts, deriv=True)
+        v_only = fc.eval_many(c, lb, ub, pts)
+        assert np.array_equal(v, v_only)
+        for f in (0, 5, howmany - 1):
+            ref = orc.OracleChebPoly(c[f], np.array([lb[f]]), np.array([ub[f]]))
+            rv, rJ = ref.jacobian(pts[f].reshape(-1, 1))
+            assert np.array_equal(v[f], rv.reshape(v[f].shape)), (n, K, cplx, f)
+            assert np.array_equal(d[f], rJ.reshape(d[f].shape)), (n, K, cplx, f)
+    # shared bounds + domain error with the flat index of the offending point
+    c = rng.uniform(-1, 1, (5, 9)).astype(dt)
+    pts = rng.random((5, 11)).astype(dt)
+    assert fc.eval_many(c, 0.0, 1.0, pts).shape == (5, 11)
+    pts[3, 4] = 1.5
+    with pytest.raises(fc.ArgumentError) as ei:
+        fc.eval_many(c, 0.0, 1.0, pts)
+    assert ei.value.index == 3 * 11 + 4
+
+
+def test_cfg5_fit_then_eval_many(fc):
+    """configs[4] end to end at full size: 10^5 order-64 fits (tensor-core DCT-I), then every polynomial evaluated at
+    10^3 of its own points (10^8 evaluations) against the analytic functions f_i(x) = sin(a_i x + b_i)."""
+    rng = np.random.default_rng(8)
+    Mfits, n, M = 100_000, 65, 1000
+    a, b = rng.uniform(0.5, 3.0, Mfits), rng.uniform(-1, 1, Mfits)
+    grid = np.cos(np.pi * np.arange(n) / (n - 1))
+    C = fc.chebcoefs(np.sin(a[:, None] * grid[None, :] + b[:, None]), ndim=1, howmany=Mfits)
+    x = rng.uniform(-1, 1, (Mfits, M))
+    v, d = fc.eval_many(C, -1.0, 1.0, x, deriv=True)
+    assert np.abs(v - np.sin(a[:, None] * x + b[:, None])).max() <= 1e-13
+    assert np.abs(d - a[:, None] * np.cos(a[:, None] * x + b[:, None])).max() <= 1e-10
