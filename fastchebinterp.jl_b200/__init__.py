@@ -16,6 +16,8 @@ Reference API mirrored (file:line under /root/reference/src):
   chebpoints(order, lb, ub)     interp.jl:4-36   (host helper: grid generation is not on the device path)
   chebinterp(f, order, lb, ub)  interp.jl:163-170 (host closure f on the host grid; a ChebPoly f stays on the device)
   chebinterp(f, lb, ub)         interp.jl:174-203 (adaptive order doubling)
+  chebregression, chebvandermonde  regression.jl:5-73 (the Vandermonde matrix is assembled on the device in
+                                one O(m P) pass; the dense QR solve `A \\ Y` stays a library call, LAPACK or cuSOLVER)
   roots, colleague_matrix       roots.jl:55-59, 88-110 (re-interpolation on the device, <= 50x50
                                 eigenproblems on the host, as the reference leaves them to LAPACK)
 
@@ -34,7 +36,7 @@ import numpy as np
 from . import _capi
 from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA  # noqa: F401
 
-__all__ = ["eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
+__all__ = ["chebregression", "chebvandermonde", "eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
            "droptol", "roots", "colleague_matrix", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]
 
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
@@ -627,3 +629,95 @@ def roots(c: ChebPoly, tol: float | None = None, maxsize: int = 50) -> np.ndarra
     c1 = chebinterp(c, order, lb, split, tol=2 * tol)
     c2 = chebinterp(c, order, split, ub, tol=2 * tol)
     return np.concatenate([roots(c1, tol=2 * tol, maxsize=maxsize), roots(c2, tol=2 * tol, maxsize=maxsize)])
+
+
+# ------------------------------------------------------------------------------------------- regression
+def chebvandermonde(x, lb, ub, order, device: int = 0):
+    """chebvandermonde(x, lb, ub, order) — regression.jl:5-46: the m x prod(order+1) Chebyshev-Vandermonde matrix,
+    columns in column-major multi-index order.  numpy in -> numpy (Fortran-ordered) out; a torch CUDA tensor in ->
+    a torch tensor on the same device (column-major strides) out, without touching the host."""
+    scalar = np.isscalar(order)
+    orders = (int(order),) if scalar else tuple(int(o) for o in order)
+    N = len(orders)
+    if any(o < 0 for o in orders):
+        raise ArgumentError(f"order {orders} must be nonnegative")  # regression.jl:30
+    lbv, ubv = _bounds(lb, ub)
+    if len(lbv) != N:
+        raise DimensionMismatch("order, lb and ub must have the same length")
+    dims = tuple(o + 1 for o in orders)
+    P = int(np.prod(dims))
+    L = _capi.lib()
+    if _is_torch(x):
+        import torch
+
+        tdt = torch.float32 if x.dtype == torch.float32 else torch.float64
+        pts = x.to(tdt).reshape(-1, N).contiguous()
+        m = pts.shape[0]
+        At = torch.empty((P, m), dtype=tdt, device=x.device)  # row i of At = column i of A
+        rc = L.fastcheb_vandermonde(N, _capi.i64_array(dims), _capi.F32 if tdt == torch.float32 else _capi.F64,
+                                    pts.data_ptr(), m, _capi.dbl_array(lbv), _capi.dbl_array(ubv), At.data_ptr(), m,
+                                    _capi.MEM_DEVICE, x.device.index,
+                                    ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        A = At.t()
+        ptsh = None
+    else:
+        xa = np.asarray(x)
+        rdt = np.float32 if xa.dtype == np.float32 and lbv.dtype != np.float64 else np.float64
+        ptsh = np.ascontiguousarray(xa.astype(rdt, copy=False).reshape(-1, N))
+        m = ptsh.shape[0]
+        A = np.empty((m, P), dtype=rdt, order="F")
+        rc = L.fastcheb_vandermonde(N, _capi.i64_array(dims), _dtype_code(rdt), ptsh.ctypes.data, m,
+                                    _capi.dbl_array(lbv), _capi.dbl_array(ubv), A.ctypes.data, m, _capi.MEM_HOST, device, None)
+    if rc == _capi.EDOMAIN:
+        bad = _capi.error_index()
+        err = ArgumentError(f"{ptsh[bad] if ptsh is not None else 'point %d' % bad} not in domain [{lbv},{ubv}]")  # regression.jl:33
+        err.index = bad
+        raise err
+    _check(rc, "fastcheb_vandermonde: ")
+    return A
+
+
+def chebregression(x, y, *args, device: int = 0) -> ChebPoly:
+    """chebregression(x, y, [lb, ub,] order) — regression.jl:52-107: least-squares fit of a Chebyshev polynomial of the
+    given order to scattered data.  x: (m,) reals (1-D) or (m, N); y: (m,) or (m, K) (vector-valued fit); lb/ub default
+    to the coordinate-wise minimum/maximum of x.  The Vandermonde matrix is assembled on the GPU; `A \\ Y` is a dense QR
+    least-squares solve (LAPACK on the host for numpy input — as in the reference — or cuSOLVER through torch for
+    device-resident input)."""
+    if len(args) == 3:
+        lb, ub, order = args
+    elif len(args) == 1:
+        order = args[0]
+        lb = ub = None
+    else:
+        raise ArgumentError("chebregression(x, y, [lb, ub,] order)")
+    scalar = np.isscalar(order)
+    orders = (int(order),) if scalar else tuple(int(o) for o in order)
+    N = len(orders)
+    on_dev = _is_torch(x)
+    xa = x if on_dev else np.asarray(x)
+    xm = xa.reshape(-1, N)
+    m = xm.shape[0]
+    if lb is None:  # regression.jl:91-96: bounds from the data
+        lb = xm.min(0)[0].cpu().numpy() if on_dev else xm.min(axis=0)
+        ub = xm.max(0)[0].cpu().numpy() if on_dev else xm.max(axis=0)
+    lbv, ubv = _bounds(lb, ub)
+    ya = y if _is_torch(y) else np.asarray(y)
+    if ya.shape[0] != m:
+        raise DimensionMismatch("x and y differ in length")  # regression.jl:54
+    P = int(np.prod([o + 1 for o in orders]))
+    if m < P:
+        raise ArgumentError(f"not enough data points {m} to fit to order {orders}")  # regression.jl:55
+    K = ya.shape[1] if ya.ndim == 2 else None
+    A = chebvandermonde(xa, lbv, ubv, orders, device=device)
+    if on_dev:
+        import torch
+
+        Y = (ya if _is_torch(ya) else torch.as_tensor(np.asarray(ya), device=x.device)).to(A.dtype).reshape(m, -1)
+        C = torch.linalg.lstsq(A, Y).solution.cpu().numpy()          # cuSOLVER QR
+    else:
+        Y = np.asarray(ya).reshape(m, -1)
+        cdt = np.result_type(A.dtype, Y.dtype)
+        C = np.linalg.lstsq(A.astype(cdt, copy=False), Y.astype(cdt, copy=False), rcond=None)[0]   # LAPACK, like `A \\ Y` (:67)
+    dims = tuple(o + 1 for o in orders)
+    coefs = C.reshape(dims + (C.shape[1],), order="F") if K is not None else C[:, 0].reshape(dims, order="F")
+    return ChebPoly(coefs, lbv, ubv, device=device if not on_dev else x.device.index)

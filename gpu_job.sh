@@ -1,9 +1,2 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_eval.py -m gpu -q -x 2>&1 | tail -8
-python tools/bench_configs.py many > gpurun_out/configs_many.jsonl 2> gpurun_out/configs.err; tail -3 gpurun_out/configs.err
-python - <<'PY'
-import json
-for l in open('gpurun_out/configs_many.jsonl'):
-    d=json.loads(l)
-    print(f"{d['config']:60s} {d['algo']:8s} {d['mode']} {d['points_per_s']:.3e} pts/s  fp {d['frac_of_fp_peak']*100:5.1f}%  hbm {d['frac_of_hbm']*100:5.1f}%")
-PY
+timeout 1200 python -m pytest tests/test_gpu_regression.py -m gpu -q -x 2>&1 | tail -30

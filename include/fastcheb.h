@@ -176,6 +176,15 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
 int fastcheb_reinterp(fastcheb_poly** out, const fastcheb_poly* p, const int64_t* order, const double* lb,
                       const double* ub, double tol, void* stream);
 
+/* chebvandermonde(x, lb, ub, order) (regression.jl:5-46): the m x P Chebyshev-Vandermonde matrix of least-squares
+ * regression, P = prod dims, A[j + lda*i] = prod_d T_{k_d}(z_d(x_j)) with i the column-major multi-index (k_1
+ * fastest) — Julia's Array{T,2} layout.  pts: m x ndim reals AoS.  One pass, O(m P) (the reference's generic routine
+ * is O(m P^2)).  Synchronous; a point whose normalised coordinate leaves [-1,1] (or is NaN) -> FASTCHEB_EDOMAIN +
+ * fastcheb_error_index (regression.jl:33).  The least-squares solve itself (`A \ Y`, regression.jl:67) is a dense
+ * QR and stays a library call on the caller's side, as it is LAPACK in the reference. */
+int fastcheb_vandermonde(int ndim, const int64_t* dims, int dtype, const void* pts, int64_t m, const double* lb,
+                         const double* ub, void* A, int64_t lda, int mem, int device, void* stream);
+
 /* ---- multi-GPU: fused evaluation + gather over NVLink ---------------------------------------------
  * One process per GPU.  The reference has no counterpart (it has no parallelism at all); these
  * entry points exist so that `c.(ys)` sharded over the GPUs of a node returns ONE result array: the gathering

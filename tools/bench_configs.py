@@ -38,7 +38,10 @@ def main():
     dev = torch.device("cuda", 0)
     peak64 = 37.0
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6400.0
+    only = os.environ.get("BENCH_ONLY")
     for name, dims, K, cplx, dt, npts in CONFIGS:
+        if only and only not in name:
+            continue
         rng = np.random.default_rng(1)
         shape = dims + ((K,) if K else ())
         c = rng.uniform(-1, 1, shape)
