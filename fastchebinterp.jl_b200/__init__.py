@@ -16,6 +16,8 @@ Reference API mirrored (file:line under /root/reference/src):
   chebpoints(order, lb, ub)     interp.jl:4-36   (host helper: grid generation is not on the device path)
   chebinterp(f, order, lb, ub)  interp.jl:163-170 (host closure f on the host grid; a ChebPoly f stays on the device)
   chebinterp(f, lb, ub)         interp.jl:174-203 (adaptive order doubling)
+  rrule, frule                  chainrules.jl:4-39 (batched pullback real(J' dy) / pushforward J dx with the
+                                Jacobian contracted inside the kernel, never written to HBM)
   chebregression, chebvandermonde  regression.jl:5-73 (the Vandermonde matrix is assembled on the device in
                                 one O(m P) pass; the dense QR solve `A \\ Y` stays a library call, LAPACK or cuSOLVER)
   roots, colleague_matrix       roots.jl:55-59, 88-110 (re-interpolation on the device, <= 50x50
@@ -36,7 +38,7 @@ import numpy as np
 from . import _capi
 from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA  # noqa: F401
 
-__all__ = ["chebregression", "chebvandermonde", "eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
+__all__ = ["rrule", "frule", "chebregression", "chebvandermonde", "eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
            "droptol", "roots", "colleague_matrix", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]
 
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
@@ -721,3 +723,73 @@ def chebregression(x, y, *args, device: int = 0) -> ChebPoly:
     dims = tuple(o + 1 for o in orders)
     coefs = C.reshape(dims + (C.shape[1],), order="F") if K is not None else C[:, 0].reshape(dims, order="F")
     return ChebPoly(coefs, lbv, ubv, device=device if not on_dev else x.device.index)
+
+
+# ------------------------------------------------------------------------------------------- AD rules
+def _tangent_call(c: ChebPoly, x, tan, mode: int):
+    """(values, contraction) for a batch of points: mode 1 = pullback real(J' dy), mode 2 = pushforward J dx."""
+    L = _capi.lib()
+    N, K, cplx = c.ndim, c.K, c.is_complex
+    E = (K or 1) * (2 if cplx else 1)
+    xa = np.asarray(x)
+    rdt = c._compute_dtype(xa.dtype if xa.dtype.kind == "f" else np.float64)
+    single = (xa.ndim == 0) if N == 1 else (xa.ndim == 1)
+    pts = np.ascontiguousarray(xa.astype(rdt, copy=False).reshape(-1, N))
+    npts = pts.shape[0]
+    ta = np.asarray(tan)
+    if mode == 1:
+        cdt = np.complex64 if rdt == np.float32 else np.complex128
+        ta = np.ascontiguousarray(ta.astype(cdt if cplx else rdt).reshape(npts, K or 1))
+        tflat = ta.view(rdt).reshape(npts, E)
+    else:
+        if np.iscomplexobj(ta):
+            raise ArgumentError("the tangent of a real point must be real")
+        tflat = np.ascontiguousarray(ta.astype(rdt).reshape(npts, N))
+    h = c._handle(rdt)
+    out_v = np.empty((npts, E), dtype=rdt)
+    out_t = np.empty((npts, N if mode == 1 else E), dtype=rdt)
+    fn = L.fastcheb_eval_vjp if mode == 1 else L.fastcheb_eval_jvp
+    rc = fn(h, pts.ctypes.data, npts, tflat.ctypes.data, out_v.ctypes.data, out_t.ctypes.data, _capi.MEM_HOST, None)
+    if rc == _capi.EDOMAIN:
+        bad = _capi.error_index()
+        err = ArgumentError(f"{pts[bad]} not in domain {c.lb} to {c.ub}")
+        err.index = bad
+        raise err
+    _check(rc, "fastcheb_eval_vjp/jvp: ")
+    cdt = np.complex64 if rdt == np.float32 else np.complex128
+    v = out_v.view(cdt) if cplx else out_v
+    v = v.reshape(npts) if K is None else v.reshape(npts, K)
+    if mode == 2:
+        t = out_t.view(cdt) if cplx else out_t
+        t = t.reshape(npts) if K is None else t.reshape(npts, K)
+    else:
+        t = out_t[:, 0] if (N == 1 and xa.ndim <= 1 and (xa.ndim == 0 or xa.shape[-1:] != (1,))) else out_t
+    return (v[0], t[0]) if single else (v, t)
+
+
+def rrule(c: ChebPoly, x):
+    """ChainRulesCore.rrule(c, x) — chainrules.jl:4-16, batched: returns (y, pullback) with
+    pullback(dy) = real(J' dy) per point (shape of x).  Each pullback call is one fused kernel launch
+    (fastcheb_eval_vjp); there is no rule for perturbing the ChebPoly itself (as in the reference)."""
+    y = c(x)
+
+    def chebpoly_pullback(dy):
+        return _tangent_call(c, x, dy, 1)[1]
+
+    return y, chebpoly_pullback
+
+
+def frule(dx, c: ChebPoly, x, dself: ChebPoly | None = None, dlb=None, dub=None):
+    """ChainRulesCore.frule((Δself, Δx), c, x) — chainrules.jl:18-39, batched: returns (y, ẏ) with ẏ = J Δx per point.
+    `dself` (a ChebPoly holding Δcoefs on c's box), `dlb`, `dub` are the optional tangents of the polynomial itself:
+    Δx' = Δx + (d2 - 1) Δlb - d2 Δub with d2 = (x - lb)/(ub - lb) (:31-32) and ẏ += Δcoefs(x) (:35-37)."""
+    xa = np.asarray(x, dtype=float)
+    dxa = np.broadcast_to(np.asarray(dx, dtype=float), xa.shape).copy()
+    if dlb is not None or dub is not None:
+        lb, ub = c.lb.astype(float), c.ub.astype(float)
+        d2 = (xa - lb) / (ub - lb)
+        dxa = dxa + (d2 - 1) * (0.0 if dlb is None else np.asarray(dlb, dtype=float)) - d2 * (0.0 if dub is None else np.asarray(dub, dtype=float))
+    y, ydot = _tangent_call(c, xa, dxa, 2)
+    if dself is not None:
+        ydot = ydot + dself(xa)
+    return y, ydot

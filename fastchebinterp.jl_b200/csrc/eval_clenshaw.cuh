@@ -48,6 +48,11 @@ struct EvalParams {
   int slabElems;         // EC * compStride
   int nstage;            // shared-memory slab buffers
   double lb[kMaxNdim], ub[kMaxNdim];
+  // Jacobian contraction (AD rules, chainrules.jl:4-39): 0 = store J; 1 = pullback, out_J[p*N + d] (+)= sum_e J[e][d] *
+  // tan[p*Etot + e] (accumulated over component groups, e0 == 0 writes); 2 = pushforward, out_J[p*Etot + e] =
+  // sum_d J[e][d] * tan[p*N + d]
+  const void* tan;
+  int mode;
 };
 
 template <typename R> struct VecOf;
@@ -361,14 +366,38 @@ struct ClenshawCta {
 #pragma unroll
         for (int p = 0; p < P; ++p)
           if (live[p]) {
+            R Js[EC][N];
 #pragma unroll
             for (int c = 0; c < EC; ++c) {
               out_v[idx[p] * prm.v_stride + prm.e0 + c] = val[p][c];
 #pragma unroll
               for (int d = 0; d < N; ++d) {
                 const R span = rsub((R)prm.ub[d], (R)prm.lb[d]);
-                out_J[idx[p] * prm.J_stride + prm.e0 + c + (long long)prm.Etot * d] =
-                    rdiv(rmul(J[p][c][d], R(2)), span);  // eval.jl:151
+                Js[c][d] = rdiv(rmul(J[p][c][d], R(2)), span);  // eval.jl:151
+              }
+            }
+            if (prm.mode == 0) {
+#pragma unroll
+              for (int c = 0; c < EC; ++c)
+#pragma unroll
+                for (int d = 0; d < N; ++d) out_J[idx[p] * prm.J_stride + prm.e0 + c + (long long)prm.Etot * d] = Js[c][d];
+            } else if (prm.mode == 1) {  // pullback: real(J' * dy), chainrules.jl:7,14
+              const R* dy = reinterpret_cast<const R*>(prm.tan) + idx[p] * prm.Etot + prm.e0;
+#pragma unroll
+              for (int d = 0; d < N; ++d) {
+                R acc = prm.e0 == 0 ? R(0) : out_J[idx[p] * N + d];
+#pragma unroll
+                for (int c = 0; c < EC; ++c) acc = rfma(Js[c][d], dy[c], acc);
+                out_J[idx[p] * N + d] = acc;
+              }
+            } else {  // pushforward: J * dx, chainrules.jl:24
+              const R* dx = reinterpret_cast<const R*>(prm.tan) + idx[p] * N;
+#pragma unroll
+              for (int c = 0; c < EC; ++c) {
+                R acc = R(0);
+#pragma unroll
+                for (int d = 0; d < N; ++d) acc = rfma(Js[c][d], dx[d], acc);
+                out_J[idx[p] * prm.Etot + prm.e0 + c] = acc;
               }
             }
           }

@@ -71,7 +71,8 @@ int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
 }
 
 int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
-              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st) {
+              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
+                const void* tan) {
   const DmmaPlan& pl = p->dmma;
   DmmaFn fn = dmma_fn(pl.KS, jac);
   if (!fn) return fail(FASTCHEB_EUNSUPPORTED, "no DMMA instantiation for KS = %d", pl.KS);
@@ -89,6 +90,8 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
     prm.idx_base = idx_base;
     prm.v_stride = v_stride;
     prm.J_stride = J_stride;
+    prm.mode = mode;
+    prm.tan = tan;
     prm.e0 = g.e0;
     prm.Etot = p->E;
     for (int d = 0; d < p->ndim; ++d) {

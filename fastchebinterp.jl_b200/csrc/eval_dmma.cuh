@@ -49,6 +49,8 @@ struct DmmaParams {
   int nstage;
   int tabStride;  // doubles per point row of the weight tables
   double lb[kMaxNdim], ub[kMaxNdim];
+  const void* tan;  // Jacobian contraction operand (see EvalParams::mode in eval_clenshaw.cuh)
+  int mode;
 #ifdef FC_PROFILE
   long long* prof;  // experiment: per-warp cycle counters
 #endif
@@ -455,13 +457,38 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
       for (int mt = 0; mt < MT; ++mt)
         if (live[mt]) {
 #pragma unroll
-          for (int e = 0; e < EC; ++e) {
-            prm.out_v[idx[mt] * prm.v_stride + prm.e0 + e] = acc[mt][e];
-            if constexpr (JAC) {
+          for (int e = 0; e < EC; ++e) prm.out_v[idx[mt] * prm.v_stride + prm.e0 + e] = acc[mt][e];
+          if constexpr (JAC) {
+            double Js[EC][N];
+#pragma unroll
+            for (int e = 0; e < EC; ++e)
 #pragma unroll
               for (int d = 0; d < N; ++d)
-                prm.out_J[idx[mt] * prm.J_stride + prm.e0 + e + (long long)prm.Etot * d] =
-                    __ddiv_rn(__dmul_rn(accJ[mt][e][d], 2.0), __dsub_rn(prm.ub[d], prm.lb[d]));  // eval.jl:151
+                Js[e][d] = __ddiv_rn(__dmul_rn(accJ[mt][e][d], 2.0), __dsub_rn(prm.ub[d], prm.lb[d]));  // eval.jl:151
+            if (prm.mode == 0) {
+#pragma unroll
+              for (int e = 0; e < EC; ++e)
+#pragma unroll
+                for (int d = 0; d < N; ++d)
+                  prm.out_J[idx[mt] * prm.J_stride + prm.e0 + e + (long long)prm.Etot * d] = Js[e][d];
+            } else if (prm.mode == 1) {  // pullback real(J' * dy), chainrules.jl:7,14 (accumulated over component groups)
+              const double* dy = reinterpret_cast<const double*>(prm.tan) + idx[mt] * prm.Etot + prm.e0;
+#pragma unroll
+              for (int d = 0; d < N; ++d) {
+                double a = prm.e0 == 0 ? 0.0 : prm.out_J[idx[mt] * N + d];
+#pragma unroll
+                for (int e = 0; e < EC; ++e) a = fma(Js[e][d], dy[e], a);
+                prm.out_J[idx[mt] * N + d] = a;
+              }
+            } else {  // pushforward J * dx, chainrules.jl:24
+              const double* dx = reinterpret_cast<const double*>(prm.tan) + idx[mt] * N;
+#pragma unroll
+              for (int e = 0; e < EC; ++e) {
+                double a = 0.0;
+#pragma unroll
+                for (int d = 0; d < N; ++d) a = fma(Js[e][d], dx[d], a);
+                prm.out_J[idx[mt] * prm.Etot + prm.e0 + e] = a;
+              }
             }
           }
         }

@@ -20,6 +20,7 @@ cudaError_t dmma_dispatch_ks16_jac(int op, int ndim, int ec, const DmmaParams& p
 // decide whether the handle gets a DMMA plan and build the fragment stream (no-op when not applicable)
 int dmma_plan(fastcheb_poly* p, cudaStream_t st);
 int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
-              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st);
+              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode = 0,
+                const void* tan = nullptr);
 
 }  // namespace fastcheb

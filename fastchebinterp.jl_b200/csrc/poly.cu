@@ -101,7 +101,8 @@ ClenshawFn clenshaw_fn(int dtype, bool jac) {
 }
 
 int eval_clenshaw(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
-                  int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st) {
+                  int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
+                const void* tan) {
   if (p->ndim > kMaxKernelNdim)
     return fail(FASTCHEB_EUNSUPPORTED, "ndim = %d: evaluation kernels cover ndim <= %d", p->ndim, kMaxKernelNdim);
   ClenshawFn fn = clenshaw_fn(p->dtype, jac);
@@ -118,6 +119,8 @@ int eval_clenshaw(const fastcheb_poly* p, const void* pts, int64_t npts, void* o
     prm.idx_base = idx_base;
     prm.v_stride = v_stride;
     prm.J_stride = J_stride;
+    prm.mode = mode;
+    prm.tan = tan;
     prm.e0 = g.e0;
     prm.Etot = p->E;
     for (int d = 0; d < p->ndim; ++d) {
@@ -163,11 +166,12 @@ bool use_dmma(const fastcheb_poly* p, bool jac) {
 namespace fastcheb {
 
 int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
-                int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st) {
+                int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
+                const void* tan) {
   if (npts == 0) return FASTCHEB_OK;
   if (use_dmma(p, jac))
-    return dmma_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st);
-  return eval_clenshaw(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st);
+    return dmma_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
+  return eval_clenshaw(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
 }
 
 int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
@@ -492,6 +496,79 @@ int fastcheb_eval_jac_async(const fastcheb_poly* p, const void* pts_dev, int64_t
   if (status_dev) FC_CUDA(set_flag_async((long long*)status_dev, kNoBad, st));
   return eval_device(p, pts_dev, npts, out_v_dev, p->E, out_J_dev, (int64_t)p->E * p->ndim, true,
                      (long long*)status_dev, 0, st);
+}
+
+}  // extern "C"
+
+// ---- batched AD rules (chainrules.jl:4-39): the Jacobian is contracted inside the kernel, never written to HBM ----
+namespace {
+// mode 1: pullback  xbar[p, :] = real(J_p' * dy[p, :])   (tan: npts x E reals, out_t: npts x ndim)
+// mode 2: pushforward ydot[p, :] = J_p * dx[p, :]         (tan: npts x ndim,    out_t: npts x E reals)
+int eval_tangent(const fastcheb_poly* p, const void* pts, int64_t npts, const void* tan, void* out_v, void* out_t,
+                 int mode, int mem, void* stream) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  if (npts < 0) return fail(FASTCHEB_EINVAL, "npts < 0");
+  if (npts == 0) return FASTCHEB_OK;
+  if (!pts || !tan || !out_v || !out_t) return fail(FASTCHEB_EINVAL, "null buffer");
+  if (mem != FASTCHEB_MEM_HOST && mem != FASTCHEB_MEM_DEVICE) return fail(FASTCHEB_EINVAL, "bad mem %d", mem);
+  DeviceGuard dg(p->device);
+  if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rs = real_size(p->dtype);
+  const int N = p->ndim, E = p->E;
+  const size_t tan_pp = (size_t)(mode == 1 ? E : N) * rs, out_pp = (size_t)(mode == 1 ? N : E) * rs;
+  FlagSlot fs;
+  FC_TRY(flag_acquire(p->device, &fs));
+  struct Rel {
+    FlagSlot& f;
+    ~Rel() { flag_release(f); }
+  } rel{fs};
+  FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+  if (mem == FASTCHEB_MEM_DEVICE) {
+    FC_TRY(eval_device(p, pts, npts, out_v, E, out_t, 0, true, fs.dev, 0, st, mode, tan));
+  } else {
+    const size_t per = (size_t)N * rs + tan_pp + (size_t)E * rs + out_pp;
+    const int64_t chunk = std::min<int64_t>(npts, std::max<int64_t>(1 << 16, (int64_t)((size_t(256) << 20) / per)));
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t b_in = al((size_t)chunk * N * rs), b_tan = al((size_t)chunk * tan_pp), b_v = al((size_t)chunk * E * rs);
+    char* buf = (char*)ws_acquire(p->device, b_in + b_tan + b_v + al((size_t)chunk * out_pp));
+    if (!buf) return fail(FASTCHEB_ENOMEM, "device staging buffer");
+    int rc = FASTCHEB_OK;
+    cudaError_t ce = cudaSuccess;
+    for (int64_t done = 0; done < npts && rc == FASTCHEB_OK && ce == cudaSuccess; done += chunk) {
+      const int64_t m = std::min<int64_t>(chunk, npts - done);
+      char *d_in = buf, *d_tan = buf + b_in, *d_v = d_tan + b_tan, *d_t = d_v + b_v;
+      ce = cudaMemcpyAsync(d_in, (const char*)pts + (size_t)done * N * rs, (size_t)m * N * rs, cudaMemcpyHostToDevice, st);
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync(d_tan, (const char*)tan + (size_t)done * tan_pp, (size_t)m * tan_pp, cudaMemcpyHostToDevice, st);
+      if (ce != cudaSuccess) break;
+      rc = eval_device(p, d_in, m, d_v, E, d_t, 0, true, fs.dev, done, st, mode, d_tan);
+      if (rc != FASTCHEB_OK) break;
+      ce = cudaMemcpyAsync((char*)out_v + (size_t)done * E * rs, d_v, (size_t)m * E * rs, cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess)
+        ce = cudaMemcpyAsync((char*)out_t + (size_t)done * out_pp, d_t, (size_t)m * out_pp, cudaMemcpyDeviceToHost, st);
+    }
+    cudaStreamSynchronize(st);
+    ws_release(p->device, buf);
+    if (rc != FASTCHEB_OK) return rc;
+    if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged tangent evaluation failed: %s", cudaGetErrorString(ce));
+  }
+  FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaStreamSynchronize(st));
+  return check_flag(*fs.host, p);
+}
+}  // namespace
+
+extern "C" {
+
+int fastcheb_eval_vjp(const fastcheb_poly* p, const void* pts, int64_t npts, const void* dy, void* out_v, void* out_xbar,
+                      int mem, void* stream) {
+  return eval_tangent(p, pts, npts, dy, out_v, out_xbar, 1, mem, stream);
+}
+
+int fastcheb_eval_jvp(const fastcheb_poly* p, const void* pts, int64_t npts, const void* dx, void* out_v, void* out_ydot,
+                      int mem, void* stream) {
+  return eval_tangent(p, pts, npts, dx, out_v, out_ydot, 2, mem, stream);
 }
 
 }  // extern "C"

@@ -53,7 +53,8 @@ struct fastcheb_poly {
 namespace fastcheb {
 // enqueue a batched evaluation on `st`; all pointers are device pointers on p->device.
 int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
-                int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st);
+                int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode = 0,
+                const void* tan = nullptr);
 // build the handle from coefficients already on the device (Julia layout); takes no ownership of d_src
 int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
                        const void* d_src, const double* lb, const double* ub, int device, cudaStream_t st);

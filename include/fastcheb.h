@@ -124,6 +124,19 @@ int fastcheb_eval_async(const fastcheb_poly* p, const void* pts_dev, int64_t npt
 int fastcheb_eval_jac_async(const fastcheb_poly* p, const void* pts_dev, int64_t npts, void* out_v_dev,
                             void* out_J_dev, int64_t* status_dev, void* stream);
 
+/* Batched AD rules of c(x) (chainrules.jl:4-39) with the Jacobian contracted inside the kernel — it is never written
+ * to HBM (24 B instead of 96 B of output per point for the headline polynomial):
+ * fastcheb_eval_vjp : rrule pullback, out_xbar[p, :] = real(J_p' * dy[p, :])   (chainrules.jl:7,14); dy is npts x E
+ *                     reals (complex cotangents as re,im pairs), out_xbar npts x ndim.
+ * fastcheb_eval_jvp : frule,          out_ydot[p, :] = J_p * dx[p, :]          (chainrules.jl:24); dx is npts x ndim,
+ *                     out_ydot npts x E.  (The reference's extra terms for a perturbed ChebPoly, chainrules.jl:27-37,
+ *                     are one more jvp with a shifted dx plus one fastcheb_eval of the coefficient tangent.)
+ * out_v (npts x E) receives the values.  Synchronous; EDOMAIN as for fastcheb_eval. */
+int fastcheb_eval_vjp(const fastcheb_poly* p, const void* pts, int64_t npts, const void* dy, void* out_v, void* out_xbar,
+                      int mem, void* stream);
+int fastcheb_eval_jvp(const fastcheb_poly* p, const void* pts, int64_t npts, const void* dx, void* out_v, void* out_ydot,
+                      int mem, void* stream);
+
 /* fastcheb_eval_many : many independent 1-D polynomials, each evaluated at its own points, in one launch — the
  * reference spells this `[c.(xs) for (c, xs) in zip(cs, xss)]` with (::ChebPoly{1})(x) eval.jl:63-70 per point (and
  * chebgradient eval.jl:174-177 when out_d != NULL: d/dx of every component).  `coefs` holds `howmany` coefficient
