@@ -144,15 +144,47 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
 
   const int c = lane & 3;   // column pair inside a tile / k index inside a k-step
   const int r = lane >> 2;  // point row inside an M tile
-  double* tab = tables + (size_t)warp * ROWS * prm.tabStride * NTAB;  // [row][tabStride] (+ derivative copy)
+  // Weight tables of this warp (+ a derivative copy for the Jacobian), two layouts chosen at compile time from
+  // measurements (profiles/r01_configs.jsonl):
+  //   plain  [point row][k]      — one 8-byte load per M tile; fastest for the 3-D K=3 value kernel (91.9 % vs 86.9 %)
+  //   paired [row r][k][mt]      — the MT points a lane owns (rows r, r+8, ..) side by side, one 16-byte load serves
+  //                                both M tiles; wins wherever the weights are a larger share of the tile: Jacobians,
+  //                                >= 3 weighted dimensions (4-D: 72 % vs 66 %), scalar-valued 3-D
+  constexpr bool PAIRED = JAC || ND >= 3 || (ND == 2 && EC < 3);
+  // (code generation of the tile loop is sensitive to how these pointers are formed: the two layouts are kept as two
+  // literal code paths, and the plain one is the form that was measured at 91.9 %)
+  double* tab = tables + (size_t)warp * ROWS * prm.tabStride * NTAB;
   double* dtab = tab + (size_t)ROWS * prm.tabStride;
   const double* trow[MT];
   const double* drow[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
-    trow[mt] = tab + (size_t)(mt * 8 + r) * prm.tabStride;
-    drow[mt] = dtab + (size_t)(mt * 8 + r) * prm.tabStride;
+    if constexpr (PAIRED) {
+      trow[mt] = tab + (size_t)r * prm.tabStride * MT + mt;
+      drow[mt] = dtab + (size_t)r * prm.tabStride * MT + mt;
+    } else {
+      trow[mt] = tab + (size_t)(mt * 8 + r) * prm.tabStride;
+      drow[mt] = dtab + (size_t)(mt * 8 + r) * prm.tabStride;
+    }
   }
+  struct TV {
+    double v[MT];
+  };
+  auto tload = [&](const double* const (&rows)[MT], int k) {
+    TV t;
+    if constexpr (PAIRED && MT == 2) {
+      const double2 q = *reinterpret_cast<const double2*>(rows[0] + 2 * k);
+      t.v[0] = q.x;
+      t.v[1] = q.y;
+    } else if constexpr (PAIRED) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) t.v[mt] = rows[mt][k * MT];
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) t.v[mt] = rows[mt][k];
+    }
+    return t;
+  };
 
   // weights of the two columns this lane owns in the tile whose record starts at `rec`
   struct Weights {
@@ -161,37 +193,40 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
   };
   auto weights = [&](const double* rec, Weights& W) {
     const int2* meta = reinterpret_cast<const int2*>(rec);
+    TV t0[ND], t1[ND];
     int2 ix[ND];
 #pragma unroll
-    for (int d = 0; d < ND; ++d) ix[d] = meta[d * 4 + c];
+    for (int d = 0; d < ND; ++d) {
+      ix[d] = meta[d * 4 + c];
+      t0[d] = tload(trow, ix[d].x);
+      t1[d] = tload(trow, ix[d].y);
+    }
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      double t0[ND], t1[ND];
-#pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        t0[d] = trow[mt][ix[d].x];
-        t1[d] = trow[mt][ix[d].y];
-      }
-      double w0 = t0[0], w1 = t1[0];
+      double w0 = t0[0].v[mt], w1 = t1[0].v[mt];
 #pragma unroll
       for (int d = 1; d < ND; ++d) {
-        w0 *= t0[d];
-        w1 *= t1[d];
+        w0 *= t0[d].v[mt];
+        w1 *= t1[d].v[mt];
       }
       W.w[mt][0] = w0;
       W.w[mt][1] = w1;
-      if constexpr (JAC) {
+    }
+    if constexpr (JAC) {
 #pragma unroll
-        for (int dd = 0; dd < ND; ++dd) {
-          double x0 = drow[mt][ix[dd].x], x1 = drow[mt][ix[dd].y];
+      for (int dd = 0; dd < ND; ++dd) {
+        const TV x0 = tload(drow, ix[dd].x), x1 = tload(drow, ix[dd].y);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          double y0 = x0.v[mt], y1 = x1.v[mt];
 #pragma unroll
           for (int d = 0; d < ND; ++d)
             if (d != dd) {
-              x0 *= t0[d];
-              x1 *= t1[d];
+              y0 *= t0[d].v[mt];
+              y1 *= t1[d].v[mt];
             }
-          W.wd[mt][0][dd + 1] = x0;
-          W.wd[mt][1][dd + 1] = x1;
+          W.wd[mt][0][dd + 1] = y0;
+          W.wd[mt][1][dd + 1] = y1;
         }
       }
     }
@@ -255,8 +290,15 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
       for (int d = 0; d < ND; ++d) {
         const double zz = z[d + 1], z2 = 2.0 * zz;
         double tkm = 1.0, tk = zz, dkm = 0.0, dk = 1.0;
-        double* tr = tab + (size_t)(mt * 8 + r) * prm.tabStride + o;
-        double* dr = dtab + (size_t)(mt * 8 + r) * prm.tabStride + o;
+        double* tr;
+        double* dr;
+        if constexpr (PAIRED) {
+          tr = tab + ((size_t)r * prm.tabStride + o) * MT + mt;
+          dr = dtab + ((size_t)r * prm.tabStride + o) * MT + mt;
+        } else {
+          tr = tab + (size_t)(mt * 8 + r) * prm.tabStride + o;
+          dr = dtab + (size_t)(mt * 8 + r) * prm.tabStride + o;
+        }
         const int nd = prm.n[d + 1];
         o += nd;
         if (c == 0) {
@@ -265,8 +307,13 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
         }
         for (int k = 1; k < nd; ++k) {
           if ((k & 3) == c) {
-            tr[k] = tk;
-            if constexpr (JAC) dr[k] = dk;
+            if constexpr (PAIRED) {
+              tr[k * MT] = tk;
+              if constexpr (JAC) dr[k * MT] = dk;
+            } else {
+              tr[k] = tk;
+              if constexpr (JAC) dr[k] = dk;
+            }
           }
           const double tn = fma(z2, tk, -tkm);
           if constexpr (JAC) {
@@ -295,61 +342,50 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
         }
       }
 
-    // first stage of the pass
-    wait_stage(v, b, ph);
-    const double* rec = stages + (size_t)b * stageDoubles;
-    Weights W;
-    weights(rec, W);
     // Software pipelining of the weighted reduction: the DFMAs that fold a finished G chain into the per-lane sums
     // depend on the chain's last DMMA, and an in-order warp that waits for that latency cannot issue the next
     // (independent) chain.  So chain e is folded only after chain e+1 has been issued; the last chain of a tile is
-    // folded after the first chain of the next tile, with the weights (Wp) of the tile it belongs to.
+    // folded after the first chain of the next tile — W still holds that tile's weights then, and the weights of the
+    // new tile are loaded right after (their first use is a whole chain away).
     double pg0[MT], pg1[MT];
-    double ph0[JAC ? MT : 1], ph1[JAC ? MT : 1];
-    Weights Wp = W;
+    [[maybe_unused]] double ph0[JAC ? MT : 1], ph1[JAC ? MT : 1];
+    Weights W;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
       pg0[mt] = pg1[mt] = 0.0;
-      if constexpr (JAC) ph0[mt] = ph1[mt] = 0.0;
+      W.w[mt][0] = W.w[mt][1] = 0.0;
+      if constexpr (JAC) {
+        ph0[mt] = ph1[mt] = 0.0;
+#pragma unroll
+        for (int d = 0; d < N; ++d) W.wd[mt][0][d] = W.wd[mt][1][d] = 0.0;
+      }
     }
-    auto fold = [&](auto ec, const Weights& Wf) {  // fold the pending chain of component `ec` with weights Wf
+    auto fold = [&](auto ec) {  // fold the pending chain (component `ec`) with the weights in W
       constexpr int e = decltype(ec)::value;
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        acc[mt][e] = fma(pg0[mt], Wf.w[mt][0], acc[mt][e]);
-        acc[mt][e] = fma(pg1[mt], Wf.w[mt][1], acc[mt][e]);
+        acc[mt][e] = fma(pg0[mt], W.w[mt][0], acc[mt][e]);
+        acc[mt][e] = fma(pg1[mt], W.w[mt][1], acc[mt][e]);
         if constexpr (JAC) {
-          accJ[mt][e][0] = fma(ph0[mt], Wf.w[mt][0], accJ[mt][e][0]);
-          accJ[mt][e][0] = fma(ph1[mt], Wf.w[mt][1], accJ[mt][e][0]);
+          accJ[mt][e][0] = fma(ph0[mt], W.w[mt][0], accJ[mt][e][0]);
+          accJ[mt][e][0] = fma(ph1[mt], W.w[mt][1], accJ[mt][e][0]);
 #pragma unroll
           for (int d = 1; d < N; ++d) {
-            accJ[mt][e][d] = fma(pg0[mt], Wf.wd[mt][0][d], accJ[mt][e][d]);
-            accJ[mt][e][d] = fma(pg1[mt], Wf.wd[mt][1][d], accJ[mt][e][d]);
+            accJ[mt][e][d] = fma(pg0[mt], W.wd[mt][0][d], accJ[mt][e][d]);
+            accJ[mt][e][d] = fma(pg1[mt], W.wd[mt][1][d], accJ[mt][e][d]);
           }
         }
       }
     };
-    int tin = 0;  // tile index inside the current stage
-    int nt = prm.ntiles < prm.tilesPerStage ? prm.ntiles : prm.tilesPerStage;
+    const double* rec = nullptr;
+    int tin = 0, nt = 0;  // tile index inside the current stage, tiles in the current stage
     for (int tile = 0; tile < prm.ntiles; ++tile) {
-      // ---- where is the next tile's record?  (crossing into the next stage waits for it one tile early)
-      const bool last_in_stage = tin + 1 == nt;
-      const bool has_next = tile + 1 < prm.ntiles;
-      const double* rec_next = rec + TR;
-      int nb = b;
-      uint32_t nph = ph;
-      if (last_in_stage) {
-        nb = b + 1 == ns ? 0 : b + 1;
-        nph = nb == 0 ? ph ^ 1u : ph;
-        if (has_next) {
-          wait_stage(v + 1, nb, nph);
-          rec_next = stages + (size_t)nb * stageDoubles;
-        } else {
-          rec_next = rec;  // harmless recomputation of this tile's weights
-        }
+      if (tin == 0) {  // entering a stage
+        wait_stage(v, b, ph);
+        rec = stages + (size_t)b * stageDoubles;
+        const int left = prm.ntiles - tile;
+        nt = left < prm.tilesPerStage ? left : prm.tilesPerStage;
       }
-      // ---- one basic block: the DMMA chains of this tile, the deferred folds, the weights of the next tile
-      Weights Wn;
       auto chain = [&](auto ec) {
         constexpr int e = decltype(ec)::value;
         const double* u = rec + kDmmaMeta + e * U;
@@ -372,10 +408,8 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
           }
         }
         // the previous chain has long finished: fold it now, then this chain becomes the pending one
-        if constexpr (e == 0)
-          fold(std::integral_constant<int, EC - 1>{}, Wp);
-        else
-          fold(std::integral_constant<int, (e > 0 ? e - 1 : 0)>{}, W);
+        fold(std::integral_constant<int, (e == 0 ? EC - 1 : e - 1)>{});
+        if constexpr (e == 0) weights(rec, W);  // the pending chain of the previous tile is folded: W moves on to this tile
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           pg0[mt] = g0[mt];
@@ -387,14 +421,11 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
         }
       };
       chain(std::integral_constant<int, 0>{});
-      weights(rec_next, Wn);
       if constexpr (EC > 1) chain(std::integral_constant<int, 1>{});
       if constexpr (EC > 2) chain(std::integral_constant<int, 2>{});
-      Wp = W;
-      W = Wn;
-      rec = rec_next;
+      rec += TR;
       // ---- release the stage after its last tile; the last warp out refills the buffer
-      if (last_in_stage) {
+      if (++tin == nt) {
         __syncwarp();
         if (lane == 0) {
           __threadfence_block();
@@ -413,16 +444,14 @@ __global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __
           }
         }
         ++v;
-        b = nb;
-        ph = nph;
+        if (++b == ns) {
+          b = 0;
+          ph ^= 1u;
+        }
         tin = 0;
-        const int left = prm.ntiles - (tile + 1);
-        nt = left < prm.tilesPerStage ? left : prm.tilesPerStage;
-      } else {
-        ++tin;
       }
     }
-    fold(std::integral_constant<int, EC - 1>{}, Wp);  // the last chain of the pass
+    fold(std::integral_constant<int, EC - 1>{});  // the last chain of the pass
 
     // ---- quad reduction and store ----
 #pragma unroll

@@ -1,5 +1,11 @@
 mkdir -p gpurun_out
-for N in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_val_${N}gpu.json 2> gpurun_out/bench_val_${N}gpu.err; tail -2 gpurun_out/bench_val_${N}gpu.err; cat gpurun_out/bench_val_${N}gpu.json
-done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 10 --warmup 3 --workload fit1d --no-cpu --no-e2e > gpurun_out/bench_fit_8gpu.json 2> gpurun_out/bench_fit_8gpu.err; tail -2 gpurun_out/bench_fit_8gpu.err; cat gpurun_out/bench_fit_8gpu.json
+timeout 1200 python -m pytest tests/test_gpu_eval.py tests/test_gpu_golden.py tests/test_gpu_fullsize.py tests/test_gpu_adrules.py -m gpu -q -x 2>&1 | tail -4
+python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_val.json 2> gpurun_out/bench_val.err; tail -3 gpurun_out/bench_val.err; grep -o '"value": [0-9.]*\|"frac": [0-9.]*' gpurun_out/bench_val.json
+python bench.py --steps 5 --warmup 3 --mode jac --no-cpu --no-e2e > gpurun_out/bench_jac.json 2> gpurun_out/bench_jac.err; tail -3 gpurun_out/bench_jac.err; grep -o '"value": [0-9.]*\|"frac": [0-9.]*' gpurun_out/bench_jac.json
+python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; tail -3 gpurun_out/configs.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/configs.jsonl'):
+    d=json.loads(l)
+    if d['algo']=='dmma': print(f"{d['config']:48s} {d['algo']:8s} {d['mode']} {d['points_per_s']:.3e} pts/s  fp {d['frac_of_fp_peak']*100:5.1f}%")
+PY
