@@ -12,7 +12,10 @@ using namespace fastcheb;
 
 int main(int argc, char** argv) {
   const long long npts = argc > 1 ? atoll(argv[1]) : (1ll << 22);
-  constexpr int N = 3, EC = 3, KS = 8, n = 33;
+#ifndef FC_EC
+#define FC_EC 3
+#endif
+  constexpr int N = 3, EC = FC_EC, KS = 8, n = 33;  // -DFC_EC=1: scalar-valued 3-D
   const int M = n * n, ntiles = (M + 7) / 8, U = KS * 32 + 8, TR = kDmmaMeta + EC * U;
   std::vector<double> coefs((size_t)EC * n * n * n), pts((size_t)npts * 3);
   srand(1);
@@ -20,7 +23,7 @@ int main(int argc, char** argv) {
   for (auto& p : pts) p = rand() / (double)RAND_MAX * 2 - 1;
   double *d_c, *d_f, *d_p, *d_o;
   CK(cudaMalloc(&d_c, coefs.size() * 8)); CK(cudaMalloc(&d_f, (size_t)ntiles * TR * 8));
-  CK(cudaMalloc(&d_p, pts.size() * 8)); CK(cudaMalloc(&d_o, (size_t)npts * 3 * 8));
+  CK(cudaMalloc(&d_p, pts.size() * 8)); CK(cudaMalloc(&d_o, (size_t)npts * EC * 8));
   CK(cudaMemcpy(d_c, coefs.data(), coefs.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_p, pts.data(), pts.size() * 8, cudaMemcpyHostToDevice));
   FragDims fd; memset(&fd, 0, sizeof fd); fd.nd = 2; fd.n[0] = n; fd.n[1] = n; fd.toff[0] = 0; fd.toff[1] = n;
@@ -35,7 +38,7 @@ int main(int argc, char** argv) {
   for (int warps : {8, 12, 16}) for (int tps : {1, 2, 4}) for (int ns : {3, 4, 6}) {
 #endif
     DmmaParams prm; memset(&prm, 0, sizeof prm);
-    prm.frag = d_f; prm.pts = d_p; prm.out_v = d_o; prm.npts = npts; prm.v_stride = 3; prm.Etot = 3;
+    prm.frag = d_f; prm.pts = d_p; prm.out_v = d_o; prm.npts = npts; prm.v_stride = EC; prm.Etot = EC;
     prm.n[0] = prm.n[1] = prm.n[2] = n; prm.ntiles = ntiles; prm.M = M; prm.tilesPerStage = tps; prm.nstage = ns;
     prm.tabStride = tabStride;
     for (int d = 0; d < 3; ++d) { prm.lb[d] = -1; prm.ub[d] = 1; }
@@ -62,7 +65,7 @@ int main(int argc, char** argv) {
 #else
            0,
 #endif
-           warps, bps, tps, ns, smem, ms, rate, rate * 222354 / 37.0e12);
+           warps, bps, tps, ns, smem, ms, rate, rate * (74118.0 * EC) / 37.0e12);
     fflush(stdout);
 #ifdef FC_PROFILE
     { long long hp[64]; CK(cudaMemcpy(hp, d_prof, sizeof hp, cudaMemcpyDeviceToHost));

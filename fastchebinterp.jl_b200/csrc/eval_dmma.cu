@@ -103,7 +103,7 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
     prm.M = pl.M;
     prm.tabStride = pl.tabStride;
     // warps per CTA: as many as the instantiation allows, fewer for small batches (spread over the SMs)
-    int warps = dmma_max_warps(jac);
+    int warps = dmma_max_warps(g.ec, pl.KS, jac);
     const long long per_sm = (npts + (long long)p->di->sms * rows - 1) / ((long long)p->di->sms * rows);
     if (per_sm < warps) warps = (int)std::max<long long>(1, per_sm);
     const size_t unitBytes = (size_t)(kDmmaMeta + g.ec * U) * 8;  // one tile record

@@ -62,11 +62,13 @@ struct DmmaParams {
 constexpr int kDmmaMT = FC_DMMA_MT;  // 8-point M tiles per warp
 constexpr int kDmmaMeta = 16;  // doubles of metadata per tile record (8 columns x up to 3 dims x int32, padded)
 
-#ifndef FC_DMMA_MAXT
-#define FC_DMMA_MAXT 512
-#endif
+// Threads per CTA the instantiation is compiled for: the value kernels with few accumulators leave registers for more
+// warps (the tile loop is latency-bound per warp when a tile has only 16 DMMAs, so more warps per SM pay directly).
+__host__ __device__ constexpr int dmma_max_threads(int EC, int KS, bool JAC) {
+  return JAC ? 256 : (KS <= 4 ? 768 : (KS <= 8 && EC < 3 ? 640 : 512));
+}
 template <int N, int EC, int KS, bool JAC>
-__global__ void __launch_bounds__(JAC ? 256 : FC_DMMA_MAXT) dmma_kernel(const __grid_constant__ DmmaParams prm) {
+__global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(const __grid_constant__ DmmaParams prm) {
   constexpr int MT = kDmmaMT;
   constexpr int U = KS * 32 + 8;
   constexpr int TR = kDmmaMeta + EC * U;  // doubles per tile record

@@ -7,7 +7,7 @@ namespace fastcheb {
 
 constexpr int kDmmaMaxEC = 3;
 
-inline int dmma_max_warps(bool jac) { return jac ? 8 : 16; }
+inline int dmma_max_warps(int ec, int ks, bool jac) { return dmma_max_threads(ec, ks, jac) / 32; }
 
 // per-(KS, JAC) translation units: op 0 = launch, op 1 = occupancy query
 cudaError_t dmma_dispatch_ks4_val(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
