@@ -8,7 +8,7 @@ template <int N, int EC>
 cudaError_t go(int op, const EvalParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps) {
   constexpr int P = FC_JAC ? kClenshawPtsJac : kClenshawPtsVal;
   auto kern = clenshaw_kernel<FC_REAL, N, EC, P, FC_JAC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
   if (e != cudaSuccess) return e;
   if (op == kOpOccupancy) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
   kern<<<grid, threads, smem, st>>>(prm);

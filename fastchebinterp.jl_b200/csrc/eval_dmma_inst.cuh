@@ -6,7 +6,7 @@ namespace {
 template <int N, int EC>
 cudaError_t go(int op, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps) {
   auto kern = dmma_kernel<N, EC, FC_KS, FC_JAC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
   if (e != cudaSuccess) return e;
   if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
   kern<<<grid, threads, smem, st>>>(prm);

@@ -116,7 +116,7 @@ cudaError_t launch(const ManyParams& prm, int sms, cudaStream_t st) {
   const int warps = 8;
   const size_t smem = (size_t)warps * prm.n * E * sizeof(R);
   auto kern = eval_many_kernel<R, E, P, DER>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
   if (e != cudaSuccess) return e;
   int bps = 1;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, warps * 32, smem);

@@ -85,7 +85,7 @@ int get_afrag(int dev, int n, AFrag* out) {
 template <typename R, int KO, int KB, int KC, int NT, bool E1>
 cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
   auto kern = fit_dmma_kernel<R, KO, KB, KC, NT, E1>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
   if (e != cudaSuccess) return e;
   if (bps) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
   kern<<<grid, threads, smem, st>>>(prm);

@@ -75,6 +75,11 @@ cudaError_t set_flag_async(long long* dev_flag, long long value, cudaStream_t st
 void note_launch(int n = 1);
 long long launch_count();
 
+// Dynamic shared-memory ceiling requested for every kernel (the sm_100 opt-in maximum).  The attribute is per kernel
+// and process-wide: setting it to the launch's own size would race between host threads that launch the same
+// instantiation with different sizes, so every launch site sets this one value.
+constexpr int kSmemOptinMax = 232448;
+
 inline size_t real_size(int dtype) { return dtype == FASTCHEB_F64 ? 8 : 4; }
 
 }  // namespace fastcheb

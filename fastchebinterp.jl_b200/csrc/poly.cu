@@ -380,7 +380,9 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
     out_pp = (size_t)o.v_stride * rs;
   else
     out_pp = (size_t)E * rs + (jac ? (size_t)E * N * rs : 0);
-  int64_t chunk = std::min<int64_t>(npts, std::max<int64_t>(1 << 16, (int64_t)((size_t(256) << 20) / (in_pp + out_pp))));
+  // chunks of ~64 MB (points + results): small enough that the first upload and the last download are a few percent of
+  // the call, large enough (>= 1 M points) that the persistent kernel stays efficient
+  int64_t chunk = std::min<int64_t>(npts, std::max<int64_t>(1 << 16, (int64_t)((size_t(64) << 20) / (in_pp + out_pp))));
   const int nbuf = npts > chunk ? 2 : 1;
   cudaStream_t ss[2] = {nullptr, nullptr};
   void* dbuf[2] = {nullptr, nullptr};
