@@ -27,10 +27,10 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(d_c, coefs.data(), coefs.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_p, pts.data(), pts.size() * 8, cudaMemcpyHostToDevice));
   FragDims fd; memset(&fd, 0, sizeof fd); fd.nd = 2; fd.n[0] = n; fd.n[1] = n; fd.toff[0] = 0; fd.toff[1] = n;
-  relayout_frag_kernel<0><<<512, 256>>>(d_c, d_f, (long long)ntiles * TR, EC, 0, EC, n, M, KS, fd);
+  relayout_frag_kernel<double><<<512, 256>>>(d_c, d_f, (long long)ntiles * TR, EC, 0, EC, n, M, KS, fd);
   CK(cudaDeviceSynchronize());
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
-  auto kern = dmma_kernel<N, EC, KS, false>;
+  auto kern = dmma_kernel<double, N, EC, KS, false>;
   const int rows = kDmmaMT * 8, tabStride = (2 * n) | 1;
   #ifdef FC_PROFILE
   for (int warps : {16}) for (int tps : {1, 4}) for (int ns : {3}) {

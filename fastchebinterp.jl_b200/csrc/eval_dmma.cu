@@ -6,7 +6,7 @@
 namespace fastcheb {
 
 namespace {
-typedef cudaError_t (*DmmaFn)(int, int, int, const DmmaParams&, int, int, size_t, cudaStream_t, int*);
+typedef cudaError_t (*DmmaFn)(int, int, int, int, const DmmaParams&, int, int, size_t, cudaStream_t, int*);
 DmmaFn dmma_fn(int ks, bool jac) {
   switch (ks) {
     case 4: return jac ? dmma_dispatch_ks4_jac : dmma_dispatch_ks4_val;
@@ -20,7 +20,7 @@ DmmaFn dmma_fn(int ks, bool jac) {
 int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
   DmmaPlan& pl = p->dmma;
   pl.ok = false;
-  if (p->dtype != FASTCHEB_F64 || p->ndim < 2 || p->ndim > 4) return FASTCHEB_OK;
+  if (p->ndim < 2 || p->ndim > 4) return FASTCHEB_OK;  // Float32 polynomials use the same FP64 tensor-core kernels
   const int n1 = (int)p->dims[0];
   if (n1 < 5 || n1 - 1 > 64) return FASTCHEB_OK;
   long long M = 1;
@@ -61,8 +61,12 @@ int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
   for (const DmmaGroup& g : pl.groups) {
     const long long total = (long long)pl.ntiles * (kDmmaMeta + g.ec * U);
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)p->di->sms * 16));
-    relayout_frag_kernel<0><<<grid, 256, 0, st>>>((const double*)p->d_coefs, (double*)pl.d_frag + g.offset, total, p->E,
-                                               g.e0, g.ec, n1, pl.M, pl.KS, fd);
+    if (p->dtype == FASTCHEB_F64)
+      relayout_frag_kernel<double><<<grid, 256, 0, st>>>((const double*)p->d_coefs, (double*)pl.d_frag + g.offset, total,
+                                                        p->E, g.e0, g.ec, n1, pl.M, pl.KS, fd);
+    else
+      relayout_frag_kernel<float><<<grid, 256, 0, st>>>((const float*)p->d_coefs, (double*)pl.d_frag + g.offset, total,
+                                                       p->E, g.e0, g.ec, n1, pl.M, pl.KS, fd);
     FC_CUDA(cudaGetLastError());
     note_launch();
   }
@@ -82,9 +86,9 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
     DmmaParams prm;
     memset(&prm, 0, sizeof prm);
     prm.frag = (const double*)pl.d_frag + g.offset;
-    prm.pts = (const double*)pts;
-    prm.out_v = (double*)out_v;
-    prm.out_J = (double*)out_J;
+    prm.pts = pts;
+    prm.out_v = out_v;
+    prm.out_J = out_J;
     prm.bad = (&g == &pl.groups[0]) ? bad_dev : nullptr;
     prm.npts = npts;
     prm.idx_base = idx_base;
@@ -128,13 +132,13 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
     const size_t smem = 128 + (size_t)nstage * tps * unitBytes + (size_t)warps * rows * pl.tabStride * 8 * (jac ? 2 : 1);
     const int threads = warps * 32;
     int bps = 1;
-    cudaError_t e = fn(1, p->ndim, g.ec, prm, threads, 0, smem, st, &bps);
+    cudaError_t e = fn(1, p->dtype, p->ndim, g.ec, prm, threads, 0, smem, st, &bps);
     if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "DMMA occupancy query failed: %s", cudaGetErrorString(e));
     if (bps < 1) return fail(FASTCHEB_ECUDA, "DMMA kernel does not fit an SM (smem %zu B)", smem);
     const long long pass_pts = (long long)warps * rows;
     const long long npass = (npts + pass_pts - 1) / pass_pts;
     const int grid = (int)std::min<long long>(npass, (long long)p->di->sms * bps);
-    e = fn(0, p->ndim, g.ec, prm, threads, grid, smem, st, nullptr);
+    e = fn(0, p->dtype, p->ndim, g.ec, prm, threads, grid, smem, st, nullptr);
     if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "DMMA kernel launch failed: %s", cudaGetErrorString(e));
   }
   return FASTCHEB_OK;

@@ -34,10 +34,10 @@
 namespace fastcheb {
 
 struct DmmaParams {
-  const double* frag;  // tile-record stream of this component group
-  const double* pts;
-  double* out_v;
-  double* out_J;
+  const double* frag;  // tile-record stream of this component group (always Float64)
+  const void* pts;     // points, values and Jacobians are in the polynomial's real type R (Float64 or Float32)
+  void* out_v;
+  void* out_J;
   long long* bad;
   long long npts, idx_base;
   long long v_stride, J_stride;
@@ -67,9 +67,15 @@ constexpr int kDmmaMeta = 16;  // doubles of metadata per tile record (8 columns
 __host__ __device__ constexpr int dmma_max_threads(int EC, int KS, bool JAC) {
   return JAC ? 256 : (KS <= 4 ? 768 : (KS <= 8 && EC < 3 ? 640 : 512));
 }
-template <int N, int EC, int KS, bool JAC>
+// R: the real type of points and results.  Float32 polynomials run the same FP64 tensor-core arithmetic (their
+// coefficients are widened once in the tile-record stream); the normalised coordinate is formed in R with the oracle's
+// operation sequence and only then widened, results are rounded to R at the very end.
+template <typename R, int N, int EC, int KS, bool JAC>
 __global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(const __grid_constant__ DmmaParams prm) {
   constexpr int MT = kDmmaMT;
+  const R* const pts_in = reinterpret_cast<const R*>(prm.pts);
+  R* const out_v = reinterpret_cast<R*>(prm.out_v);
+  [[maybe_unused]] R* const out_J = reinterpret_cast<R*>(prm.out_J);
   constexpr int U = KS * 32 + 8;
   constexpr int TR = kDmmaMeta + EC * U;  // doubles per tile record
   constexpr int ROWS = MT * 8;
@@ -255,11 +261,11 @@ __global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(con
       double z[N];
 #pragma unroll
       for (int d = 0; d < N; ++d) {
-        const double lb = prm.lb[d], ub = prm.ub[d];
-        const double x = live[mt] ? prm.pts[idx[mt] * N + d] : lb;
+        const R lb = (R)prm.lb[d], ub = (R)prm.ub[d];
+        const R x = live[mt] ? pts_in[idx[mt] * N + d] : lb;
         const bool in = (lb <= x) && (x <= ub);  // eval.jl:64
         ok = ok && in;
-        z[d] = in ? __dsub_rn(__ddiv_rn(__dmul_rn(__dsub_rn(x, lb), 2.0), __dsub_rn(ub, lb)), 1.0) : 0.0;  // eval.jl:65
+        z[d] = in ? (double)rsub(rdiv(rmul(rsub(x, lb), R(2)), rsub(ub, lb)), R(1)) : 0.0;  // eval.jl:65
       }
       if (live[mt] && !ok) {
         live[mt] = false;
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(con
       for (int mt = 0; mt < MT; ++mt)
         if (live[mt]) {
 #pragma unroll
-          for (int e = 0; e < EC; ++e) prm.out_v[idx[mt] * prm.v_stride + prm.e0 + e] = acc[mt][e];
+          for (int e = 0; e < EC; ++e) out_v[idx[mt] * prm.v_stride + prm.e0 + e] = (R)acc[mt][e];
           if constexpr (JAC) {
             double Js[EC][N];
 #pragma unroll
@@ -501,24 +507,24 @@ __global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(con
               for (int e = 0; e < EC; ++e)
 #pragma unroll
                 for (int d = 0; d < N; ++d)
-                  prm.out_J[idx[mt] * prm.J_stride + prm.e0 + e + (long long)prm.Etot * d] = Js[e][d];
+                  out_J[idx[mt] * prm.J_stride + prm.e0 + e + (long long)prm.Etot * d] = (R)Js[e][d];
             } else if (prm.mode == 1) {  // pullback real(J' * dy), chainrules.jl:7,14 (accumulated over component groups)
-              const double* dy = reinterpret_cast<const double*>(prm.tan) + idx[mt] * prm.Etot + prm.e0;
+              const R* dy = reinterpret_cast<const R*>(prm.tan) + idx[mt] * prm.Etot + prm.e0;
 #pragma unroll
               for (int d = 0; d < N; ++d) {
-                double a = prm.e0 == 0 ? 0.0 : prm.out_J[idx[mt] * N + d];
+                double a = prm.e0 == 0 ? 0.0 : (double)out_J[idx[mt] * N + d];
 #pragma unroll
-                for (int e = 0; e < EC; ++e) a = fma(Js[e][d], dy[e], a);
-                prm.out_J[idx[mt] * N + d] = a;
+                for (int e = 0; e < EC; ++e) a = fma(Js[e][d], (double)dy[e], a);
+                out_J[idx[mt] * N + d] = (R)a;
               }
             } else {  // pushforward J * dx, chainrules.jl:24
-              const double* dx = reinterpret_cast<const double*>(prm.tan) + idx[mt] * N;
+              const R* dx = reinterpret_cast<const R*>(prm.tan) + idx[mt] * N;
 #pragma unroll
               for (int e = 0; e < EC; ++e) {
                 double a = 0.0;
 #pragma unroll
-                for (int d = 0; d < N; ++d) a = fma(Js[e][d], dx[d], a);
-                prm.out_J[idx[mt] * prm.Etot + prm.e0 + e] = a;
+                for (int d = 0; d < N; ++d) a = fma(Js[e][d], (double)dx[d], a);
+                out_J[idx[mt] * prm.Etot + prm.e0 + e] = (R)a;
               }
             }
           }
@@ -533,8 +539,8 @@ struct FragDims {
   int n[kMaxNdim];        // n2..nN
   int toff[kMaxNdim];     // offset of each dim's table inside a weight-table row
 };
-template <int DUMMY>
-__global__ void __launch_bounds__(256) relayout_frag_kernel(const double* __restrict__ src, double* __restrict__ dst,
+template <typename S>
+__global__ void __launch_bounds__(256) relayout_frag_kernel(const S* __restrict__ src, double* __restrict__ dst,
                                                             long long total, int E, int e0, int ec, int n1, int M,
                                                             int KS, const FragDims fd) {
   const int U = KS * 32 + 8;
@@ -571,7 +577,7 @@ __global__ void __launch_bounds__(256) relayout_frag_kernel(const double* __rest
       k1 = 1 + 4 * ks + (l & 3);
       m = tile * 8 + (l >> 2);
     }
-    dst[g] = (k1 < n1 && m < M) ? src[(e0 + e) + (long long)E * (k1 + (long long)n1 * m)] : 0.0;
+    dst[g] = (k1 < n1 && m < M) ? (double)src[(e0 + e) + (long long)E * (k1 + (long long)n1 * m)] : 0.0;
   }
 }
 

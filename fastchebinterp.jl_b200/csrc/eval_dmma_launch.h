@@ -10,12 +10,12 @@ constexpr int kDmmaMaxEC = 3;
 inline int dmma_max_warps(int ec, int ks, bool jac) { return dmma_max_threads(ec, ks, jac) / 32; }
 
 // per-(KS, JAC) translation units: op 0 = launch, op 1 = occupancy query
-cudaError_t dmma_dispatch_ks4_val(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
-cudaError_t dmma_dispatch_ks8_val(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
-cudaError_t dmma_dispatch_ks16_val(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
-cudaError_t dmma_dispatch_ks4_jac(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
-cudaError_t dmma_dispatch_ks8_jac(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
-cudaError_t dmma_dispatch_ks16_jac(int op, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks4_val(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks8_val(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks16_val(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks4_jac(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks8_jac(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+cudaError_t dmma_dispatch_ks16_jac(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
 
 // decide whether the handle gets a DMMA plan and build the fragment stream (no-op when not applicable)
 int dmma_plan(fastcheb_poly* p, cudaStream_t st);

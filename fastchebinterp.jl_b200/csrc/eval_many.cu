@@ -16,15 +16,6 @@
 namespace fastcheb {
 namespace {
 
-__device__ __forceinline__ double rsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ float rsub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float rmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double rdiv(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ float rdiv(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ double rfma(double a, double b, double c) { return __fma_rn(a, b, c); }
-__device__ __forceinline__ float rfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-
 struct ManyParams {
   const void* coefs;   // [howmany][n][E]
   const void* pts;     // [howmany][M]

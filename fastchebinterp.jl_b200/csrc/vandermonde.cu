@@ -19,13 +19,6 @@
 namespace fastcheb {
 namespace {
 
-__device__ __forceinline__ double rsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ float rsub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float rmul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double rdiv(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ float rdiv(float a, float b) { return __fdiv_rn(a, b); }
-
 struct VdmParams {
   const void* pts;  // m x N, AoS
   void* A;          // m x P column-major, leading dimension lda

@@ -17,6 +17,8 @@ CASES = [
     ((65, 65), None, False, np.float64),
     ((49, 40), None, False, np.float32),
     ((33, 33, 33), 3, False, np.float64),
+    ((33, 33, 33), 3, False, np.float32),
+    ((17, 9, 5, 4), 2, True, np.float32),
     ((17, 17, 17, 17), None, True, np.float64),
     ((9, 8, 7), 5, False, np.float64),       # E = 5: two component groups
     ((6, 5, 4), 4, True, np.float32),        # E = 8
@@ -73,9 +75,9 @@ def test_value_parity(fc, orc, case):
     got = poly(pts)
     assert got.dtype == ref.dtype and got.shape == ref.shape
     assert np.array_equal(got, ref), f"Clenshaw kernel not bit-identical: max diff {np.abs(got - ref).max():.3e} (tol {tol:.3e})"
-    if dt == np.float64 and len(dims) >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8:
+    if len(dims) >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8:   # Float32 runs the same FP64 tensor-core kernels
         poly.set_algo(fc.ALGO_DMMA, dt)
-        assert poly.get_algo(False) == fc.ALGO_DMMA
+        assert poly.get_algo(False, dt) == fc.ALGO_DMMA
         got2 = poly(pts)
         assert np.abs(got2 - ref).max() <= tol, f"DMMA: {np.abs(got2 - ref).max():.3e} > {tol:.3e}"
     # single-point call == the batched entry (runtests.jl:176-178)
@@ -100,7 +102,7 @@ def test_jacobian_parity(fc, orc, case):
     for d, n in enumerate(dims):
         if n == 1:
             assert np.all(J[:, :, d] == 0)       # exactly zero (runtests.jl:152,158,165)
-    if dt == np.float64 and len(dims) >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8:
+    if len(dims) >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8:
         poly.set_algo(fc.ALGO_DMMA, dt)
         v2, J2 = fc.chebjacobian(poly, pts)
         tol = 16 * np.finfo(dt).eps * np.abs(c).sum()
