@@ -188,3 +188,66 @@ function chebcoefs_batched(vals::Matrix{R}; device::Integer=0) where {R<:Union{F
     _check(rc)
     coefs, maxabs      # droptol per column: trailing |c| < tol*maxabs[j] (interp.jl:77-93)
 end
+
+# ---- callers of the hot path (SURVEY.md 8f): the same pattern, one ccall each ------------------------------------
+
+# chebinterp(c, order, lb, ub; tol) with a device-resident ChebPoly as the function (interp.jl:163-170; the loop body of
+# roots, roots.jl:105-107): grid -> evaluation -> fit -> droptol never leave the GPU.
+function cuchebinterp(cu::CuChebPoly{N,T,Td}, order::NTuple{N,Int}, lb, ub; tol::Real=-1) where {N,T,Td}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:fastcheb_reinterp, libfastcheb), Cint,
+                 (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Cvoid}),
+                 h, cu.handle, collect(Int64, order), collect(Float64, lb), collect(Float64, ub), tol, C_NULL))
+    nd = Vector{Int64}(undef, N)
+    _check(ccall((:fastcheb_dims, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Int64}), h[], nd))
+    CuChebPoly{N,T,Td}(h[], SVector{N,Td}(lb), SVector{N,Td}(ub), Tuple(nd), cu.device)
+end
+
+# rrule / frule (chainrules.jl:4-39) over batches: the Jacobian is contracted inside the kernel.
+function cheb_pullback(cu::CuChebPoly{N,T}, ys::Vector{SVector{N,R}}, dy::Vector{T}) where {N,T,R<:Union{Float32,Float64}}
+    v = Vector{T}(undef, length(ys)); xbar = Vector{SVector{N,R}}(undef, length(ys))
+    GC.@preserve ys dy v xbar begin
+        rc = ccall((:fastcheb_eval_vjp, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                   cu.handle, pointer(ys), length(ys), pointer(dy), pointer(v), pointer(xbar), FASTCHEB_MEM_HOST, C_NULL)
+    end
+    _check(rc, cu, ys)
+    v, xbar            # real(J' * dy) per point (chainrules.jl:7,14)
+end
+function cheb_pushforward(cu::CuChebPoly{N,T}, ys::Vector{SVector{N,R}}, dx::Vector{SVector{N,R}}) where {N,T,R<:Union{Float32,Float64}}
+    v = Vector{T}(undef, length(ys)); ydot = Vector{T}(undef, length(ys))
+    GC.@preserve ys dx v ydot begin
+        rc = ccall((:fastcheb_eval_jvp, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                   cu.handle, pointer(ys), length(ys), pointer(dx), pointer(v), pointer(ydot), FASTCHEB_MEM_HOST, C_NULL)
+    end
+    _check(rc, cu, ys)
+    v, ydot            # J * dx per point (chainrules.jl:24)
+end
+
+# chebvandermonde (regression.jl:5-46) assembled on the device in one O(m P) pass; `A \ Y` (regression.jl:67) stays Julia.
+function cuchebvandermonde(x::Vector{SVector{N,R}}, lb::SVector{N}, ub::SVector{N}, order::NTuple{N,Int}) where {N,R<:Union{Float32,Float64}}
+    A = Matrix{R}(undef, length(x), prod(order .+ 1))
+    GC.@preserve x A begin
+        rc = ccall((:fastcheb_vandermonde, libfastcheb), Cint,
+                   (Cint, Ptr{Int64}, Cint, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Cvoid}),
+                   N, collect(Int64, order .+ 1), _dtype(R), pointer(x), length(x), collect(Float64, lb), collect(Float64, ub),
+                   pointer(A), size(A, 1), FASTCHEB_MEM_HOST, 0, C_NULL)
+    end
+    rc == FASTCHEB_EDOMAIN && throw(ArgumentError("$(x[_error_index() + 1]) not in domain [$lb,$ub]"))   # regression.jl:33
+    _check(rc)
+    A
+end
+
+# many independent 1-D polynomials, each at its own points: [c.(xs) for (c, xs) in zip(cs, xss)] in one launch.
+# coefs: n x howmany (column j = polynomial j, e.g. the output of chebcoefs_batched), xs: M x howmany.
+function cheb_eval_many(coefs::Matrix{R}, lb::Real, ub::Real, xs::Matrix{R}) where {R<:Union{Float32,Float64}}
+    n, howmany = size(coefs); M = size(xs, 1)
+    out = similar(xs)
+    GC.@preserve coefs xs out begin
+        rc = ccall((:fastcheb_eval_many, libfastcheb), Cint,
+                   (Int64, Int64, Cint, Cint, Cint, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}),
+                   howmany, n, _dtype(R), 0, 1, pointer(coefs), Float64[lb], Float64[ub], 0, pointer(xs), M, pointer(out), C_NULL, C_NULL,
+                   FASTCHEB_MEM_HOST, 0, C_NULL)
+    end
+    _check(rc)
+    out
+end
