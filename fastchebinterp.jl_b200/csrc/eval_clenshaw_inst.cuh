@@ -6,7 +6,7 @@ namespace fastcheb {
 namespace {
 template <int N, int EC>
 cudaError_t go(int op, const EvalParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps) {
-  constexpr int P = FC_JAC ? kClenshawPtsJac : kClenshawPtsVal;
+  constexpr int P = clenshaw_pts(N, EC, FC_JAC);
   auto kern = clenshaw_kernel<FC_REAL, N, EC, P, FC_JAC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
   if (e != cudaSuccess) return e;

@@ -7,8 +7,9 @@
 namespace fastcheb {
 
 // points per thread used by the instantiations (value kernels interleave 2 points for ILP)
-constexpr int kClenshawPtsVal = 2;
-constexpr int kClenshawPtsJac = 1;
+// 1-D polynomials have tiny per-point state, so a thread carries more points: every broadcast coefficient load then
+// feeds more independent recurrences
+constexpr int clenshaw_pts(int ndim, int ec, bool jac) { return jac ? (ndim == 1 && ec <= 2 ? 2 : 1) : (ndim == 1 && ec <= 2 ? 4 : 2); }
 constexpr int kClenshawMaxThreadsVal = 512;
 constexpr int kClenshawMaxThreadsJac = 256;
 constexpr int kClenshawMaxEC = 4;

@@ -106,8 +106,8 @@ int eval_clenshaw(const fastcheb_poly* p, const void* pts, int64_t npts, void* o
   if (p->ndim > kMaxKernelNdim)
     return fail(FASTCHEB_EUNSUPPORTED, "ndim = %d: evaluation kernels cover ndim <= %d", p->ndim, kMaxKernelNdim);
   ClenshawFn fn = clenshaw_fn(p->dtype, jac);
-  const int P = jac ? kClenshawPtsJac : kClenshawPtsVal;
   for (const ClenshawGroup& g : p->groups) {
+    const int P = clenshaw_pts(p->ndim, g.ec, jac);
     EvalParams prm;
     memset(&prm, 0, sizeof prm);
     prm.coefs = g.d_pp;

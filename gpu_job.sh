@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-BENCH_ONLY="cfg1" ncu --set full --clock-control none --import-source on -k regex:clenshaw_kernel -s 3 -c 1 -o gpurun_out/r01_clenshaw_cfg1 -f python tools/bench_configs.py > gpurun_out/ncu_s.log 2>&1
-BENCH_ONLY="cfg5 eval: 1-D order 64 real F64" ncu --set full --clock-control none --import-source on -k regex:clenshaw_kernel -s 3 -c 1 -o gpurun_out/r01_clenshaw_cfg5 -f python tools/bench_configs.py > gpurun_out/ncu_s2.log 2>&1
-tail -n 2 gpurun_out/ncu_s.log gpurun_out/ncu_s2.log
+timeout 1200 python -m pytest tests/test_gpu_eval.py tests/test_gpu_golden.py tests/test_gpu_adrules.py -m gpu -q -x 2>&1 | tail -4
+BENCH_ONLY="1-D" python tools/bench_configs.py > gpurun_out/configs1d.jsonl 2> gpurun_out/configs.err; tail -3 gpurun_out/configs.err
+BENCH_ONLY="cfg1" python tools/bench_configs.py >> gpurun_out/configs1d.jsonl 2> gpurun_out/configs.err; tail -3 gpurun_out/configs.err
+python - <<'PY'
+import json
+for l in open('gpurun_out/configs1d.jsonl'):
+    d=json.loads(l)
+    print(f"{d['config']:60s} {d['algo']:8s} {d['mode']} {d['points_per_s']:.3e} pts/s  fp {d['frac_of_fp_peak']*100:5.1f}%  hbm {d['frac_of_hbm']*100:5.1f}%")
+PY
