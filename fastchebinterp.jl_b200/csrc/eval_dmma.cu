@@ -81,7 +81,7 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
   DmmaFn fn = dmma_fn(pl.KS, jac);
   if (!fn) return fail(FASTCHEB_EUNSUPPORTED, "no DMMA instantiation for KS = %d", pl.KS);
   const int U = pl.KS * 32 + 8;
-  const int rows = kDmmaMT * 8;
+  const int rows = dmma_mt(jac) * 8;
   for (const DmmaGroup& g : pl.groups) {
     DmmaParams prm;
     memset(&prm, 0, sizeof prm);

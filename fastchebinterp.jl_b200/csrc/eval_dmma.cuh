@@ -59,20 +59,25 @@ struct DmmaParams {
 #ifndef FC_DMMA_MT
 #define FC_DMMA_MT 2
 #endif
-constexpr int kDmmaMT = FC_DMMA_MT;  // 8-point M tiles per warp
+constexpr int kDmmaMT = FC_DMMA_MT;  // 8-point M tiles per warp (value kernels)
+#ifndef FC_DMMA_MT_JAC
+#define FC_DMMA_MT_JAC 1
+#endif
+constexpr int kDmmaMTJac = FC_DMMA_MT_JAC;  // Jacobian kernels: the G and G' chains already give two MMAs per B fragment
+__host__ __device__ constexpr int dmma_mt(bool jac) { return jac ? kDmmaMTJac : kDmmaMT; }
 constexpr int kDmmaMeta = 16;  // doubles of metadata per tile record (8 columns x up to 3 dims x int32, padded)
 
 // Threads per CTA the instantiation is compiled for: the value kernels with few accumulators leave registers for more
 // warps (the tile loop is latency-bound per warp when a tile has only 16 DMMAs, so more warps per SM pay directly).
 __host__ __device__ constexpr int dmma_max_threads(int EC, int KS, bool JAC) {
-  return JAC ? 256 : (KS <= 4 ? 768 : (KS <= 8 && EC < 3 ? 640 : 512));
+  return JAC ? (kDmmaMTJac == 1 ? 512 : 256) : (KS <= 4 ? 768 : (KS <= 8 && EC < 3 ? 640 : 512));
 }
 // R: the real type of points and results.  Float32 polynomials run the same FP64 tensor-core arithmetic (their
 // coefficients are widened once in the tile-record stream); the normalised coordinate is formed in R with the oracle's
 // operation sequence and only then widened, results are rounded to R at the very end.
 template <typename R, int N, int EC, int KS, bool JAC>
 __global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(const __grid_constant__ DmmaParams prm) {
-  constexpr int MT = kDmmaMT;
+  constexpr int MT = dmma_mt(JAC);
   const R* const pts_in = reinterpret_cast<const R*>(prm.pts);
   R* const out_v = reinterpret_cast<R*>(prm.out_v);
   [[maybe_unused]] R* const out_J = reinterpret_cast<R*>(prm.out_J);
