@@ -397,8 +397,11 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
       if (dbuf[i]) ws_release(p->device, dbuf[i]);
     }
   };
+  // a call that fits one chunk (single points, small batches) runs on the caller's stream: creating streams costs
+  // more than such a call itself
+  const bool own_streams = nbuf > 1;
   for (int i = 0; i < nbuf; ++i) {
-    if (cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) != cudaSuccess) {
+    if (own_streams && cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) != cudaSuccess) {
       cleanup();
       return fail(FASTCHEB_ECUDA, "cudaStreamCreate failed");
     }
@@ -408,8 +411,9 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
       return fail(FASTCHEB_ENOMEM, "device staging buffer of %zu bytes", in_al + v_al + J_bytes);
     }
   }
-  cudaError_t ce = set_flag_async(fs.dev, kNoBad, ss[0]);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ss[0]);
+  auto stream_of = [&](int b) { return own_streams ? ss[b] : st; };
+  cudaError_t ce = set_flag_async(fs.dev, kNoBad, stream_of(0));
+  if (ce == cudaSuccess && own_streams) ce = cudaStreamSynchronize(ss[0]);  // ordered before the second stream's work
   int64_t done = 0;
   for (int it = 0; ce == cudaSuccess && rc == FASTCHEB_OK && done < npts; ++it) {
     const int b = it % nbuf;
@@ -417,28 +421,33 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
     char* d_in = (char*)dbuf[b];
     char* d_v = d_in + in_al;
     char* d_J = d_v + v_al;
-    ce = cudaMemcpyAsync(d_in, (const char*)pts + (size_t)done * in_pp, (size_t)m * in_pp, cudaMemcpyHostToDevice, ss[b]);
+    ce = cudaMemcpyAsync(d_in, (const char*)pts + (size_t)done * in_pp, (size_t)m * in_pp, cudaMemcpyHostToDevice, stream_of(b));
     if (ce != cudaSuccess) break;
     if (o.interleaved) {
-      rc = eval_device(p, d_in, m, d_v, o.v_stride, (char*)d_v + (size_t)E * rs, o.J_stride, jac, fs.dev, done, ss[b]);
+      rc = eval_device(p, d_in, m, d_v, o.v_stride, (char*)d_v + (size_t)E * rs, o.J_stride, jac, fs.dev, done, stream_of(b));
       if (rc != FASTCHEB_OK) break;
-      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * out_pp, d_v, (size_t)m * out_pp, cudaMemcpyDeviceToHost, ss[b]);
+      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * out_pp, d_v, (size_t)m * out_pp, cudaMemcpyDeviceToHost, stream_of(b));
     } else {
-      rc = eval_device(p, d_in, m, d_v, E, d_J, (int64_t)E * N, jac, fs.dev, done, ss[b]);
+      rc = eval_device(p, d_in, m, d_v, E, d_J, (int64_t)E * N, jac, fs.dev, done, stream_of(b));
       if (rc != FASTCHEB_OK) break;
-      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * E * rs, d_v, (size_t)m * E * rs, cudaMemcpyDeviceToHost, ss[b]);
+      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * E * rs, d_v, (size_t)m * E * rs, cudaMemcpyDeviceToHost, stream_of(b));
       if (ce == cudaSuccess && jac)
         ce = cudaMemcpyAsync((char*)o.J + (size_t)done * E * N * rs, d_J, (size_t)m * E * N * rs,
-                             cudaMemcpyDeviceToHost, ss[b]);
+                             cudaMemcpyDeviceToHost, stream_of(b));
     }
     done += m;
   }
-  for (int i = 0; i < nbuf; ++i)
-    if (ss[i]) {
+  if (own_streams) {
+    for (int i = 0; i < nbuf; ++i) {
       cudaError_t e2 = cudaStreamSynchronize(ss[i]);
       if (ce == cudaSuccess) ce = e2;
     }
-  if (ce == cudaSuccess) ce = cudaMemcpy(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost);
+    if (ce == cudaSuccess) ce = cudaMemcpy(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost);
+  } else {
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);  // one synchronisation for the whole call
+    if (ce == cudaSuccess) ce = e2;
+  }
   cleanup();
   if (rc != FASTCHEB_OK) return rc;
   if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged evaluation failed: %s", cudaGetErrorString(ce));
