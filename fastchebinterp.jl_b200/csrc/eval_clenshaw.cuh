@@ -26,7 +26,7 @@
 
 namespace fastcheb {
 
-constexpr int kMaxKernelNdim = 4;  // dimension nests instantiated (eval_clenshaw_inst.cuh)
+constexpr int kMaxKernelNdim = 6;  // dimension nests instantiated (eval_clenshaw_inst.cuh)
 
 struct EvalParams {
   const void* coefs;  // planar-padded slabs of this component group (device)

@@ -34,6 +34,8 @@ cudaError_t FC_FUNC(int op, int ndim, int ec, const EvalParams& prm, int threads
     case 2: return go_ec<2>(op, ec, prm, threads, grid, smem, st, bps);
     case 3: return go_ec<3>(op, ec, prm, threads, grid, smem, st, bps);
     case 4: return go_ec<4>(op, ec, prm, threads, grid, smem, st, bps);
+    case 5: return go_ec<5>(op, ec, prm, threads, grid, smem, st, bps);
+    case 6: return go_ec<6>(op, ec, prm, threads, grid, smem, st, bps);
   }
   return cudaErrorInvalidValue;
 }

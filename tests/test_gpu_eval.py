@@ -29,6 +29,9 @@ CASES = [
     ((3, 1, 4), None, False, np.float64),
     ((34, 3), None, False, np.float64),
     ((5, 70), 3, False, np.float64),
+    ((4, 3, 5, 2, 3), 2, False, np.float64),     # 5-D and 6-D: the Clenshaw nest covers FASTCHEB_MAX_NDIM
+    ((3, 2, 4, 2, 3, 2), None, True, np.float64),
+    ((3, 3, 2, 2, 2, 3), 3, False, np.float32),
 ]
 
 
