@@ -1,5 +1,6 @@
+set -x
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_fit.py tests/test_gpu_fullsize.py tests/test_gpu_sharded.py -m gpu -q -x 2>&1 | tail -8
-python bench.py --workload fit1d --steps 20 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_fit1d_f64.json; grep -o '"value": [0-9.]*\|"frac": [0-9.]*\|max_rel_err_vs_oracle": [0-9.e-]*' gpurun_out/bench_fit1d_f64.json
-python bench.py --workload fit1d --steps 20 --warmup 3 --dtype f32 --no-cpu --no-e2e > gpurun_out/bench_fit1d_f32.json; grep -o '"value": [0-9.]*\|"frac": [0-9.]*\|max_rel_err_vs_oracle": [0-9.e-]*' gpurun_out/bench_fit1d_f32.json
-python bench.py --workload fit1d --steps 20 --warmup 3 --howmany 100000 --no-cpu --no-e2e > gpurun_out/bench_fit1d_f64_1e5.json; grep -o '"value": [0-9.]*\|"frac": [0-9.]*' gpurun_out/bench_fit1d_f64_1e5.json
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
+python -c "import __graft_entry__ as g; g.smoke()"
+python bench.py --impl reference > gpurun_out/bench_ref.json 2>gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cut -c1-300 gpurun_out/bench_ref.json
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -3 gpurun_out/bench_default.err; cat gpurun_out/bench_default.json
