@@ -102,3 +102,28 @@ def test_droptol_semantics(orc):
     assert orc.droptol(c, 2, 1e-16).shape == (3, 2)
     full = np.ones((4, 4))
     assert orc.droptol(full, 2, 0.5) is full or orc.droptol(full, 2, 0.5).shape == (4, 4)
+
+
+GOLD_NAMES = ["d1", "d1c", "d2", "d2k", "d3", "d4c", "n1", "n2"]
+
+
+def _gold():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "truth_small.npz"))
+
+
+@pytest.mark.parametrize("name", GOLD_NAMES)
+def test_oracle_against_committed_truth(orc, name):
+    """tests/golden/truth_small.npz (made by tests/golden/make_golden.py from long-double arithmetic that shares no
+    code with the oracle's C kernels): values, Jacobians and fitted coefficients."""
+    g = _gold()
+    c, lb, ub, pts = (g[f"{name}_{k}"] for k in ("coefs", "lb", "ub", "pts"))
+    N = len(lb)
+    p = orc.OracleChebPoly(c, lb, ub)
+    v, J = p.jacobian(pts if N > 1 else pts[:, 0])
+    tol = 16 * np.finfo(np.float64).eps * np.abs(c).sum()
+    nmax2 = max(1, max(n - 1 for n in c.shape[:N]) ** 2)
+    assert np.abs(np.asarray(v).reshape(g[f"{name}_val"].shape) - g[f"{name}_val"]).max() <= tol
+    assert np.abs(np.asarray(J).reshape(g[f"{name}_jac"].shape) - g[f"{name}_jac"]).max() <= tol * nmax2 * (2 / (ub - lb)).max()
+    fit = orc.chebcoefs_fft(g[f"{name}_fitvals"], N)            # the FFT stand-in against the long-double cosine sums
+    assert np.abs(fit - g[f"{name}_fitcoefs"]).max() <= 1e-14 * np.abs(g[f"{name}_fitcoefs"]).max()
