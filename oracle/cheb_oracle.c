@@ -39,6 +39,43 @@
 #undef FMA
 #undef NAME
 
+/* all components of an element together (the SIMD the reference gets from SVector / Complex elements): Float64, the
+ * component counts of the benchmark configs */
+#define REAL double
+#define FMA fma
+#define NAME(x) x##_f64
+#define EV 1
+#include "cheb_oracle_vec.inc"
+#undef EV
+#define EV 2
+#include "cheb_oracle_vec.inc"
+#undef EV
+#define EV 3
+#include "cheb_oracle_vec.inc"
+#undef EV
+#define EV 4
+#include "cheb_oracle_vec.inc"
+#undef EV
+#define EV 6
+#include "cheb_oracle_vec.inc"
+#undef EV
+#undef REAL
+#undef FMA
+#undef NAME
+
+/* values of all E components per pass; falls back to the component-by-component routine for other E */
+int oracle_eval_vec_f64(int ndim, const int64_t* dims, int E, const double* coefs, const double* lb, const double* ub,
+                        const double* pts, int64_t npts, double* out, int64_t* bad) {
+  switch (E) {
+    case 1: return oracle_eval_vec_v1_f64(ndim, dims, coefs, lb, ub, pts, npts, out, bad);
+    case 2: return oracle_eval_vec_v2_f64(ndim, dims, coefs, lb, ub, pts, npts, out, bad);
+    case 3: return oracle_eval_vec_v3_f64(ndim, dims, coefs, lb, ub, pts, npts, out, bad);
+    case 4: return oracle_eval_vec_v4_f64(ndim, dims, coefs, lb, ub, pts, npts, out, bad);
+    case 6: return oracle_eval_vec_v6_f64(ndim, dims, coefs, lb, ub, pts, npts, out, bad);
+  }
+  return oracle_eval_f64(ndim, dims, E, coefs, lb, ub, pts, npts, out, bad);
+}
+
 /* ------------------------------------------------------------------ fit: interp.jl:39-57 chebcoefs
  * vals/coefs: Julia column-major array of elements of E inline reals (E = K*(1|2)); every real
  * component is transformed independently (interp.jl:59-65 for SVector, FFTW r2r on complex arrays

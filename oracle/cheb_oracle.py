@@ -46,6 +46,8 @@ def lib() -> ctypes.CDLL:
             f = getattr(L, f"oracle_eval_jac_{sfx}")
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.c_int, i64p, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int64, vp, vp, i64p]
+        L.oracle_eval_vec_f64.restype = ctypes.c_int
+        L.oracle_eval_vec_f64.argtypes = [ctypes.c_int, i64p, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int64, vp, i64p]
         L.oracle_fit_ld.restype = ctypes.c_int
         L.oracle_fit_ld.argtypes = [ctypes.c_int, i64p, ctypes.c_int, vp, vp, i64p]
         L.oracle_droptol_shape.restype = ctypes.c_int
@@ -197,7 +199,7 @@ class OracleChebPoly:
         pts = np.ascontiguousarray(np.asarray(x, dtype=rdt).reshape(-1, self.ndim))
         return rdt, single, pts
 
-    def _call(self, x, jac: bool):
+    def _call(self, x, jac: bool, vec: bool = False):
         rdt, single, pts = self._prep(x)
         N = self.ndim
         dims = self.coefs.shape[:N]
@@ -216,8 +218,9 @@ class OracleChebPoly:
             rc = getattr(lib(), f"oracle_eval_jac_{sfx}")(N, _dims_ptr(dims), E, flat.ctypes.data, lb.ctypes.data, ub.ctypes.data,
                                                           pts.ctypes.data, npts, out.ctypes.data, outJ.ctypes.data, ctypes.byref(bad))
         else:
-            rc = getattr(lib(), f"oracle_eval_{sfx}")(N, _dims_ptr(dims), E, flat.ctypes.data, lb.ctypes.data, ub.ctypes.data,
-                                                      pts.ctypes.data, npts, out.ctypes.data, ctypes.byref(bad))
+            fn = f"oracle_eval_vec_{sfx}" if (vec and sfx == "f64") else f"oracle_eval_{sfx}"
+            rc = getattr(lib(), fn)(N, _dims_ptr(dims), E, flat.ctypes.data, lb.ctypes.data, ub.ctypes.data,
+                                    pts.ctypes.data, npts, out.ctypes.data, ctypes.byref(bad))
         if rc == 1:
             err = ValueError(f"{pts[bad.value]} not in domain {self.lb} to {self.ub}")   # ArgumentError eval.jl:64
             err.index = int(bad.value)
@@ -236,6 +239,11 @@ class OracleChebPoly:
 
     def __call__(self, x):                                           # eval.jl:63-70
         return self._call(x, False)
+
+    def eval_simd(self, x):
+        """Same values, bit for bit, with all components of an element advanced together (cheb_oracle_vec.inc): the
+        SIMD over SVector/Complex lanes that the reference gets from LLVM.  Used for the timed CPU baseline."""
+        return self._call(x, False, vec=True)
 
     def jacobian(self, x):                                           # eval.jl:147-155
         return self._call(x, True)

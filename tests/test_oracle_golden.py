@@ -127,3 +127,17 @@ def test_oracle_against_committed_truth(orc, name):
     assert np.abs(np.asarray(J).reshape(g[f"{name}_jac"].shape) - g[f"{name}_jac"]).max() <= tol * nmax2 * (2 / (ub - lb)).max()
     fit = orc.chebcoefs_fft(g[f"{name}_fitvals"], N)            # the FFT stand-in against the long-double cosine sums
     assert np.abs(fit - g[f"{name}_fitcoefs"]).max() <= 1e-14 * np.abs(g[f"{name}_fitcoefs"]).max()
+
+
+def test_simd_baseline_variant_is_bit_identical(orc):
+    """The component-vectorised evaluation used for the timed CPU baseline == the line-faithful restatement."""
+    rng = np.random.default_rng(9)
+    for dims, K, cplx in (((33, 33, 33), 3, False), ((9, 8), None, False), ((5, 4, 3, 6), 2, True), ((7,), 2, False),
+                          ((2, 1, 3), 3, True), ((6, 5), 5, False)):
+        shape = dims + ((K,) if K else ())
+        c = rng.uniform(-1, 1, shape) + (1j * rng.uniform(-1, 1, shape) if cplx else 0)
+        N = len(dims)
+        p = orc.OracleChebPoly(c, -np.ones(N), np.ones(N))
+        x = rng.uniform(-1, 1, (257, N))
+        x = x if N > 1 else x[:, 0]
+        assert np.array_equal(p(x), p.eval_simd(x))
