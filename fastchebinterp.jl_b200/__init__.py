@@ -36,7 +36,7 @@ import ctypes
 import numpy as np
 
 from . import _capi
-from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA  # noqa: F401
+from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA, ALGO_DMMA_RING  # noqa: F401
 
 __all__ = ["rrule", "frule", "chebregression", "chebvandermonde", "eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
            "droptol", "roots", "colleague_matrix", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libfastcheb_cuda.so")
 F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 OK, EDOMAIN, ENONFINITE, EDIMMISMATCH, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = range(8)
-ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA = 0, 1, 2
+ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA, ALGO_DMMA_RING = 0, 1, 2, 3
 MAX_NDIM = 6
 
 # every symbol include/fastcheb.h declares (tests check the library exports all of them)

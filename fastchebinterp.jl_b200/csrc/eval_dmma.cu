@@ -15,6 +15,50 @@ DmmaFn dmma_fn(int ks, bool jac) {
   }
   return nullptr;
 }
+typedef cudaError_t (*Dmma2dFn)(int, int, const Dmma2dParams&, int, int, size_t, cudaStream_t);
+Dmma2dFn dmma2d_fn(int ks, bool jac) {
+  switch (ks) {
+    case 4: return jac ? dmma2d_dispatch_ks4_jac : dmma2d_dispatch_ks4_val;
+    case 8: return jac ? dmma2d_dispatch_ks8_jac : dmma2d_dispatch_ks8_val;
+    case 16: return jac ? dmma2d_dispatch_ks16_jac : dmma2d_dispatch_ks16_val;
+  }
+  return nullptr;
+}
+
+// Launch geometry of the resident 2-D kernel for one component group; warps == 0: does not apply (the weight
+// tables hold k2 <= 4 KS + 1, and the tile records plus the per-warp tables must fit shared memory).
+struct Plan2d {
+  int warps = 0, nscratch = 0, nmma = 0, ntail = 0;
+  size_t smem = 0;
+};
+Plan2d plan2d(const fastcheb_poly* p, int ec, bool jac, int64_t npts) {
+  Plan2d q;
+  const DmmaPlan& pl = p->dmma;
+  const int n2 = (int)p->dims[1];
+  if (p->ndim != 2 || n2 > 4 * pl.KS + 2 || p->algo == FASTCHEB_ALGO_DMMA_RING) return q;
+  const int rem = n2 % 8;
+  q.nmma = (rem == 1 || rem == 2) ? n2 / 8 : pl.ntiles;
+  q.ntail = n2 - 8 * q.nmma > 0 ? n2 - 8 * q.nmma : 0;
+  const int rows = jac ? 8 : 16;
+  // fewer warps for small batches (spread over the SMs), as in the ring kernel
+  int warps = kDmma2dThreads / 32;
+  const long long per_sm = (npts + (long long)p->di->sms * rows - 1) / ((long long)p->di->sms * rows);
+  if (per_sm < warps) warps = (int)std::max<long long>(1, per_sm);
+  const size_t budget = std::min<size_t>(p->di->smem_optin, kSmemOptinMax);
+  for (; warps >= 4 || (warps >= 1 && per_sm < 4); --warps) {
+    // as many scratch tables as fit, at least one per four warps (a warp holds one for ~5 % of a unit)
+    int ns = warps;
+    while (ns > 0 && dmma2d_smem(ec, pl.KS, jac, pl.ntiles, warps, ns) > budget) --ns;
+    if (ns >= (warps + 3) / 4 && ns >= 1) {
+      q.warps = warps;
+      q.nscratch = ns;
+      q.smem = dmma2d_smem(ec, pl.KS, jac, pl.ntiles, warps, ns);
+      return q;
+    }
+    if (warps == 1) break;
+  }
+  return q;
+}
 }  // namespace
 
 int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
@@ -83,6 +127,37 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
   const int U = pl.KS * 32 + 8;
   const int rows = dmma_mt(jac) * 8;
   for (const DmmaGroup& g : pl.groups) {
+    if (const Plan2d q = plan2d(p, g.ec, jac, npts); q.warps > 0) {  // 2-D, tile records resident in shared memory
+      Dmma2dParams prm;
+      memset(&prm, 0, sizeof prm);
+      prm.frag = (const double*)pl.d_frag + g.offset;
+      prm.pts = pts;
+      prm.out_v = out_v;
+      prm.out_J = out_J;
+      prm.bad = (&g == &pl.groups[0]) ? bad_dev : nullptr;
+      prm.npts = npts;
+      prm.idx_base = idx_base;
+      prm.v_stride = v_stride;
+      prm.J_stride = J_stride;
+      prm.mode = mode;
+      prm.tan = tan;
+      prm.e0 = g.e0;
+      prm.Etot = p->E;
+      prm.ntiles = pl.ntiles;
+      prm.nmma = q.nmma;
+      prm.ntail = q.ntail;
+      prm.nscratch = q.nscratch;
+      for (int d = 0; d < 2; ++d) {
+        prm.lb[d] = p->lb[d];
+        prm.ub[d] = p->ub[d];
+      }
+      const long long nunits = (npts + rows - 1) / rows;
+      // every CTA's warp 0 owns at least one unit (it is the warp that waits for the CTA's bulk copy)
+      const int grid = (int)std::min<long long>((nunits + q.warps - 1) / q.warps, (long long)p->di->sms);
+      cudaError_t e = dmma2d_fn(pl.KS, jac)(p->dtype, g.ec, prm, q.warps * 32, grid, q.smem, st);
+      if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "2-D DMMA kernel launch failed: %s", cudaGetErrorString(e));
+      continue;
+    }
     DmmaParams prm;
     memset(&prm, 0, sizeof prm);
     prm.frag = (const double*)pl.d_frag + g.offset;

@@ -1,6 +1,7 @@
 // Host-side entry points of the DMMA evaluation path (eval_dmma.cuh).
 #pragma once
 #include "eval_dmma.cuh"
+#include "eval_dmma2d.cuh"
 #include "poly.h"
 
 namespace fastcheb {
@@ -16,6 +17,14 @@ cudaError_t dmma_dispatch_ks16_val(int op, int dtype, int ndim, int ec, const Dm
 cudaError_t dmma_dispatch_ks4_jac(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
 cudaError_t dmma_dispatch_ks8_jac(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
 cudaError_t dmma_dispatch_ks16_jac(int op, int dtype, int ndim, int ec, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps);
+
+// resident 2-D kernels (eval_dmma2d.cuh), one translation unit per (KS, JAC)
+cudaError_t dmma2d_dispatch_ks4_val(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
+cudaError_t dmma2d_dispatch_ks8_val(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
+cudaError_t dmma2d_dispatch_ks16_val(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
+cudaError_t dmma2d_dispatch_ks4_jac(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
+cudaError_t dmma2d_dispatch_ks8_jac(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
+cudaError_t dmma2d_dispatch_ks16_jac(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
 
 // decide whether the handle gets a DMMA plan and build the fragment stream (no-op when not applicable)
 int dmma_plan(fastcheb_poly* p, cudaStream_t st);

@@ -313,9 +313,10 @@ int fastcheb_get_coefs(const fastcheb_poly* p, void* dst, int dst_mem) {
 
 int fastcheb_set_algo(fastcheb_poly* p, int algo) {
   if (!p) return fail(FASTCHEB_EINVAL, "null handle");
-  if (algo == FASTCHEB_ALGO_DMMA && !p->dmma.ok)
+  if ((algo == FASTCHEB_ALGO_DMMA || algo == FASTCHEB_ALGO_DMMA_RING) && !p->dmma.ok)
     return fail(FASTCHEB_EUNSUPPORTED, "the DMMA path needs ndim >= 2, n1 >= 5 and at least 8 coefficient columns");
-  if (algo != FASTCHEB_ALGO_AUTO && algo != FASTCHEB_ALGO_CLENSHAW && algo != FASTCHEB_ALGO_DMMA)
+  if (algo != FASTCHEB_ALGO_AUTO && algo != FASTCHEB_ALGO_CLENSHAW && algo != FASTCHEB_ALGO_DMMA &&
+      algo != FASTCHEB_ALGO_DMMA_RING)
     return fail(FASTCHEB_EINVAL, "bad algo %d", algo);
   p->algo = algo;
   return FASTCHEB_OK;

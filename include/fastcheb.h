@@ -61,6 +61,7 @@ extern "C" {
 #define FASTCHEB_ALGO_AUTO 0
 #define FASTCHEB_ALGO_CLENSHAW 1 /* CUDA-core Clenshaw, one thread per point            */
 #define FASTCHEB_ALGO_DMMA 2     /* FP64 tensor-core first-dimension contraction (F64)   */
+#define FASTCHEB_ALGO_DMMA_RING 3 /* same, but never the shared-memory-resident 2-D kernel */
 
 typedef struct fastcheb_poly fastcheb_poly; /* device-resident ChebPoly{N,T,Td} (FastChebInterp.jl:37-41) */
 

@@ -29,6 +29,16 @@ CASES = [
     ((3, 1, 4), None, False, np.float64),
     ((34, 3), None, False, np.float64),
     ((5, 70), 3, False, np.float64),
+    # 2-D shapes of the shared-memory-resident tensor-core kernel (eval_dmma2d.cuh): trailing columns k2 = 8j+1 / 8j+2
+    # contracted on the CUDA cores (from the tail slots and from the main weight table), every KS, EC = 1..3, two groups
+    ((33, 33), 3, False, np.float64),
+    ((17, 10), None, True, np.float32),
+    ((65, 66), None, False, np.float64),
+    ((65, 67), None, False, np.float64),         # n2 > 4 KS + 2: falls back to the ring kernel
+    ((65, 33), 2, False, np.float64),
+    ((40, 16), None, False, np.float64),
+    ((9, 9), 5, False, np.float64),
+    ((30, 25), 2, True, np.float64),
     ((4, 3, 5, 2, 3), 2, False, np.float64),     # 5-D and 6-D: the Clenshaw nest covers FASTCHEB_MAX_NDIM
     ((3, 2, 4, 2, 3, 2), None, True, np.float64),
     ((3, 3, 2, 2, 2, 3), 3, False, np.float32),
@@ -83,6 +93,9 @@ def test_value_parity(fc, orc, case):
         assert poly.get_algo(False, dt) == fc.ALGO_DMMA
         got2 = poly(pts)
         assert np.abs(got2 - ref).max() <= tol, f"DMMA: {np.abs(got2 - ref).max():.3e} > {tol:.3e}"
+        poly.set_algo(fc.ALGO_DMMA_RING, dt)      # 2-D: the streaming kernel instead of the resident one
+        got3 = poly(pts)
+        assert np.abs(got3 - ref).max() <= tol, f"DMMA ring: {np.abs(got3 - ref).max():.3e} > {tol:.3e}"
     # single-point call == the batched entry (runtests.jl:176-178)
     one = poly(pts[5] if len(dims) > 1 else pts[5, 0])
     poly.set_algo(fc.ALGO_AUTO, dt)
@@ -113,6 +126,39 @@ def test_jacobian_parity(fc, orc, case):
         for d, n in enumerate(dims):
             told = tol * max(1, (n - 1) ** 2) * 2 / (ub[d] - lb[d])
             assert np.abs(J2[:, :, d] - J0[:, :, d]).max() <= told, (d, np.abs(J2[:, :, d] - J0[:, :, d]).max(), told)
+        poly.set_algo(fc.ALGO_DMMA_RING, dt)
+        v3, J3 = fc.chebjacobian(poly, pts)
+        assert np.abs(v3 - v0).max() <= tol
+        for d, n in enumerate(dims):
+            told = tol * max(1, (n - 1) ** 2) * 2 / (ub[d] - lb[d])
+            assert np.abs(J3[:, :, d] - J0[:, :, d]).max() <= told
+
+
+@pytest.mark.parametrize("K,npts", [(None, 150_011), (3, 60_007)], ids=["scalar", "K3"])
+def test_resident_2d_full_ctas(fc, orc, K, npts):
+    """configs[1] shape (order (64,64)) at a batch large enough that the resident 2-D kernel runs with all of its
+    warps, so the A-fragment scratch tables are shared under their locks; out-of-domain index from a late unit."""
+    case = ((65, 65), K, False, np.float64)
+    rng, c, lb, ub = make(*case, seed=21)
+    pts = points(rng, lb, ub, npts, np.float64)
+    ref = orc.OracleChebPoly(c, lb, ub)
+    poly = fc.ChebPoly(c, lb, ub)
+    poly.set_algo(fc.ALGO_DMMA)
+    tol = 16 * np.finfo(float).eps * np.abs(c).sum()
+    v0, J0 = ref.jacobian(pts)
+    assert np.abs(poly(pts) - v0).max() <= tol
+    v, J = fc.chebjacobian(poly, pts)
+    assert np.abs(v - v0).max() <= tol
+    for d in range(2):
+        assert np.abs(J[:, :, d] - J0[:, :, d]).max() <= tol * 64 ** 2 * 2 / (ub[d] - lb[d])
+    bad = pts.copy()
+    bad[npts - 3, 1] = ub[1] + 1.0
+    bad[npts - 2, 0] = np.nan
+    with pytest.raises(fc.ArgumentError) as ei:
+        poly(bad)
+    assert str(bad[npts - 3]) in str(ei.value)    # the FIRST offending point is reported
+    with pytest.raises(fc.ArgumentError):
+        fc.chebjacobian(poly, bad)
 
 
 def test_gradient_shapes_and_errors(fc, orc):

@@ -18,6 +18,8 @@ from fastcheb import _capi  # noqa: E402
 CONFIGS = [
     ("cfg1: 1-D order 200 real F64", (201,), None, False, np.float64, 1 << 24),
     ("cfg2: 2-D order (64,64) real F64", (65, 65), None, False, np.float64, 1 << 24),
+    ("2-D order (64,64) SVector{3} F64", (65, 65), 3, False, np.float64, 1 << 23),
+    ("2-D order (32,32) real F64", (33, 33), None, False, np.float64, 1 << 24),
     ("cfg3: 3-D order (32,32,32) SVector{3} F64", (33, 33, 33), 3, False, np.float64, 1 << 23),
     ("cfg3 scalar: 3-D order (32,32,32) real F64", (33, 33, 33), None, False, np.float64, 1 << 23),
     ("cfg4: 4-D order (16,16,16,16) ComplexF64", (17,) * 4, None, True, np.float64, 1 << 22),
@@ -60,9 +62,12 @@ def main():
         status = torch.zeros(1, dtype=torch.int64, device=dev)
         h = poly._handle(dt)
         sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        for algo in ("dmma", "clenshaw"):
+        for algo in ("dmma", "dmma_ring", "clenshaw"):
+            if algo == "dmma_ring" and N != 2:   # only 2-D has a second tensor-core kernel (resident vs ring)
+                continue
             try:
-                poly.set_algo(fastcheb.ALGO_DMMA if algo == "dmma" else fastcheb.ALGO_CLENSHAW, rdt=dt)
+                poly.set_algo({"dmma": fastcheb.ALGO_DMMA, "dmma_ring": fastcheb.ALGO_DMMA_RING,
+                               "clenshaw": fastcheb.ALGO_CLENSHAW}[algo], rdt=dt)
             except Exception:
                 continue
             for jac in (False, True):
