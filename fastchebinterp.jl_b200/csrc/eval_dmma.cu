@@ -1,5 +1,6 @@
 // Host side of the DMMA evaluation path: plan (fragment re-layout) and launch.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "eval_dmma_launch.h"
 
@@ -41,7 +42,12 @@ Plan2d plan2d(const fastcheb_poly* p, int ec, bool jac, int64_t npts) {
   q.ntail = n2 - 8 * q.nmma > 0 ? n2 - 8 * q.nmma : 0;
   const int rows = jac ? 8 : 16;
   // fewer warps for small batches (spread over the SMs), as in the ring kernel
-  int warps = kDmma2dThreads / 32;
+  static const int tuned = [] {  // experiments only: FASTCHEB_2D_WARPS=n caps the warps per CTA
+    const char* e = getenv("FASTCHEB_2D_WARPS");
+    const int v = e ? atoi(e) : 0;
+    return v >= 1 && v <= kDmma2dThreads / 32 ? v : kDmma2dThreads / 32;
+  }();
+  int warps = tuned;
   const long long per_sm = (npts + (long long)p->di->sms * rows - 1) / ((long long)p->di->sms * rows);
   if (per_sm < warps) warps = (int)std::max<long long>(1, per_sm);
   const size_t budget = std::min<size_t>(p->di->smem_optin, kSmemOptinMax);

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
 
   extern __shared__ __align__(128) unsigned char fastcheb_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(fastcheb_smem);
-  unsigned int* locks = reinterpret_cast<unsigned int*>(fastcheb_smem + 16);  // <= 16 scratch locks
+  unsigned int* counter = reinterpret_cast<unsigned int*>(fastcheb_smem + 8);  // units drawn by this CTA's warps
+  unsigned int* locks = reinterpret_cast<unsigned int*>(fastcheb_smem + 16);    // <= 16 scratch locks
   double* recs = reinterpret_cast<double*>(fastcheb_smem + 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncw = blockDim.x >> 5;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     mbar_init(full, 1);
+    *counter = 0;
     for (int i = 0; i < 16; ++i) locks[i] = 0;
     fence_mbar_init();
     const uint32_t bytes = (uint32_t)prm.ntiles * TR * 8u;
@@ -111,20 +113,28 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
   double* const ttail = tails + (size_t)(tkind * ROWS + trow) * 2;
   const R tlb = (R)prm.lb[tdim], tub = (R)prm.ub[tdim];
 
+  // Units of ROWS consecutive points; a CTA owns a contiguous range and its warps draw units from a shared-memory
+  // counter (warps differ in speed — scratch-lock waits, their share of the FP64 pipe — and with a static split
+  // the slow ones finished last with the pipe mostly idle: 14.5 of 16 warps active on average).
   const long long nunits = (prm.npts + ROWS - 1) / ROWS;
-  const long long ustride = (long long)gridDim.x * ncw;
-  long long unit = (long long)blockIdx.x * ncw + warp;
+  const long long ubeg = nunits * blockIdx.x / gridDim.x, uend = nunits * (blockIdx.x + 1) / gridDim.x;
+  auto draw = [&]() -> long long {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1u);
+    return ubeg + __shfl_sync(0xffffffffu, t, 0);
+  };
   auto load_x = [&](long long u) -> R {
     const long long i = u * ROWS + trow;
-    return (u < nunits && i < prm.npts) ? pts_in[i * N + tdim] : tlb;
+    return (u < uend && i < prm.npts) ? pts_in[i * N + tdim] : tlb;
   };
+  long long unit = draw(), unit_next = draw();
   R xn = load_x(unit);
   bool first = true;
 
-  for (; unit < nunits; unit += ustride) {
+  for (; unit < uend; unit = unit_next, unit_next = draw()) {
     const long long base = unit * ROWS;
     const R x = xn;
-    xn = load_x(unit + ustride);  // prefetch: consumed a whole unit later
+    xn = load_x(unit_next);  // prefetch: consumed a whole unit later
     const bool in = (tlb <= x) && (x <= tub);  // eval.jl:64
     const double z = in ? (double)rsub(rdiv(rmul(rsub(x, tlb), R(2)), rsub(tub, tlb)), R(1)) : 0.0;  // eval.jl:65
     const unsigned inmask = __ballot_sync(0xffffffffu, in);
@@ -137,8 +147,7 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
     // ---- tables: T_k (or k U_{k-1}) for k = 1..KA+1, one recurrence per lane ----
     if (shared_scratch) {
       if (lane == 0) {
-        while (atomicCAS(&locks[sidx], 0u, 1u) != 0u) {
-        }
+        while (atomicCAS(&locks[sidx], 0u, 1u) != 0u) __nanosleep(100);
         __threadfence_block();
       }
     }
@@ -211,90 +220,83 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
 
     double acc[MT][EC];
     double accJ[JAC ? MT : 1][JAC ? EC : 1][JAC ? N : 1];
-    double pg0[MT], pg1[MT];
-    [[maybe_unused]] double ph0[JAC ? MT : 1], ph1[JAC ? MT : 1];
-    double w[MT][2];
-    [[maybe_unused]] double wd[JAC ? MT : 1][2];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      pg0[mt] = pg1[mt] = 0.0;
-      w[mt][0] = w[mt][1] = 0.0;
-      if constexpr (JAC) {
-        ph0[mt] = ph1[mt] = 0.0;
-        wd[mt][0] = wd[mt][1] = 0.0;
-      }
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int e = 0; e < EC; ++e) {
         acc[mt][e] = 0.0;
         if constexpr (JAC) accJ[mt][e][0] = accJ[mt][e][1] = 0.0;
       }
-    }
-    // software-pipelined weighted fold, as in dmma_kernel: chain e is folded after chain e+1 has been issued
-    auto fold = [&](auto ec) {
-      constexpr int e = decltype(ec)::value;
+    // NTL column tiles at a time: NTL * MT (* 2 with the derivative) independent accumulator chains per warp, so that
+    // one or two warps in this loop keep the DMMA pipe of their SM sub-partition busy while the others are in the
+    // latency-bound prologue.  The chains are folded with the weights T_{k2}(z2) right after their last k-step, the
+    // oldest chain first.
+    auto tiles = [&](auto ntl, const double* rec, int tile) {
+      constexpr int NTL = decltype(ntl)::value;
+      double w[NTL][MT][2];
+      [[maybe_unused]] double wd[NTL][JAC ? MT : 1][2];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        acc[mt][e] = fma(pg0[mt], w[mt][0], acc[mt][e]);
-        acc[mt][e] = fma(pg1[mt], w[mt][1], acc[mt][e]);
-        if constexpr (JAC) {
-          accJ[mt][e][0] = fma(ph0[mt], w[mt][0], accJ[mt][e][0]);
-          accJ[mt][e][0] = fma(ph1[mt], w[mt][1], accJ[mt][e][0]);
-          accJ[mt][e][1] = fma(pg0[mt], wd[mt][0], accJ[mt][e][1]);
-          accJ[mt][e][1] = fma(pg1[mt], wd[mt][1], accJ[mt][e][1]);
-        }
-      }
-    };
-    const double* rec = recs;
-    for (int tile = 0; tile < prm.nmma; ++tile, rec += TR) {
-      auto chain = [&](auto ec) {
-        constexpr int e = decltype(ec)::value;
-        const double* u = rec + kDmmaMeta + e * U;
-        const double2 c0 = *reinterpret_cast<const double2*>(u + 2 * c);
-        double g0[MT], g1[MT];
-        [[maybe_unused]] double h0[JAC ? MT : 1], h1[JAC ? MT : 1];
+      for (int t = 0; t < NTL; ++t) {
+        const int k = 8 * (tile + t) + 2 * c;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          g0[mt] = c0.x;  // k1 = 0 term: T_0 = 1
-          g1[mt] = c0.y;
-          if constexpr (JAC) h0[mt] = h1[mt] = 0.0;
+          w[t][mt][0] = wload(mt, k, false);
+          w[t][mt][1] = wload(mt, k + 1, false);
+          if constexpr (JAC) {
+            wd[t][mt][0] = wload(mt, k, true);
+            wd[t][mt][1] = wload(mt, k + 1, true);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < EC; ++e) {
+        const double* u = rec + kDmmaMeta + e * U;
+        double g0[NTL][MT], g1[NTL][MT];
+        [[maybe_unused]] double h0[NTL][JAC ? MT : 1], h1[NTL][JAC ? MT : 1];
+#pragma unroll
+        for (int t = 0; t < NTL; ++t) {
+          const double2 c0 = *reinterpret_cast<const double2*>(u + t * TR + 2 * c);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            g0[t][mt] = c0.x;  // k1 = 0 term: T_0 = 1
+            g1[t][mt] = c0.y;
+            if constexpr (JAC) h0[t][mt] = h1[t][mt] = 0.0;
+          }
         }
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          const double bf = u[8 + ks * 32 + lane];
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            dmma884(g0[mt], g1[mt], A[mt][ks], bf);
-            if constexpr (JAC) dmma884(h0[mt], h1[mt], Ad[mt][ks], bf);
-          }
-        }
-        fold(std::integral_constant<int, (e == 0 ? EC - 1 : e - 1)>{});
-        if constexpr (e == 0) {  // the pending chain of the previous tile is folded: the weights move on to this tile
-          const int k = 8 * tile + 2 * c;
+          for (int t = 0; t < NTL; ++t) {
+            const double bf = u[t * TR + 8 + ks * 32 + lane];
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            w[mt][0] = wload(mt, k, false);
-            w[mt][1] = wload(mt, k + 1, false);
-            if constexpr (JAC) {
-              wd[mt][0] = wload(mt, k, true);
-              wd[mt][1] = wload(mt, k + 1, true);
+            for (int mt = 0; mt < MT; ++mt) {
+              dmma884(g0[t][mt], g1[t][mt], A[mt][ks], bf);
+              if constexpr (JAC) dmma884(h0[t][mt], h1[t][mt], Ad[mt][ks], bf);
             }
           }
         }
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          pg0[mt] = g0[mt];
-          pg1[mt] = g1[mt];
-          if constexpr (JAC) {
-            ph0[mt] = h0[mt];
-            ph1[mt] = h1[mt];
+        for (int t = 0; t < NTL; ++t)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            acc[mt][e] = fma(g0[t][mt], w[t][mt][0], acc[mt][e]);
+            acc[mt][e] = fma(g1[t][mt], w[t][mt][1], acc[mt][e]);
+            if constexpr (JAC) {
+              accJ[mt][e][0] = fma(h0[t][mt], w[t][mt][0], accJ[mt][e][0]);
+              accJ[mt][e][0] = fma(h1[t][mt], w[t][mt][1], accJ[mt][e][0]);
+              accJ[mt][e][1] = fma(g0[t][mt], wd[t][mt][0], accJ[mt][e][1]);
+              accJ[mt][e][1] = fma(g1[t][mt], wd[t][mt][1], accJ[mt][e][1]);
+            }
           }
-        }
-      };
-      chain(std::integral_constant<int, 0>{});
-      if constexpr (EC > 1) chain(std::integral_constant<int, 1>{});
-      if constexpr (EC > 2) chain(std::integral_constant<int, 2>{});
+      }
+    };
+    const double* rec = recs;
+    int tile = 0;
+    for (; tile + 2 <= prm.nmma; tile += 2, rec += 2 * TR) tiles(std::integral_constant<int, 2>{}, rec, tile);
+    if (tile < prm.nmma) {
+      tiles(std::integral_constant<int, 1>{}, rec, tile);
+      rec += TR;
     }
-    fold(std::integral_constant<int, EC - 1>{});  // the last chain of the unit
 
     // ---- trailing columns on the CUDA cores: each lane contracts the k1 it holds, the quad sum finishes it ----
     for (int j = 0; j < prm.ntail; ++j) {
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
       }
     }
   }
+  if (first) mbar_wait(full, 0);  // never leave with the CTA's bulk copy still in flight
 }
 
 }  // namespace fastcheb
