@@ -254,6 +254,19 @@ int main() {
     report("dmma1688_ch4", warps * 4 * ITERS * 2.0 * 16 * 8 * 8, time_kernel([&] { k_dmma1688<4><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps), ex);
     report("dmma1684_ch4", warps * 4 * ITERS * 2.0 * 16 * 8 * 4, time_kernel([&] { k_dmma1684<4><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps), ex);
   }
+  // DMMA dependent-issue latency: ONE warp per SM sub-partition (128 threads per SM), CH independent accumulator chains.
+  // Throughput saturates once CH * 16 cycles (the issue interval of an m8n8k4 DMMA per sub-partition) covers the latency.
+  {
+    const double warps = (double)sms * 4;
+    report("dmma884_1warp_per_smsp_ch1", warps * 1 * ITERS * 512.0, time_kernel([&] { k_dmma884<1><<<sms, 128>>>(out, 1.0000001, 1e-9); }, reps), "");
+    report("dmma884_1warp_per_smsp_ch2", warps * 2 * ITERS * 512.0, time_kernel([&] { k_dmma884<2><<<sms, 128>>>(out, 1.0000001, 1e-9); }, reps), "");
+    report("dmma884_1warp_per_smsp_ch3", warps * 3 * ITERS * 512.0, time_kernel([&] { k_dmma884<3><<<sms, 128>>>(out, 1.0000001, 1e-9); }, reps), "");
+    report("dmma884_1warp_per_smsp_ch4", warps * 4 * ITERS * 512.0, time_kernel([&] { k_dmma884<4><<<sms, 128>>>(out, 1.0000001, 1e-9); }, reps), "");
+    report("dmma884_1warp_per_smsp_ch6", warps * 6 * ITERS * 512.0, time_kernel([&] { k_dmma884<6><<<sms, 128>>>(out, 1.0000001, 1e-9); }, reps), "");
+    report("dmma884_1warp_per_smsp_ch8", warps * 8 * ITERS * 512.0, time_kernel([&] { k_dmma884<8><<<sms, 128>>>(out, 1.0000001, 1e-9); }, reps), "");
+    report("dmma884_2warp_per_smsp_ch2", 2 * warps * 2 * ITERS * 512.0, time_kernel([&] { k_dmma884<2><<<sms, 256>>>(out, 1.0000001, 1e-9); }, reps), "");
+    report("dmma884_2warp_per_smsp_ch4", 2 * warps * 4 * ITERS * 512.0, time_kernel([&] { k_dmma884<4><<<sms, 256>>>(out, 1.0000001, 1e-9); }, reps), "");
+  }
   {
     int grid = sms * 4; double thr = (double)grid * threads; double warps = thr / 32;
     // report total flops (dmma + dfma); compare with dmma-only and dfma-only to see overlap

@@ -29,7 +29,7 @@ Dmma2dFn dmma2d_fn(int ks, bool jac) {
 // Launch geometry of the resident 2-D kernel for one component group; warps == 0: does not apply (the weight
 // tables hold k2 <= 4 KS + 1, and the tile records plus the per-warp tables must fit shared memory).
 struct Plan2d {
-  int warps = 0, nscratch = 0, nmma = 0, ntail = 0;
+  int warps = 0, nmma = 0, ntail = 0;
   size_t smem = 0;
 };
 Plan2d plan2d(const fastcheb_poly* p, int ec, bool jac, int64_t npts) {
@@ -51,18 +51,11 @@ Plan2d plan2d(const fastcheb_poly* p, int ec, bool jac, int64_t npts) {
   const long long per_sm = (npts + (long long)p->di->sms * rows - 1) / ((long long)p->di->sms * rows);
   if (per_sm < warps) warps = (int)std::max<long long>(1, per_sm);
   const size_t budget = std::min<size_t>(p->di->smem_optin, kSmemOptinMax);
-  for (; warps >= 4 || (warps >= 1 && per_sm < 4); --warps) {
-    // as many scratch tables as fit, at least one per four warps (a warp holds one for ~5 % of a unit)
-    int ns = warps;
-    while (ns > 0 && dmma2d_smem(ec, pl.KS, jac, pl.ntiles, warps, ns) > budget) --ns;
-    if (ns >= (warps + 3) / 4 && ns >= 1) {
-      q.warps = warps;
-      q.nscratch = ns;
-      q.smem = dmma2d_smem(ec, pl.KS, jac, pl.ntiles, warps, ns);
-      return q;
-    }
-    if (warps == 1) break;
-  }
+  for (; warps >= 1; --warps)
+    if (dmma2d_smem(ec, pl.KS, jac, pl.ntiles, warps) <= budget) break;
+  if (warps < 1 || (warps < 4 && per_sm >= 4)) return q;  // too few warps to hide the prologue: use the ring kernel
+  q.warps = warps;
+  q.smem = dmma2d_smem(ec, pl.KS, jac, pl.ntiles, warps);
   return q;
 }
 }  // namespace
@@ -152,7 +145,6 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
       prm.ntiles = pl.ntiles;
       prm.nmma = q.nmma;
       prm.ntail = q.ntail;
-      prm.nscratch = q.nscratch;
       for (int d = 0; d < 2; ++d) {
         prm.lb[d] = p->lb[d];
         prm.ub[d] = p->ub[d];

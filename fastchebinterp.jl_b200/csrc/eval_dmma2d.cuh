@@ -14,10 +14,10 @@
 //     after that warps never synchronise with each other, so the latency-bound prologue of one warp
 //     hides under the DMMAs of the others;
 //   * the Chebyshev recurrences of a pass are run once per (point, dimension) — one lane each — into
-//     shared memory instead of once per lane of a quad: T_k(z1) goes through a small scratch table into
-//     the A fragments (registers), T_k(z2) stays in the warp's weight table.  Both tables are rotated by
-//     a row-dependent amount inside 16-column blocks so that the column-wise stores of the prologue AND
-//     the fragment / weight loads of the tile loop are bank-conflict free;
+//     shared memory instead of once per lane of a quad: T_k(z1) goes, 16 values at a time, through a
+//     2 KB scratch block of the warp into the A fragments (registers), T_k(z2) stays in the warp's weight
+//     table.  Both are rotated by a row-dependent amount inside 16-column blocks so that the column-wise
+//     stores of the prologue AND the fragment / weight loads of the tile loop are bank-conflict free;
 //   * when n2 = 8j+1 or 8j+2 (every power-of-two order), the 1-2 trailing columns are contracted with
 //     DFMAs from the A fragments already in registers instead of a whole, mostly padded DMMA tile
 //     (order 64: 8 tiles instead of 9);
@@ -42,7 +42,6 @@ struct Dmma2dParams {
   int ntiles;    // tile records (all resident in shared memory)
   int nmma;      // leading tiles contracted on the tensor cores
   int ntail;     // 0..2 trailing columns k2 = 8*nmma + j, contracted with DFMAs from tile record `nmma`
-  int nscratch;  // A-fragment scratch tables in shared memory (<= warps; shared under a lock when fewer)
   double lb[2], ub[2];
   const void* tan;
   int mode;
@@ -50,11 +49,10 @@ struct Dmma2dParams {
 
 constexpr int kDmma2dThreads = 512;
 
-// shared-memory bytes of a launch with `warps` warps and `nscratch` scratch tables
-__host__ __device__ constexpr size_t dmma2d_smem(int EC, int KS, bool JAC, int ntiles, int warps, int nscratch) {
+// shared-memory bytes of a launch with `warps` warps: tile records + per warp [weight table | tail slots | scratch block]
+__host__ __device__ constexpr size_t dmma2d_smem(int EC, int KS, bool JAC, int ntiles, int warps) {
   const size_t rows = JAC ? 8 : 16, nt = JAC ? 2 : 1, KA = 4 * (size_t)KS;
-  return 128 + 8 * ((size_t)ntiles * (kDmmaMeta + EC * (KS * 32 + 8)) + (size_t)warps * nt * rows * (KA + 2) +
-                    (size_t)nscratch * nt * rows * KA);
+  return 128 + 8 * ((size_t)ntiles * (kDmmaMeta + EC * (KS * 32 + 8)) + (size_t)warps * nt * rows * (KA + 2 + 16));
 }
 
 template <typename R, int EC, int KS, bool JAC>
@@ -73,20 +71,16 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
   extern __shared__ __align__(128) unsigned char fastcheb_smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(fastcheb_smem);
   unsigned int* counter = reinterpret_cast<unsigned int*>(fastcheb_smem + 8);  // units drawn by this CTA's warps
-  unsigned int* locks = reinterpret_cast<unsigned int*>(fastcheb_smem + 16);    // <= 16 scratch locks
   double* recs = reinterpret_cast<double*>(fastcheb_smem + 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncw = blockDim.x >> 5;
   double* t2 = recs + (size_t)prm.ntiles * TR + (size_t)warp * NT * ROWS * KA;  // [NT][ROWS][KA], rotated
   double* tails = recs + (size_t)prm.ntiles * TR + (size_t)ncw * NT * ROWS * KA + (size_t)warp * NT * ROWS * 2;
-  const int sidx = warp % prm.nscratch;
-  double* sA = recs + (size_t)prm.ntiles * TR + (size_t)ncw * NT * ROWS * (KA + 2) + (size_t)sidx * NT * ROWS * KA;
-  const bool shared_scratch = prm.nscratch < ncw;
+  double* sA = recs + (size_t)prm.ntiles * TR + (size_t)ncw * NT * ROWS * (KA + 2) + (size_t)warp * NT * ROWS * 16;
 
   if (threadIdx.x == 0) {
     mbar_init(full, 1);
     *counter = 0;
-    for (int i = 0; i < 16; ++i) locks[i] = 0;
     fence_mbar_init();
     const uint32_t bytes = (uint32_t)prm.ntiles * TR * 8u;
     mbar_arrive_expect_tx(full, bytes);
@@ -108,14 +102,13 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
   auto rotT = [](int row) { return (row & 1) + 8 * ((row >> 1) & 1) + 2 * (row >> 2); };
   // the task stores value k (1..KA) at position k-1 (A scratch) or k (weight table): position j + tdim for j = k-1
   const int trot = (tdim ? rotT(trow) : rotA(trow)) + tdim;
-  double* const tbase = (tdim ? t2 : sA) + (size_t)(tkind * ROWS + trow) * KA;
-  const int t16 = tdim * 16;
+  double* const tbase = tdim ? t2 + (size_t)(tkind * ROWS + trow) * KA : sA + (tkind * ROWS + trow) * 16;
   double* const ttail = tails + (size_t)(tkind * ROWS + trow) * 2;
   const R tlb = (R)prm.lb[tdim], tub = (R)prm.ub[tdim];
 
   // Units of ROWS consecutive points; a CTA owns a contiguous range and its warps draw units from a shared-memory
-  // counter (warps differ in speed — scratch-lock waits, their share of the FP64 pipe — and with a static split
-  // the slow ones finished last with the pipe mostly idle: 14.5 of 16 warps active on average).
+  // counter (warps differ in speed — their share of the FP64 pipe — and with a static split the slow ones finished
+  // last with the pipe mostly idle: 14.5 of 16 warps active on average).
   const long long nunits = (prm.npts + ROWS - 1) / ROWS;
   const long long ubeg = nunits * blockIdx.x / gridDim.x, uend = nunits * (blockIdx.x + 1) / gridDim.x;
   auto draw = [&]() -> long long {
@@ -144,62 +137,48 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
     const unsigned badrows = liverows & ~okrows;
     if (badrows && lane == 0 && prm.bad) atomicMin(prm.bad, base + (__ffs(badrows) - 1) + prm.idx_base);
 
-    // ---- tables: T_k (or k U_{k-1}) for k = 1..KA+1, one recurrence per lane ----
-    if (shared_scratch) {
-      if (lane == 0) {
-        while (atomicCAS(&locks[sidx], 0u, 1u) != 0u) __nanosleep(100);
-        __threadfence_block();
-      }
-    }
-    __syncwarp();  // the previous unit has finished reading this warp's tables (and the scratch is ours)
+    // ---- tables: T_k (or k U_{k-1}) for k = 1..KA+1, one recurrence per lane; the A fragments are picked up from
+    //      the warp's 16-column scratch block after every 16 steps ----
+    double A[MT][KS];
+    double Ad[JAC ? MT : 1][JAC ? KS : 1];
+    __syncwarp();  // the previous unit has finished reading this warp's tables
     {
       const double z2 = 2.0 * z;
       double prev = tkind ? 0.0 : 1.0, cur = tkind ? 1.0 : z;
       if (tdim) tbase[(trot - 1) & 15] = tkind ? 0.0 : 1.0;  // k2 = 0: T_0 = 1, T'_0 = 0
 #pragma unroll
-      for (int j = 0; j < KA; ++j) {  // value index k = j + 1
-        double val = cur;
-        if constexpr (JAC) val = cur * (tkind ? (double)(j + 1) : 1.0);
-        if (j < KA - 1) {
-          const int hi = (j & ~15) + ((j & 15) == 15 ? t16 : 0);
-          tbase[hi + ((j + trot) & 15)] = val;
-        } else {
-          if (tdim)
+      for (int q = 0; q < KS / 4; ++q) {
+        if (q > 0) __syncwarp();  // the A loads of the previous round are done: the scratch block may be overwritten
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = 16 * q + jj;  // value index k = j + 1
+          double val = cur;
+          if constexpr (JAC) val = cur * (tkind ? (double)(j + 1) : 1.0);
+          if (j == KA - 1 && tdim)
             ttail[0] = val;  // k2 = KA
           else
-            tbase[(j & ~15) + ((j + trot) & 15)] = val;
+            tbase[(tdim ? (j & ~15) + (jj == 15 ? 16 : 0) : 0) + ((j + trot) & 15)] = val;
+          const double nx = fma(z2, cur, -prev);
+          prev = cur;
+          cur = nx;
         }
-        const double nx = fma(z2, cur, -prev);
-        prev = cur;
-        cur = nx;
+        __syncwarp();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int row = mt * 8 + r;
+          const int b0 = c + rotA(row);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // T_k(z1), k = 1 + 4*ks + c, ks = 4q + i, of rows r (+8)
+            A[mt][4 * q + i] = sA[row * 16 + ((b0 + 4 * i) & 15)];
+            if constexpr (JAC) Ad[mt][4 * q + i] = sA[(ROWS + row) * 16 + ((b0 + 4 * i) & 15)];
+          }
+        }
       }
       double val = cur;  // k = KA + 1 (second tail column)
       if constexpr (JAC) val = cur * (tkind ? (double)(KA + 1) : 1.0);
       if (tdim) ttail[1] = val;
     }
     __syncwarp();
-
-    // ---- A fragments: T_k(z1), k = 1 + 4*ks + c, of rows r (+8) ----
-    double A[MT][KS];
-    double Ad[JAC ? MT : 1][JAC ? KS : 1];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const int row = mt * 8 + r;
-      const int b = c + rotA(row);
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int o = ((4 * ks) & ~15) + ((b + 4 * ks) & 15);
-        A[mt][ks] = sA[(size_t)row * KA + o];
-        if constexpr (JAC) Ad[mt][ks] = sA[(size_t)(ROWS + row) * KA + o];
-      }
-    }
-    if (shared_scratch) {
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence_block();
-        atomicExch(&locks[sidx], 0u);
-      }
-    }
     if (first) {
       mbar_wait(full, 0);  // the tile records have landed (overlapped with the first prologue)
       first = false;
