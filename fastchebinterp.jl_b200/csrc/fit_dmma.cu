@@ -18,7 +18,7 @@ struct AFrag {
   size_t doubles = 0;
 };
 std::mutex g_mu;
-std::map<std::pair<int, int>, AFrag> g_afrag;  // (device, n)
+std::map<std::pair<int, int>, AFrag> g_afrag;  // (device, 4 n + slot map)
 
 // cos(pi r / N) with r reduced exactly, so that the symmetries of the transform hold bit for bit
 long double cospi_ratio(long long r, int N) {
@@ -30,9 +30,20 @@ long double cospi_ratio(long long r, int N) {
   return -cosl(pi * (long double)(N - r) / (long double)N);
 }
 
-int get_afrag(int dev, int n, AFrag* out) {
+// slot map of the launch (fit_dmma.cuh): the tuned, bank-conflict-free ones exist for n = 65
+int fit_slot_map(int n, int dtype) {
+  static const bool plain = [] {  // experiments: FASTCHEB_FIT_MAP=0 forces the plain map
+    const char* e = getenv("FASTCHEB_FIT_MAP");
+    return e && atoi(e) == 0;
+  }();
+  return (n == 65 && !plain && dtype == FASTCHEB_F32) ? 1 : 0;
+}
+
+// map != 0 implies the split odd half (parts P, Q), map == 0 the unsplit one (part O)
+int get_afrag(int dev, int n, int map, AFrag* out) {
   std::lock_guard<std::mutex> lk(g_mu);
-  auto key = std::make_pair(dev, n);
+  auto key = std::make_pair(dev, 4 * n + map);
+  const bool split = map != 0;
   auto it = g_afrag.find(key);
   if (it != g_afrag.end()) {
     *out = it->second;
@@ -49,7 +60,8 @@ int get_afrag(int dev, int n, AFrag* out) {
   a.kb = (Jb + 3) / 4;
   a.kc = (Jc + 3) / 4;
   const int mo = (a.ko + 1) / 2, mb = (a.kb + 1) / 2, mc = (a.kc + 1) / 2;
-  a.doubles = (size_t)(mo * a.ko + mb * a.kb + mc * a.kc) * 32;
+  // two folds: the odd half is split once more by the parity of j (parts P and Q, fit_dmma.cuh) and replaces part O
+  a.doubles = (size_t)(split ? 2 * mc * a.kc : mo * a.ko) * 32 + (size_t)(mb * a.kb + mc * a.kc) * 32;
   std::vector<double> h(a.doubles, 0.0);
   // REDFT00 (interp.jl:44) with the scaling of interp.jl:49-54 folded in: output k, folded input j carrying REDFT00
   // weight w (end points and self-paired middle elements count once, everything else twice)
@@ -61,13 +73,26 @@ int get_afrag(int dev, int n, AFrag* out) {
     for (int mt = 0; mt < M; ++mt)
       for (int ks = 0; ks < K; ++ks)
         for (int l = 0; l < 32; ++l) {
-          const int row = 8 * mt + l / 4, j = 4 * ks + l % 4, k = kstride * row + koff;
+          const int row = 8 * mt + l / 4, j = fit_map_j(map, ks, l % 4), k = kstride * row + koff;
           if (row < J && j < J && k <= N) h[off + (size_t)(mt * K + ks) * 32 + l] = entry(k, j, j == 0 || j == selfpair);
         }
   };
   size_t off = 0;
-  fill(off, a.ko, mo, Jo, 2, 1, -1);                                  // part O: k = 2l+1, b_j
-  off += (size_t)mo * a.ko * 32;
+  if (split) {
+    // parts P, Q: row l (k = 2l+1, l < N/4), column i: b_{2i} resp. b_{2i+1}; b_0 = x_0 - x_N carries weight 1
+    for (int odd = 0; odd < 2; ++odd) {
+      for (int mt = 0; mt < mc; ++mt)
+        for (int ks = 0; ks < a.kc; ++ks)
+          for (int l = 0; l < 32; ++l) {
+            const int row = 8 * mt + l / 4, i = fit_map_i(map, ks, l % 4), j = 2 * i + odd;
+            if (row < Jc && i < Jc) h[off + (size_t)(mt * a.kc + ks) * 32 + l] = entry(2 * row + 1, j, j == 0);
+          }
+      off += (size_t)mc * a.kc * 32;
+    }
+  } else {
+    fill(off, a.ko, mo, Jo, 2, 1, -1);                                  // part O: k = 2l+1, b_j
+    off += (size_t)mo * a.ko * 32;
+  }
   if (two) {
     fill(off, a.kb, mb, Jb, 4, 0, H / 2);                               // part B: k = 4l, aa_j (self-paired at j = N/4)
     off += (size_t)mb * a.kb * 32;
@@ -82,9 +107,9 @@ int get_afrag(int dev, int n, AFrag* out) {
   return FASTCHEB_OK;
 }
 
-template <typename R, int KO, int KB, int KC, int NT, bool E1>
+template <typename R, int KO, int KB, int KC, int NT, bool E1, int MAP = 0, bool SPLIT = false>
 cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
-  auto kern = fit_dmma_kernel<R, KO, KB, KC, NT, E1>;
+  auto kern = fit_dmma_kernel<R, KO, KB, KC, NT, E1, MAP, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
   if (e != cudaSuccess) return e;
   if (bps) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
@@ -94,8 +119,14 @@ cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem,
 }
 
 template <typename R>
-cudaError_t dispatch(int ko, int kb, int kc, bool e1, const FitDmmaParams& prm, int grid, int threads, size_t smem,
-                     cudaStream_t st, int* bps) {
+cudaError_t dispatch(int ko, int kb, int kc, bool e1, int map, const FitDmmaParams& prm, int grid, int threads,
+                     size_t smem, cudaStream_t st, int* bps) {
+  if (map != 0) {  // n = 65 with the tuned slot map of this precision
+    constexpr int M = sizeof(R) == 4 ? 1 : 2;
+    if (ko != 8 || kb != 5 || kc != 4 || map != M) return cudaErrorInvalidValue;
+    return e1 ? launch<R, 8, 5, 4, 1, true, M, true>(prm, grid, threads, smem, st, bps)
+              : launch<R, 8, 5, 4, 1, false, M, true>(prm, grid, threads, smem, st, bps);
+  }
 #define FC_CASE(A, B, C)                                                                   \
   if (ko == A && kb == B && kc == C)                                                       \
     return e1 ? launch<R, A, B, C, 1, true>(prm, grid, threads, smem, st, bps)             \
@@ -154,13 +185,15 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   // launch shape: FASTCHEB_FIT_TUNE="warps,slots,nt" overrides the defaults (benchmark sweeps)
   // measured best on B200 (profiles/r01_fit_sweep.txt): Float64 is HBM-bound with 16 warps; Float32 units are half
   // the bytes, so 24 warps fit and the (then DMMA-bound) kernel wants them.  NT = 2 is not instantiated.
-  int warps = dtype == FASTCHEB_F64 ? 16 : 24, S = 3, NT = 1;
+  int warps = dtype == FASTCHEB_F64 ? 16 : 24, S = 3, NT = 1, lag = 1;
   if (const char* t = getenv("FASTCHEB_FIT_TUNE")) {
-    int a = 0, b = 0, c = 0;
-    if (sscanf(t, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && a <= 24 && b >= 2 && a * b <= 128 && c == 1) {
+    int a = 0, b = 0, c = 0, d = 1;
+    const int got = sscanf(t, "%d,%d,%d,%d", &a, &b, &c, &d);
+    if (got >= 3 && a >= 1 && a <= 24 && b >= 2 && a * b <= 128 && c == 1 && (d == 1 || d == 2) && b > d) {
       warps = a;
       S = b;
       NT = c;
+      lag = d;
     }
   }
   const int rs = (int)real_size(dtype);
@@ -173,7 +206,8 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   const long long nunits = howmany / U;
   if (nunits < 1) return FASTCHEB_OK;
   AFrag af;
-  FC_TRY(get_afrag(dev, n, &af));
+  const int map = fit_slot_map(n, dtype);
+  FC_TRY(get_afrag(dev, n, map, &af));
   FitDmmaParams prm;
   memset(&prm, 0, sizeof prm);
   prm.src = vals;
@@ -190,9 +224,10 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   prm.slotBytes = (prm.unitBytes + 127) / 128 * 128;
   const size_t afragBytes = (af.doubles * 8 + 127) / 128 * 128;
   const size_t budget = di->smem_optin - 1024;
-  while (1024 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > 2) --S;
+  while (1024 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > lag + 1) --S;
   while (1024 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && warps > 1) --warps;
   prm.nslots = S;
+  prm.lag = lag;
   const size_t smem = 1024 + afragBytes + (size_t)warps * S * prm.slotBytes;
   if (smem > budget) return FASTCHEB_OK;
   double* linemax = nullptr;
@@ -205,8 +240,8 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   int bps = 0;
   cudaError_t e;
   auto go = [&](int* bp, int grid) {
-    if (dtype == FASTCHEB_F64) return dispatch<double>(af.ko, af.kb, af.kc, E == 1, prm, grid, threads, smem, st, bp);
-    return dispatch<float>(af.ko, af.kb, af.kc, E == 1, prm, grid, threads, smem, st, bp);
+    if (dtype == FASTCHEB_F64) return dispatch<double>(af.ko, af.kb, af.kc, E == 1, map, prm, grid, threads, smem, st, bp);
+    return dispatch<float>(af.ko, af.kb, af.kc, E == 1, map, prm, grid, threads, smem, st, bp);
   };
   e = go(&bps, 0);
   if (e != cudaSuccess || bps < 1) {

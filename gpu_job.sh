@@ -1,4 +1,4 @@
-mkdir -p gpurun_out
-export BENCH_ONLY="cfg2"
-ncu --set full --clock-control none --import-source on -k regex:dmma2d_kernel -s 3 -c 1 -o gpurun_out/r01_dmma2d_val_v3 -f python tools/bench_configs.py > gpurun_out/ncu_2d.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:dmma2d_kernel -s 11 -c 1 -o gpurun_out/r01_dmma2d_jac_v3 -f python tools/bench_configs.py > gpurun_out/ncu_2dj.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_fit.py tests/test_gpu_golden.py tests/test_gpu_fullsize.py tests/test_gpu_roots.py -x -q -m gpu 2>&1 | tail -3
+for dt in f64 f32; do
+python bench.py --workload fit1d --steps 20 --warmup 3 --dtype $dt --no-cpu --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$dt 2^20', round(d['roofline']['frac'],4), d['ms_per_step'], d['max_rel_err_vs_oracle'])"
+done
