@@ -26,16 +26,6 @@ Dmma2dFn dmma2d_fn(int ks, bool jac) {
   return nullptr;
 }
 
-typedef cudaError_t (*DmmaRowsFn)(int, int, int, int, const DmmaRowsParams&, int, int, size_t, cudaStream_t);
-DmmaRowsFn dmma_rows_fn(int ks) {
-  switch (ks) {
-    case 4: return dmma_rows_dispatch_ks4;
-    case 8: return dmma_rows_dispatch_ks8;
-    case 16: return dmma_rows_dispatch_ks16;
-  }
-  return nullptr;
-}
-
 // Launch geometry of the resident 2-D kernel for one component group; warps == 0: does not apply (the weight
 // tables hold k2 <= 4 KS + 1, and the tile records plus the per-warp tables must fit shared memory).
 struct Plan2d {
@@ -123,36 +113,6 @@ int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
     FC_CUDA(cudaGetLastError());
     note_launch();
   }
-  // row-aligned stream for the 3-D / 4-D value kernel: n2 = 8 TPR + {0,1,2}, TPR in {1,2,4}
-  if (p->ndim == 3 || p->ndim == 4) {
-    const int n2 = (int)p->dims[1];
-    const int tpr = n2 / 8, tail = n2 % 8;
-    if ((tpr == 1 || tpr == 2 || tpr == 4) && tail <= 2) {
-      pl.TPR = tpr;
-      pl.ntail = tail;
-      pl.nrows = pl.M / n2;
-      size_t roff = 0;
-      for (DmmaGroup& g : pl.groups) {
-        g.rows_offset = roff;
-        roff += (size_t)pl.nrows * dmma_rows_row_doubles(g.ec, pl.KS, tpr, tail);
-      }
-      pl.rows_bytes = roff * sizeof(double);
-      FC_CUDA(cudaMalloc(&pl.d_rows, pl.rows_bytes));
-      for (const DmmaGroup& g : pl.groups) {
-        const int rowDoubles = dmma_rows_row_doubles(g.ec, pl.KS, tpr, tail);
-        const long long total = (long long)pl.nrows * rowDoubles;
-        const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)p->di->sms * 16));
-        if (p->dtype == FASTCHEB_F64)
-          relayout_rows_kernel<double><<<grid, 256, 0, st>>>((const double*)p->d_coefs, (double*)pl.d_rows + g.rows_offset,
-                                                            total, p->E, g.e0, g.ec, n1, n2, pl.KS, tpr, tail, rowDoubles);
-        else
-          relayout_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)p->d_coefs, (double*)pl.d_rows + g.rows_offset,
-                                                           total, p->E, g.e0, g.ec, n1, n2, pl.KS, tpr, tail, rowDoubles);
-        FC_CUDA(cudaGetLastError());
-        note_launch();
-      }
-    }
-  }
   pl.ok = true;
   return FASTCHEB_OK;
 }
@@ -166,48 +126,6 @@ int dmma_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
   const int U = pl.KS * 32 + 8;
   const int rows = dmma_mt(jac) * 8;
   for (const DmmaGroup& g : pl.groups) {
-    if (!jac && mode == 0 && pl.TPR > 0 && p->algo != FASTCHEB_ALGO_DMMA_RING) {  // 3-D / 4-D values: tiles aligned to rows
-      DmmaRowsParams prm;
-      memset(&prm, 0, sizeof prm);
-      prm.stream = (const double*)pl.d_rows + g.rows_offset;
-      prm.pts = pts;
-      prm.out_v = out_v;
-      prm.bad = (&g == &pl.groups[0]) ? bad_dev : nullptr;
-      prm.npts = npts;
-      prm.idx_base = idx_base;
-      prm.v_stride = v_stride;
-      prm.e0 = g.e0;
-      int tab = 0;
-      for (int d = 0; d < p->ndim; ++d) {
-        prm.n[d] = (int)p->dims[d];
-        prm.lb[d] = p->lb[d];
-        prm.ub[d] = p->ub[d];
-        if (d >= 2) tab += (int)p->dims[d];
-      }
-      prm.nrows = pl.nrows;
-      prm.ntail = pl.ntail;
-      prm.rowDoubles = dmma_rows_row_doubles(g.ec, pl.KS, pl.TPR, pl.ntail);
-      prm.tabStride = tab | 1;
-      // a stage holds about four tiles (as in the ring kernel); three stages of look-ahead
-      prm.rowsPerStage = std::min(pl.nrows, std::max(1, 4 / pl.TPR));
-      prm.nstage = 3;
-      int warps = kDmmaRowsThreads / 32;
-      const long long per_sm = (npts + (long long)p->di->sms * 16 - 1) / ((long long)p->di->sms * 16);
-      if (per_sm < warps) warps = (int)std::max<long long>(1, per_sm);
-      const size_t budget = std::min<size_t>(p->di->smem_optin, kSmemOptinMax);
-      auto smem_of = [&](int w) {
-        return 128 + (size_t)prm.nstage * prm.rowsPerStage * prm.rowDoubles * 8 + (size_t)w * 16 * prm.tabStride * 8;
-      };
-      while (warps > 1 && smem_of(warps) > budget) --warps;
-      if (smem_of(warps) <= budget) {
-        const long long pass_pts = (long long)warps * 16;
-        const long long npass = (npts + pass_pts - 1) / pass_pts;
-        const int grid = (int)std::min<long long>(npass, (long long)p->di->sms);
-        cudaError_t e = dmma_rows_fn(pl.KS)(p->dtype, p->ndim, g.ec, pl.TPR, prm, warps * 32, grid, smem_of(warps), st);
-        if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "row-aligned DMMA kernel launch failed: %s", cudaGetErrorString(e));
-        continue;
-      }
-    }
     if (const Plan2d q = plan2d(p, g.ec, jac, npts); q.warps > 0) {  // 2-D, tile records resident in shared memory
       Dmma2dParams prm;
       memset(&prm, 0, sizeof prm);

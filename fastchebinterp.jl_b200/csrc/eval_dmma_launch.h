@@ -2,7 +2,6 @@
 #pragma once
 #include "eval_dmma.cuh"
 #include "eval_dmma2d.cuh"
-#include "eval_dmma_rows.cuh"
 #include "poly.h"
 
 namespace fastcheb {
@@ -26,11 +25,6 @@ cudaError_t dmma2d_dispatch_ks16_val(int dtype, int ec, const Dmma2dParams& prm,
 cudaError_t dmma2d_dispatch_ks4_jac(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
 cudaError_t dmma2d_dispatch_ks8_jac(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
 cudaError_t dmma2d_dispatch_ks16_jac(int dtype, int ec, const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
-
-// row-aligned 3-D / 4-D value kernels (eval_dmma_rows.cuh), one translation unit per KS
-cudaError_t dmma_rows_dispatch_ks4(int dtype, int ndim, int ec, int tpr, const DmmaRowsParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
-cudaError_t dmma_rows_dispatch_ks8(int dtype, int ndim, int ec, int tpr, const DmmaRowsParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
-cudaError_t dmma_rows_dispatch_ks16(int dtype, int ndim, int ec, int tpr, const DmmaRowsParams& prm, int threads, int grid, size_t smem, cudaStream_t st);
 
 // decide whether the handle gets a DMMA plan and build the fragment stream (no-op when not applicable)
 int dmma_plan(fastcheb_poly* p, cudaStream_t st);

@@ -286,7 +286,6 @@ int fastcheb_destroy(fastcheb_poly* p) {
   for (auto& g : p->groups)
     if (g.d_pp) cudaFree(g.d_pp);
   if (p->dmma.d_frag) cudaFree(p->dmma.d_frag);
-  if (p->dmma.d_rows) cudaFree(p->dmma.d_rows);
   if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
   cudaGetLastError();
   delete p;

@@ -20,8 +20,7 @@ struct ClenshawGroup {
 // DMMA-path plan (FP64, ndim >= 2); see eval_dmma.cuh
 struct DmmaGroup {
   int e0 = 0, ec = 0;
-  size_t offset = 0;       // doubles into d_frag
-  size_t rows_offset = 0;  // doubles into d_rows
+  size_t offset = 0;  // doubles into d_frag
 };
 struct DmmaPlan {
   bool ok = false;
@@ -31,10 +30,6 @@ struct DmmaPlan {
   int M = 0;          // columns per component = prod(n2..nN)
   int ntiles = 0;     // ceil(M / 8)
   int tabStride = 0;  // doubles per point row of the weight tables
-  // row-aligned stream of the 3-D / 4-D value kernel (eval_dmma_rows.cuh); TPR == 0: the shape does not qualify
-  void* d_rows = nullptr;
-  size_t rows_bytes = 0;
-  int TPR = 0, ntail = 0, nrows = 0;
   std::vector<DmmaGroup> groups;
 };
 

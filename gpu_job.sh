@@ -1,10 +1,10 @@
-set -x
 mkdir -p gpurun_out
-python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
-python bench.py --workload fit1d --steps 20 --warmup 3 > gpurun_out/bench_fit1d_f64.json
-python bench.py --workload fit1d --steps 20 --warmup 3 --dtype f32 > gpurun_out/bench_fit1d_f32.json
-python bench.py --workload fit1d --steps 20 --warmup 3 --howmany 100000 --no-cpu > gpurun_out/bench_fit1d_f64_1e5.json
-python bench.py --workload fit1d --steps 20 --warmup 3 --howmany 100000 --no-cpu --dtype f32 > gpurun_out/bench_fit1d_f32_1e5.json
-CMDF="python bench.py --workload fit1d --steps 2 --warmup 3 --no-cpu --no-e2e --dtype f32"
-ncu --set full --clock-control none --import-source on -k regex:fit_dmma_kernel -s 3 -c 1 -o gpurun_out/r01_fit_dmma_v7_f32 -f $CMDF > gpurun_out/ncu_ff32.log 2>&1
-grep -o '"frac": [0-9.]*' gpurun_out/bench_fit1d_*.json
+timeout 900 python -m pytest tests/test_gpu_eval.py tests/test_gpu_golden.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -5
+BENCH_ONLY="cfg3" timeout 300 python tools/bench_configs.py 2>/dev/null | grep '"dmma' | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['config'][:44], d['algo'], d['mode'], round(d['frac_of_fp_peak'], 4))"
+BENCH_ONLY="cfg4" timeout 300 python tools/bench_configs.py 2>/dev/null | grep '"dmma' | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['config'][:44], d['algo'], d['mode'], round(d['frac_of_fp_peak'], 4))"

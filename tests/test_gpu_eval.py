@@ -39,6 +39,11 @@ CASES = [
     ((40, 16), None, False, np.float64),
     ((9, 9), 5, False, np.float64),
     ((30, 25), 2, True, np.float64),
+    # 3-D / 4-D shapes of the row-aligned value kernel (eval_dmma_rows.cuh): n2 = 8 TPR + {0,1,2}, TPR = 1, 2, 4
+    ((33, 34, 5), None, False, np.float64),      # two trailing columns
+    ((9, 16, 6, 3), 2, False, np.float64),       # no trailing column, 4-D
+    ((65, 17, 4), None, True, np.float32),       # KS = 16
+    ((12, 10, 7), 4, False, np.float64),         # two component groups
     ((4, 3, 5, 2, 3), 2, False, np.float64),     # 5-D and 6-D: the Clenshaw nest covers FASTCHEB_MAX_NDIM
     ((3, 2, 4, 2, 3, 2), None, True, np.float64),
     ((3, 3, 2, 2, 2, 3), 3, False, np.float32),
