@@ -139,6 +139,28 @@ __global__ void __launch_bounds__(256) k_mix(double* out, double a, double b) {
   if (s == 12345.678) out[0] = s;
 }
 
+// As k_mix, but every DFMA consumes the accumulator of a DMMA chain (like the weighted fold of the evaluation kernels):
+// GROUP DMMAs of one chain, then NF DFMAs that read that chain's result.
+template <int GROUP, int NF>
+__global__ void __launch_bounds__(256) k_mix_dep(double* out, double a, double b) {
+  double d0[4], d1[4], x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { d0[i] = threadIdx.x * 1e-9; d1[i] = i; x[i] = i; }
+  for (int it = 0; it < ITERS / GROUP; ++it) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int g = 0; g < GROUP; ++g) dmma884(d0[i], d1[i], a, b);
+#pragma unroll
+      for (int j = 0; j < NF; ++j) x[i] = fma(j & 1 ? d1[i] : d0[i], a, x[i]);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += d0[i] + d1[i] + x[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 // ---------------------------------------------------------------- DFMA fed by broadcast LDS
 // Each DFMA group consumes coefficients loaded from shared memory at a warp-uniform address.
 // W = doubles per LDS (1 -> LDS.64, 2 -> LDS.128), P = points (independent chains) per thread
@@ -253,6 +275,21 @@ int main() {
     report("dmma884_ch8", warps * 8 * ITERS * 2.0 * 8 * 8 * 4, time_kernel([&] { k_dmma884<8><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps), ex);
     report("dmma1688_ch4", warps * 4 * ITERS * 2.0 * 16 * 8 * 8, time_kernel([&] { k_dmma1688<4><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps), ex);
     report("dmma1684_ch4", warps * 4 * ITERS * 2.0 * 16 * 8 * 4, time_kernel([&] { k_dmma1684<4><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps), ex);
+  }
+  {  // GROUP-DMMA chains each followed by NF dependent DFMAs; pipe_cycles = 16 per DMMA + 2 per DFMA if nothing is lost
+    int grid = sms * 2; double thr = (double)grid * threads; double warps = thr / 32;
+    auto rep2 = [&](const char* name, int group, int nf, float ms) {
+      const double dm = warps * 4 * (ITERS / group) * group, df = warps * 4 * (ITERS / group) * nf;
+      const double ideal_cycles = (dm * 16 + df * 2) / (sms * 4.0);
+      printf("{\"test\":\"%s\",\"ms\":%.4f,\"pipe_busy_if_no_loss\":%.3f,\"extra_cycles_per_dfma\":%.2f}\n", name, ms,
+             ideal_cycles / (ms * 1e-3 * 1.965e9), (ms * 1e-3 * 1.965e9 - ideal_cycles) * (sms * 4.0) / df);
+      fflush(stdout);
+    };
+    rep2("mixdep_g8_f2", 8, 2, time_kernel([&] { k_mix_dep<8, 2><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps));
+    rep2("mixdep_g8_f4", 8, 4, time_kernel([&] { k_mix_dep<8, 4><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps));
+    rep2("mixdep_g16_f4", 16, 4, time_kernel([&] { k_mix_dep<16, 4><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps));
+    rep2("mixdep_g16_f8", 16, 8, time_kernel([&] { k_mix_dep<16, 8><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps));
+    rep2("mixdep_g4_f2", 4, 2, time_kernel([&] { k_mix_dep<4, 2><<<grid, threads>>>(out, 1.0000001, 1e-9); }, reps));
   }
   // DMMA dependent-issue latency: ONE warp per SM sub-partition (128 threads per SM), CH independent accumulator chains.
   // Throughput saturates once CH * 16 cycles (the issue interval of an m8n8k4 DMMA per sub-partition) covers the latency.
