@@ -1,10 +1,6 @@
-set -x
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; cut -c1-300 gpurun_out/bench_default.json
-python bench.py --steps 5 --warmup 3 --mode jac --no-cpu > gpurun_out/bench_jac.json 2>/dev/null; cut -c1-200 gpurun_out/bench_jac.json
-python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-300 gpurun_out/bench_ref.json
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01_launches.csv $CMD > gpurun_out/ncu_l.log 2>&1
-CMDF="python bench.py --workload fit1d --steps 2 --warmup 3 --no-cpu --no-e2e"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/r01_launches_fit.csv $CMDF > gpurun_out/ncu_lf.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fit_dmma_kernel -s 3 -c 1 -o gpurun_out/r01_fit_dmma_v7 -f $CMDF > gpurun_out/ncu_ff.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_fit.py tests/test_gpu_golden.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -5
+for dt in f64 f32; do
+python bench.py --workload fit1d --steps 20 --warmup 3 --dtype $dt --no-cpu --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$dt 2^20', round(d['roofline']['frac'],4), d['ms_per_step'])"
+python bench.py --workload fit1d --steps 50 --warmup 5 --dtype $dt --howmany 100000 --no-cpu --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$dt 1e5', round(d['roofline']['frac'],4), d['ms_per_step'])"
+done

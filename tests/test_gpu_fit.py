@@ -44,6 +44,29 @@ def test_chebcoefs_complex_and_batched(fc, orc):
         assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max(), n
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("kind", ["K3", "complex", "K2complex"])
+def test_batched_order64_vector_and_complex(fc, orc, dt, kind):
+    """Batched order-64 fits with E = 3, 2 and 4 inline reals per element: units with dead lines (E = 3 -> 2 fits =
+    6 of 8 lines) and strided lines on the tensor-core path, incl. the Float32 slot maps; non-finite detection."""
+    rng = np.random.default_rng(29)
+    howmany = 501
+    if kind == "K3":
+        vals = rng.uniform(-1, 1, (howmany, 65, 3)).astype(dt)
+    else:
+        shape = (howmany, 65) + ((2,) if kind == "K2complex" else ())
+        vals = (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(np.complex128 if dt == np.float64 else np.complex64)
+    got = fc.chebcoefs(vals, ndim=1, howmany=howmany)
+    assert got.shape == vals.shape and got.dtype == vals.dtype
+    wide = vals.astype(np.complex128 if np.iscomplexobj(vals) else np.float64)
+    want = np.stack([orc.chebcoefs(x, 1) for x in wide])
+    assert np.abs(got - want).max() <= tol_for(dt) * np.abs(want).max()
+    bad = vals.copy()
+    bad[417, 33] = np.nan
+    with pytest.raises(fc.DomainError):
+        fc.chebcoefs(bad, ndim=1, howmany=howmany)
+
+
 def test_nonfinite_raises_domainerror(fc):
     v = np.ones((9, 9))
     v[3, 4] = np.inf
