@@ -158,6 +158,14 @@ bool use_dmma(const fastcheb_poly* p, bool jac) {
   if (!p->dmma.ok) return false;
   if (p->algo == FASTCHEB_ALGO_CLENSHAW) return false;
   (void)jac;
+  if (p->algo == FASTCHEB_ALGO_AUTO) {
+    // Measured on B200 (tools/bench_configs.py with BENCH_SHAPES): the MMA K extent is padded to 4 KS = 16, 32 or 64
+    // slots, and the Clenshaw kernel runs at ~30 % of FP64 peak whatever the shape, so the tensor-core path only wins
+    // when dimension 1 fills most of its slots and there are a few column tiles to amortise a pass over
+    // (5x8, 9x9, 5x40, 9x9x9: Clenshaw 1.1-1.7x faster; 33x9: equal; 17x17, 17^3, 6^4, 9^4 and up: DMMA 1.1-2.9x).
+    const int n1 = (int)p->dims[0];
+    if (5 * (n1 - 1) < 3 * 4 * p->dmma.KS || p->dmma.M < 16) return p->ndim >= 4 && n1 >= 6;
+  }
   return true;
 }
 

@@ -1,6 +1,1 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_fit.py tests/test_gpu_golden.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -5
-for dt in f64 f32; do
-python bench.py --workload fit1d --steps 20 --warmup 3 --dtype $dt --no-cpu --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$dt 2^20', round(d['roofline']['frac'],4), d['ms_per_step'])"
-python bench.py --workload fit1d --steps 50 --warmup 5 --dtype $dt --howmany 100000 --no-cpu --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$dt 1e5', round(d['roofline']['frac'],4), d['ms_per_step'])"
-done
+timeout 900 python -m pytest tests/test_gpu_eval.py tests/test_gpu_adrules.py tests/test_gpu_regression.py tests/test_gpu_roots.py -x -q -m gpu 2>&1 | tail -3

@@ -29,6 +29,12 @@ CONFIGS = [
 ]
 
 
+# extra real-Float64 shapes from the environment (AUTO-threshold checks): BENCH_SHAPES="9x9,17x17x17"
+for _s in filter(None, os.environ.get("BENCH_SHAPES", "").split(",")):
+    _d = tuple(int(v) for v in _s.split("x"))
+    CONFIGS.append((f"shape {_s} real F64", _d, None, False, np.float64, 1 << 22))
+
+
 def work(dims, E, jac):
     N = len(dims)
     Sd = [int(np.prod(dims[d:])) for d in range(N)]
