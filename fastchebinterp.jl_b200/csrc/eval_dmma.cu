@@ -12,6 +12,7 @@ DmmaFn dmma_fn(int ks, bool jac) {
   switch (ks) {
     case 4: return jac ? dmma_dispatch_ks4_jac : dmma_dispatch_ks4_val;
     case 8: return jac ? dmma_dispatch_ks8_jac : dmma_dispatch_ks8_val;
+    case 12: return jac ? dmma_dispatch_ks12_jac : dmma_dispatch_ks12_val;
     case 16: return jac ? dmma_dispatch_ks16_jac : dmma_dispatch_ks16_val;
   }
   return nullptr;
@@ -21,6 +22,7 @@ Dmma2dFn dmma2d_fn(int ks, bool jac) {
   switch (ks) {
     case 4: return jac ? dmma2d_dispatch_ks4_jac : dmma2d_dispatch_ks4_val;
     case 8: return jac ? dmma2d_dispatch_ks8_jac : dmma2d_dispatch_ks8_val;
+    case 12: return jac ? dmma2d_dispatch_ks12_jac : dmma2d_dispatch_ks12_val;
     case 16: return jac ? dmma2d_dispatch_ks16_jac : dmma2d_dispatch_ks16_val;
   }
   return nullptr;
@@ -74,7 +76,7 @@ int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
   }
   if (M < 8 || M > (1 << 28)) return FASTCHEB_OK;  // fewer than one column tile: the Clenshaw path is the right tool
   if (tab > 1024) return FASTCHEB_OK;              // weight tables would not fit shared memory
-  pl.KS = n1 - 1 <= 16 ? 4 : (n1 - 1 <= 32 ? 8 : 16);
+  pl.KS = n1 - 1 <= 16 ? 4 : (n1 - 1 <= 32 ? 8 : (n1 - 1 <= 48 ? 12 : 16));
   pl.M = (int)M;
   pl.ntiles = (int)((M + 7) / 8);
   pl.tabStride = tab | 1;  // odd row stride: spreads the rows over the banks

@@ -44,6 +44,9 @@ CASES = [
     ((9, 16, 6, 3), 2, False, np.float64),       # no trailing column, 4-D
     ((65, 17, 4), None, True, np.float32),       # KS = 16
     ((12, 10, 7), 4, False, np.float64),         # two component groups
+    ((41, 41), None, False, np.float64),         # 33 < n1 <= 49: 12 k-steps
+    ((45, 9, 5), 2, False, np.float32),
+    ((49, 50), None, True, np.float64),          # n2 = 4 KS + 2 at KS = 12
     ((4, 3, 5, 2, 3), 2, False, np.float64),     # 5-D and 6-D: the Clenshaw nest covers FASTCHEB_MAX_NDIM
     ((3, 2, 4, 2, 3, 2), None, True, np.float64),
     ((3, 3, 2, 2, 2, 3), 3, False, np.float32),
