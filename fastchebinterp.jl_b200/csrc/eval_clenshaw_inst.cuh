@@ -8,9 +8,9 @@ template <int N, int EC>
 cudaError_t go(int op, const EvalParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps) {
   constexpr int P = clenshaw_pts(N, EC, FC_JAC);
   auto kern = clenshaw_kernel<FC_REAL, N, EC, P, FC_JAC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
-  if (op == kOpOccupancy) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
+  if (op == kOpOccupancy) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
   kern<<<grid, threads, smem, st>>>(prm);
   note_launch();
   return cudaGetLastError();

@@ -94,7 +94,7 @@ int dmma_plan(fastcheb_poly* p, cudaStream_t st) {
     e0 += ec;
   }
   pl.frag_bytes = off * sizeof(double);
-  FC_CUDA(cudaMalloc(&pl.d_frag, pl.frag_bytes));
+  FC_CUDA(pool_alloc(&pl.d_frag, pl.frag_bytes, st));
   FragDims fd;
   memset(&fd, 0, sizeof fd);
   fd.nd = p->ndim - 1;

@@ -6,7 +6,7 @@ namespace {
 template <typename R, int EC>
 cudaError_t go2d(const Dmma2dParams& prm, int threads, int grid, size_t smem, cudaStream_t st) {
   auto kern = dmma2d_kernel<R, EC, FC_KS, FC_JAC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   kern<<<grid, threads, smem, st>>>(prm);
   note_launch();

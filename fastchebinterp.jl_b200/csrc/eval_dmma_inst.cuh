@@ -6,9 +6,9 @@ namespace {
 template <typename R, int N, int EC>
 cudaError_t go(int op, const DmmaParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps) {
   auto kern = dmma_kernel<R, N, EC, FC_KS, FC_JAC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
-  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
+  if (op == 1) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
   kern<<<grid, threads, smem, st>>>(prm);
   note_launch();
   return cudaGetLastError();

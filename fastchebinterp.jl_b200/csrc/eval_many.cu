@@ -107,10 +107,10 @@ cudaError_t launch(const ManyParams& prm, int sms, cudaStream_t st) {
   const int warps = 8;
   const size_t smem = (size_t)warps * prm.n * E * sizeof(R);
   auto kern = eval_many_kernel<R, E, P, DER>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   int bps = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, warps * 32, smem);
+  e = cached_occupancy(&bps, reinterpret_cast<const void*>(kern), warps * 32, smem);
   if (e != cudaSuccess) return e;
   const long long want = (prm.howmany + warps - 1) / warps;
   const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * std::max(1, bps)));

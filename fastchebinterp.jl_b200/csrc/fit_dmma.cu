@@ -107,25 +107,34 @@ int get_afrag(int dev, int n, int map, AFrag* out) {
   return FASTCHEB_OK;
 }
 
-template <typename R, int KO, int KB, int KC, int NT, bool E1, int MAP = 0, bool SPLIT = false>
+template <typename R, int KO, int KB, int KC, int NT, bool E1, int MAP = 0, bool SPLIT = false, bool DYN = false>
 cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
-  auto kern = fit_dmma_kernel<R, KO, KB, KC, NT, E1, MAP, SPLIT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
+  auto kern = fit_dmma_kernel<R, KO, KB, KC, NT, E1, MAP, SPLIT, DYN>;
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
-  if (bps) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, threads, smem);
+  if (bps) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
   kern<<<grid, threads, smem, st>>>(prm);
   note_launch();
   return cudaGetLastError();
 }
 
 template <typename R>
-cudaError_t dispatch(int ko, int kb, int kc, bool e1, int map, const FitDmmaParams& prm, int grid, int threads,
+cudaError_t dispatch(int ko, int kb, int kc, bool e1, int map, bool dyn, const FitDmmaParams& prm, int grid, int threads,
                      size_t smem, cudaStream_t st, int* bps) {
-  if (map != 0) {  // n = 65 with the tuned slot map of this precision
+  if (ko == 8 && kb == 5 && kc == 4) {  // n = 65: tuned slot map of this precision, dynamic unit assignment
     constexpr int M = sizeof(R) == 4 ? 1 : 2;
-    if (ko != 8 || kb != 5 || kc != 4 || map != M) return cudaErrorInvalidValue;
-    return e1 ? launch<R, 8, 5, 4, 1, true, M, true>(prm, grid, threads, smem, st, bps)
-              : launch<R, 8, 5, 4, 1, false, M, true>(prm, grid, threads, smem, st, bps);
+    if (map != 0 && map != M) return cudaErrorInvalidValue;
+#define FC_N65(MAPV, SPLITV)                                                                                        \
+  return dyn ? (e1 ? launch<R, 8, 5, 4, 1, true, MAPV, SPLITV, true>(prm, grid, threads, smem, st, bps)            \
+                   : launch<R, 8, 5, 4, 1, false, MAPV, SPLITV, true>(prm, grid, threads, smem, st, bps))          \
+             : (e1 ? launch<R, 8, 5, 4, 1, true, MAPV, SPLITV, false>(prm, grid, threads, smem, st, bps)           \
+                   : launch<R, 8, 5, 4, 1, false, MAPV, SPLITV, false>(prm, grid, threads, smem, st, bps))
+    if (map != 0) {
+      FC_N65(M, true);
+    } else {
+      FC_N65(0, false);
+    }
+#undef FC_N65
   }
 #define FC_CASE(A, B, C)                                                                   \
   if (ko == A && kb == B && kc == C)                                                       \
@@ -160,7 +169,6 @@ cudaError_t dispatch(int ko, int kb, int kc, bool e1, int map, const FitDmmaPara
   FC_CASE(6, 4, 3);
   FC_CASE(7, 4, 4);
   FC_CASE(8, 4, 4);
-  FC_CASE(8, 5, 4);
 #undef FC_CASE
   return cudaErrorInvalidValue;
 }
@@ -186,6 +194,7 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   // measured best on B200 (profiles/r01_fit_sweep.txt): Float64 is HBM-bound with 16 warps; Float32 units are half
   // the bytes, so 24 warps fit and the (then DMMA-bound) kernel wants them.  NT = 2 is not instantiated.
   int warps = dtype == FASTCHEB_F64 ? 16 : 24, S = 3, NT = 1, lag = 1;
+  const long long dyn_threshold = 32;  // units per warp below which the static round-robin split loses to imbalance
   if (const char* t = getenv("FASTCHEB_FIT_TUNE")) {
     int a = 0, b = 0, c = 0, d = 1;
     const int got = sscanf(t, "%d,%d,%d,%d", &a, &b, &c, &d);
@@ -224,11 +233,16 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   prm.slotBytes = (prm.unitBytes + 127) / 128 * 128;
   const size_t afragBytes = (af.doubles * 8 + 127) / 128 * 128;
   const size_t budget = di->smem_optin - 1024;
-  while (1024 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > lag + 1) --S;
-  while (1024 + afragBytes + (size_t)warps * S * prm.slotBytes > budget && warps > 1) --warps;
+  while (kFitHeaderBytes + afragBytes + (size_t)warps * S * prm.slotBytes > budget && S > lag + 1) --S;
+  while (kFitHeaderBytes + afragBytes + (size_t)warps * S * prm.slotBytes > budget && warps > 1) --warps;
   prm.nslots = S;
   prm.lag = lag;
-  const size_t smem = 1024 + afragBytes + (size_t)warps * S * prm.slotBytes;
+  const size_t smem = kFitHeaderBytes + afragBytes + (size_t)warps * S * prm.slotBytes;
+  // few units per warp: draw them dynamically inside each CTA (n = 65 instantiations; FASTCHEB_FIT_DYN=0/1 overrides).
+  // Measured: Float32 +7 % at 10^5 fits, +18 % at 3*10^4; Float64 unchanged at 10^5 and 10 % slower at 2^20, so it
+  // keeps the static round-robin split.
+  bool dyn = n == 65 && dtype == FASTCHEB_F32 && nunits < (long long)di->sms * warps * dyn_threshold;
+  if (const char* t = getenv("FASTCHEB_FIT_DYN")) dyn = n == 65 && atoi(t) != 0;
   if (smem > budget) return FASTCHEB_OK;
   double* linemax = nullptr;
   if (fit_max_dev) {
@@ -240,8 +254,8 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   int bps = 0;
   cudaError_t e;
   auto go = [&](int* bp, int grid) {
-    if (dtype == FASTCHEB_F64) return dispatch<double>(af.ko, af.kb, af.kc, E == 1, map, prm, grid, threads, smem, st, bp);
-    return dispatch<float>(af.ko, af.kb, af.kc, E == 1, map, prm, grid, threads, smem, st, bp);
+    if (dtype == FASTCHEB_F64) return dispatch<double>(af.ko, af.kb, af.kc, E == 1, map, dyn, prm, grid, threads, smem, st, bp);
+    return dispatch<float>(af.ko, af.kb, af.kc, E == 1, map, dyn, prm, grid, threads, smem, st, bp);
   };
   e = go(&bps, 0);
   if (e != cudaSuccess || bps < 1) {

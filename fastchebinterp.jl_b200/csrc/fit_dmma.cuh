@@ -33,6 +33,8 @@
 
 namespace fastcheb {
 
+constexpr int kFitHeaderBytes = 2048;  // mbarriers [<= 128] | unit counter | per-slot unit numbers [<= 128 x 4 B]
+
 struct FitDmmaParams {
   const void* src;
   void* dst;
@@ -88,9 +90,10 @@ __host__ __device__ constexpr int fit_map_j(int map, int ks, int c) {
 __host__ __device__ constexpr int fit_map_i(int map, int ks, int c) {
   return map == 0 ? 4 * ks + c : (map == 1 ? ks + 4 * c : 2 * c + (ks & 1) + 8 * (ks >> 1));
 }
-template <typename R, int KO, int KB, int KC, int NT, bool E1, int MAP = 0, bool SPLIT = false>
+template <typename R, int KO, int KB, int KC, int NT, bool E1, int MAP = 0, bool SPLIT = false, bool DYN = false>
 __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __grid_constant__ FitDmmaParams prm) {
   static_assert(MAP == 0 || (KO == 8 && KB == 5 && KC == 4 && NT == 1 && SPLIT), "tuned slot maps are built for n = 65");
+  static_assert(!DYN || (KO == 8 && KB == 5 && KC == 4 && NT == 1), "dynamic unit assignment is instantiated for n = 65");
   constexpr bool L2 = KC > 0;
   constexpr bool PQ = L2 && SPLIT;  // the odd half as parts P, Q instead of part O
   constexpr int MO = (KO + 1) / 2, MB = (KB + 1) / 2, MC = (KC + 1) / 2;  // 8-row m-tiles: ceil(4 K / 8)
@@ -101,32 +104,52 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
   const int nwarps = blockDim.x >> 5;
   const int S = prm.nslots;
   uint64_t* bars = reinterpret_cast<uint64_t*>(fastcheb_smem);  // [nwarps][S], <= 128 entries
+  // DYN: the CTA owns a contiguous range of units and its warps draw them from a shared-memory counter (small batches:
+  // with 5-6 units per warp the static round-robin split leaves most warps idle during the last round)
+  unsigned int* counter = reinterpret_cast<unsigned int*>(fastcheb_smem + 1024);
+  unsigned int* uq = reinterpret_cast<unsigned int*>(fastcheb_smem + 1088) + warp * S;  // units in this warp's slots
   constexpr int afragDoubles = ((PQ ? 2 * MC * KC : MO * KO) + MB * KB + MC * KC) * 32;
-  double* afrag = reinterpret_cast<double*>(fastcheb_smem + 1024);
-  unsigned char* ring = fastcheb_smem + 1024 + ((afragDoubles * 8 + 127) / 128) * 128 + (size_t)warp * S * prm.slotBytes;
+  double* afrag = reinterpret_cast<double*>(fastcheb_smem + kFitHeaderBytes);
+  unsigned char* ring =
+      fastcheb_smem + kFitHeaderBytes + ((afragDoubles * 8 + 127) / 128) * 128 + (size_t)warp * S * prm.slotBytes;
 
   for (int i = threadIdx.x; i < afragDoubles; i += blockDim.x) afrag[i] = prm.afrag[i];
   if (lane == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&bars[warp * S + s], 1);
     fence_mbar_init();
   }
+  if (DYN && threadIdx.x == 0) *counter = 0;
   __syncthreads();  // the only CTA-wide barrier
 
   const long long gw = (long long)blockIdx.x * nwarps + warp;
   const long long tw = (long long)gridDim.x * nwarps;
-  if (gw >= prm.nunits) return;
-  const long long my_units = (prm.nunits - gw + tw - 1) / tw;
+  if (!DYN && gw >= prm.nunits) return;
+  const long long my_units = DYN ? 0 : (prm.nunits - gw + tw - 1) / tw;
+  const long long ubeg = prm.nunits * blockIdx.x / gridDim.x, uend = prm.nunits * (blockIdx.x + 1) / gridDim.x;
   const char* src = reinterpret_cast<const char*>(prm.src);
   char* dst = reinterpret_cast<char*>(prm.dst);
-  auto issue = [&](long long i) {  // lane 0 only
+  // lane 0 only: put the load of this warp's i-th unit in flight; false when there is no i-th unit
+  auto issue = [&](long long i) -> bool {
     const int s = (int)(i % S);
-    const long long u = gw + i * tw;
+    long long u;
+    if constexpr (DYN) {
+      const unsigned d = atomicAdd(counter, 1u);
+      u = ubeg + d;
+      if (u >= uend) return false;
+      uq[s] = d;
+    } else {
+      if (i >= my_units) return false;
+      u = gw + i * tw;
+    }
     mbar_arrive_expect_tx(&bars[warp * S + s], (uint32_t)prm.unitBytes);
     bulk_g2s(ring + (size_t)s * prm.slotBytes, src + u * (long long)prm.unitBytes, (uint32_t)prm.unitBytes,
              &bars[warp * S + s]);
+    return true;
   };
+  long long issued = 0;  // units of this warp whose load has been issued (warp-uniform)
   if (lane == 0)
-    for (long long i = 0; i < S - prm.lag && i < my_units; ++i) issue(i);
+    while (issued < S - prm.lag && issue(issued)) ++issued;
+  if constexpr (DYN) issued = __shfl_sync(0xffffffffu, issued, 0);
 
   const int n = prm.n, N = n - 1, H = N / 2, E = E1 ? 1 : prm.E;
   const int c = lane & 3, q = lane >> 2;
@@ -164,10 +187,11 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
   const bool lastC = L2 && 4 * (8 * (MC - 1) + q) + 2 <= N;
   const bool lastP = PQ && 4 * (8 * (MC - 1) + q) < N;  // row l = 8 mt + q of P, Q exists: l < N/4
 
-  for (long long i = 0; i < my_units; ++i) {
+  for (long long i = 0; DYN ? i < issued : i < my_units; ++i) {
     const int s = (int)(i % S);
     const uint32_t parity = (uint32_t)((i / S) & 1);
-    const long long u = gw + i * tw;
+    if constexpr (DYN) __syncwarp();  // lane 0's uq[s] is visible
+    const long long u = DYN ? ubeg + uq[s] : gw + i * tw;
     R* x = reinterpret_cast<R*>(ring + (size_t)s * prm.slotBytes);
     mbar_wait(&bars[warp * S + s], parity);
 
@@ -352,14 +376,15 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
       // S - lag ahead.  lag = 2 costs a slot of look-ahead but the wait then almost never blocks: with lag = 1 a warp
       // that computes faster than its previous store drains stalls here instead of keeping loads in flight.
       const long long nxt = i + S - prm.lag;
-      if (nxt < my_units) {
+      if (DYN ? nxt == issued : nxt < my_units) {  // DYN: the queue has never run dry
         if (prm.lag == 1)
           bulk_wait_read<1>();
         else
           bulk_wait_read<2>();
-        issue(nxt);
+        if (issue(nxt)) ++issued;
       }
     }
+    if constexpr (DYN) issued = __shfl_sync(0xffffffffu, issued, 0);
   }
   if (lane == 0) bulk_wait_all();
 }

@@ -192,4 +192,88 @@ void flag_release(const FlagSlot& s) {
   g_flags[s.dev_id].used &= ~(uint64_t(1) << s.slot);
 }
 
+
+namespace {
+struct LaunchKey {
+  int dev;
+  const void* fn;
+  int threads;
+  size_t smem;
+  bool operator<(const LaunchKey& o) const {
+    if (dev != o.dev) return dev < o.dev;
+    if (fn != o.fn) return fn < o.fn;
+    if (threads != o.threads) return threads < o.threads;
+    return smem < o.smem;
+  }
+};
+std::mutex g_launch_mu;
+std::map<LaunchKey, int> g_launch_cache;  // threads == -1: attribute set; otherwise blocks per SM
+}  // namespace
+
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  {
+    static std::mutex mu;
+    static unsigned long long configured = 0;  // bit per device
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && !(configured >> dev & 1ull)) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+      configured |= 1ull << dev;
+    }
+  }
+  return cudaMallocAsync(p, bytes ? bytes : 16, st);
+}
+
+void pool_free_all(void* const* ptrs, int n) {
+  bool any = false;
+  for (int i = 0; i < n; ++i) any = any || ptrs[i] != nullptr;
+  if (!any) return;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < n; ++i)
+    if (ptrs[i]) cudaFreeAsync(ptrs[i], cudaStreamPerThread);
+}
+
+cudaError_t ensure_max_smem(const void* kernel) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const LaunchKey key{dev, kernel, -1, 0};
+  {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    if (g_launch_cache.count(key)) return cudaSuccess;
+  }
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemOptinMax);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_launch_mu);
+  g_launch_cache[key] = 1;
+  return cudaSuccess;
+}
+
+cudaError_t cached_occupancy(int* blocks_per_sm, const void* kernel, int threads, size_t smem) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const LaunchKey key{dev, kernel, threads, smem};
+  {
+    std::lock_guard<std::mutex> lk(g_launch_mu);
+    auto it = g_launch_cache.find(key);
+    if (it != g_launch_cache.end()) {
+      *blocks_per_sm = it->second;
+      return cudaSuccess;
+    }
+  }
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, threads, smem);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_launch_mu);
+  g_launch_cache[key] = *blocks_per_sm;
+  return cudaSuccess;
+}
+
 }  // namespace fastcheb

@@ -58,6 +58,13 @@ class DeviceGuard {
 void* ws_acquire(int dev, size_t bytes);
 void ws_release(int dev, void* p);
 
+// Handle-lifetime device memory from the device's stream-ordered pool (cudaMallocAsync, release threshold 1 GiB):
+// creating and destroying handles in a loop (roots, the adaptive chebinterp, chebinterp(vals) per call) then costs
+// microseconds instead of the ~1 ms of a cudaMalloc / cudaFree pair.  pool_free_all synchronises the device first, like
+// cudaFree does, because work on any stream may still read the buffers.
+cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st);
+void pool_free_all(void* const* ptrs, int n);
+
 // one int64 device flag (+ pinned host mirror) per in-flight synchronous call
 struct FlagSlot {
   long long* dev = nullptr;
@@ -79,6 +86,12 @@ long long launch_count();
 // and process-wide: setting it to the launch's own size would race between host threads that launch the same
 // instantiation with different sizes, so every launch site sets this one value.
 constexpr int kSmemOptinMax = 232448;
+
+// Host-side launch set-up, paid once instead of on every call (each is several microseconds of driver time, which
+// is what bounds small batches): the opt-in attribute once per (device, kernel), the occupancy once per
+// (device, kernel, threads, dynamic shared memory).  Thread-safe.
+cudaError_t ensure_max_smem(const void* kernel);
+cudaError_t cached_occupancy(int* blocks_per_sm, const void* kernel, int threads, size_t smem);
 
 inline size_t real_size(int dtype) { return dtype == FASTCHEB_F64 ? 8 : 4; }
 

@@ -77,7 +77,7 @@ int plan_clenshaw(fastcheb_poly* p, cudaStream_t st) {
       str *= (d == 0 ? n1p : p->dims[d]);
     }
     g.pp_bytes = slabBytes * (size_t)T;
-    FC_CUDA(cudaMalloc(&g.d_pp, g.pp_bytes));
+    FC_CUDA(pool_alloc(&g.d_pp, g.pp_bytes, st));
     const long long total = (long long)(g.pp_bytes / rs);
     const int grid = grid_for(total, 256, p->di->sms);
     if (p->dtype == FASTCHEB_F64)
@@ -203,7 +203,7 @@ int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int d
   p->coef_bytes = (size_t)p->nelems * p->E * real_size(dtype);
   int rc = FASTCHEB_OK;
   do {
-    if (cudaMalloc(&p->d_coefs, p->coef_bytes) != cudaSuccess) {
+    if (pool_alloc(&p->d_coefs, p->coef_bytes, st) != cudaSuccess) {
       cudaGetLastError();
       rc = fail(FASTCHEB_ENOMEM, "cudaMalloc of %zu coefficient bytes failed", p->coef_bytes);
       break;
@@ -290,10 +290,9 @@ int fastcheb_destroy(fastcheb_poly* p) {
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != p->device) cudaSetDevice(p->device);
-  if (p->d_coefs) cudaFree(p->d_coefs);
-  for (auto& g : p->groups)
-    if (g.d_pp) cudaFree(g.d_pp);
-  if (p->dmma.d_frag) cudaFree(p->dmma.d_frag);
+  std::vector<void*> bufs{p->d_coefs, p->dmma.d_frag};
+  for (auto& g : p->groups) bufs.push_back(g.d_pp);
+  pool_free_all(bufs.data(), (int)bufs.size());
   if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
   cudaGetLastError();
   delete p;
