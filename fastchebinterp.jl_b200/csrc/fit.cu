@@ -101,7 +101,11 @@ int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int
       }
       const double2* ctab = nullptr;
       if ((rc = cos_table(dev, n, &ctab)) != FASTCHEB_OK) break;
-      dct1_direct_kernel<R><<<grid_for(total, 256, di->sms), 256, 0, st>>>(src, dst, ctab, total, n, inner);
+      // long lines in a small array: one warp per output element (see fit_direct.cuh)
+      if (n >= 256 && total < (long long)di->sms * 2048)
+        dct1_direct_warp_kernel<R><<<grid_for(total * 32, 256, di->sms), 256, 0, st>>>(src, dst, ctab, total, n, inner);
+      else
+        dct1_direct_kernel<R><<<grid_for(total, 256, di->sms), 256, 0, st>>>(src, dst, ctab, total, n, inner);
       if (cudaGetLastError() != cudaSuccess) {
         rc = fail(FASTCHEB_ECUDA, "DCT-I kernel launch failed");
         break;

@@ -1,3 +1,2 @@
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python tools/probe_interp.py 2>&1 | head -6
+timeout 1500 python -m pytest tests/test_gpu_fit.py tests/test_gpu_roots.py tests/test_gpu_golden.py tests/test_gpu_regression.py -x -q -m gpu 2>&1 | tail -3
 python tools/latency_probe.py 2>&1 | tail -9
