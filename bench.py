@@ -247,6 +247,8 @@ def run_fit(args):
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL logs (e.g. the version banner under NCCL_DEBUG=VERSION) go to stderr: stdout carries the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     L = _capi.lib()
     M = int(args.howmany)
@@ -405,6 +407,8 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL logs (e.g. the version banner under NCCL_DEBUG=VERSION) go to stderr: stdout carries the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     L = _capi.lib()
