@@ -113,9 +113,20 @@ cudaError_t launch(const FitDmmaParams& prm, int grid, int threads, size_t smem,
   cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   if (bps) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
-  kern<<<grid, threads, smem, st>>>(prm);
+  // programmatic dependent launch: see the head of fit_dmma_kernel
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, prm);
   note_launch();
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <typename R>

@@ -113,6 +113,10 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
   unsigned char* ring =
       fastcheb_smem + kFitHeaderBytes + ((afragDoubles * 8 + 127) / 128) * 128 + (size_t)warp * S * prm.slotBytes;
 
+  // Back-to-back fits (a 10^5-fit launch is ~25 us, ~9 of them fixed cost): let the next launch in the stream start its
+  // CTAs and this set-up on SMs that are already done with the current one.  The matrices are constants written at
+  // plan time; everything a predecessor may touch (src, dst, linemax, bad) comes after grid_dep_wait().
+  grid_dep_launch_dependents();
   for (int i = threadIdx.x; i < afragDoubles; i += blockDim.x) afrag[i] = prm.afrag[i];
   if (lane == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&bars[warp * S + s], 1);
@@ -120,6 +124,7 @@ __global__ void __launch_bounds__(NT == 1 ? 768 : 256) fit_dmma_kernel(const __g
   }
   if (DYN && threadIdx.x == 0) *counter = 0;
   __syncthreads();  // the only CTA-wide barrier
+  grid_dep_wait();
 
   const long long gw = (long long)blockIdx.x * nwarps + warp;
   const long long tw = (long long)gridDim.x * nwarps;

@@ -49,6 +49,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// (CTA launch, constant set-up) while its predecessor in the stream drains; it must not touch memory the predecessor
+// may access before grid_dep_wait() returns (all prerequisite grids complete, their writes visible).
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // exact IEEE helpers (no contraction regardless of compiler flags), one spelling for both precisions
 __device__ __forceinline__ double rsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ float rsub(float a, float b) { return __fsub_rn(a, b); }
