@@ -50,6 +50,7 @@ def main():
     for name, dims, K, cplx, dt, npts in CONFIGS:
         if only and only not in name:
             continue
+        npts = int(os.environ.get("BENCH_NPTS", npts))   # e.g. the literal 10^6 points of configs[0]
         rng = np.random.default_rng(1)
         shape = dims + ((K,) if K else ())
         c = rng.uniform(-1, 1, shape)
