@@ -323,6 +323,10 @@ struct ClenshawCta {
     R* __restrict__ out_v = reinterpret_cast<R*>(prm.out_v);
     R* __restrict__ out_J = reinterpret_cast<R*>(prm.out_J);
 
+    SpanDiv<R> sdiv[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) sdiv[d].init((R)prm.lb[d], (R)prm.ub[d]);
+
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       long long idx[P];
       bool live[P];
@@ -337,7 +341,7 @@ struct ClenshawCta {
           const R lb = (R)prm.lb[d], ub = (R)prm.ub[d];
           const R x = live[p] ? pts[idx[p] * N + d] : lb;
           ok = ok && (lb <= x) && (x <= ub);                           // eval.jl:64 (closed box, NaN fails)
-          R zz = rsub(rdiv(rmul(rsub(x, lb), R(2)), rsub(ub, lb)), R(1));  // eval.jl:65, this operation order
+          R zz = rsub(sdiv[d].div(rmul(rsub(x, lb), R(2))), R(1));  // eval.jl:65, this operation order (SpanDiv: the IEEE quotient)
           if (!(lb <= x && x <= ub)) zz = R(0);
           z[d][p] = zz;
           z2[d][p] = rmul(R(2), zz);

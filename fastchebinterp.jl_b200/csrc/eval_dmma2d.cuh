@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
   double* const tbase = tdim ? t2 + (size_t)(tkind * ROWS + trow) * KA : sA + (tkind * ROWS + trow) * 16;
   double* const ttail = tails + (size_t)(tkind * ROWS + trow) * 2;
   const R tlb = (R)prm.lb[tdim], tub = (R)prm.ub[tdim];
+  SpanDiv<R> tdiv;
+  tdiv.init(tlb, tub);
 
   // Units of ROWS consecutive points; a CTA owns a contiguous range and its warps draw units from a shared-memory
   // counter (warps differ in speed — their share of the FP64 pipe — and with a static split the slow ones finished
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kDmma2dThreads) dmma2d_kernel(const __grid_con
     const R x = xn;
     xn = load_x(unit_next);  // prefetch: consumed a whole unit later
     const bool in = (tlb <= x) && (x <= tub);  // eval.jl:64
-    const double z = in ? (double)rsub(rdiv(rmul(rsub(x, tlb), R(2)), rsub(tub, tlb)), R(1)) : 0.0;  // eval.jl:65
+    const double z = in ? (double)rsub(tdiv.div(rmul(rsub(x, tlb), R(2))), R(1)) : 0.0;  // eval.jl:65 (SpanDiv: the IEEE quotient)
     const unsigned inmask = __ballot_sync(0xffffffffu, in);
     const unsigned okrows = (inmask & (inmask >> ROWS)) & ((1u << ROWS) - 1u);  // both coordinates inside the box
     const long long left = prm.npts - base;

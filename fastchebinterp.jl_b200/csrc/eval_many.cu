@@ -44,7 +44,9 @@ __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ 
     for (int i = lane; i < nE; i += 32) cs[i] = coefs[f * nE + i];
     __syncwarp();
     const R lb = (R)prm.lb[prm.bounds_per_poly ? f : 0], ub = (R)prm.ub[prm.bounds_per_poly ? f : 0];
-    const R span = rsub(ub, lb);
+    SpanDiv<R> sdiv;
+    sdiv.init(lb, ub);
+    const R span = sdiv.span;
     for (long long p0 = lane; p0 < prm.M; p0 += 32 * P) {
       R z[P], z2[P];
       bool live[P];
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ 
         live[p] = ip < prm.M;
         const R x = live[p] ? pts[f * prm.M + ip] : lb;
         const bool ok = (lb <= x) && (x <= ub);                       // eval.jl:64 (closed box, NaN fails)
-        z[p] = ok ? rsub(rdiv(rmul(rsub(x, lb), R(2)), span), R(1)) : R(0);  // eval.jl:65
+        z[p] = ok ? rsub(sdiv.div(rmul(rsub(x, lb), R(2))), R(1)) : R(0);  // eval.jl:65 (SpanDiv: the IEEE quotient)
         z2[p] = rmul(R(2), z[p]);
         if (live[p] && !ok) {
           live[p] = false;

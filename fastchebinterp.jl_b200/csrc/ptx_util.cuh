@@ -65,6 +65,41 @@ __device__ __forceinline__ float rdiv(float a, float b) { return __fdiv_rn(a, b)
 __device__ __forceinline__ double rfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 __device__ __forceinline__ float rfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 
+// Division by the loop-invariant span ub - lb of the affine map z = ((x - lb) * 2) / (ub - lb) - 1 (eval.jl:65).
+// With y = RN(1 / span) — one IEEE division per thread — Markstein's sequence
+//     q = RN(a y),   r = a - span q  (exact in an FMA),   q' = RN(q + r y)
+// returns RN(a / span), the IEEE quotient, for EVERY a, provided y is the correctly rounded reciprocal (it is), the
+// significand of span is not all ones, and nothing leaves the normal range (span's exponent is checked; a <= 2 span
+// here, and for a < 2^-60 span both quotients round z to -1).  3 operations instead of the ~12 + MUFU of a division,
+// and still bit-identical to the oracle; bench_micro/micro_divconst.cu checks 1.6e11 (a, span) pairs against the
+// IEEE division (none differ).  Otherwise: the plain division.
+template <typename R>
+struct SpanDiv {
+  R span, y;
+  bool fast;
+  __device__ __forceinline__ void init(R lb, R ub) {
+    span = rsub(ub, lb);
+    y = rdiv(R(1), span);
+    if constexpr (sizeof(R) == 8) {
+      const unsigned long long u = (unsigned long long)__double_as_longlong((double)span);
+      const unsigned e = (unsigned)(u >> 52) & 0x7ffu;
+      fast = (u & 0xfffffffffffffull) != 0xfffffffffffffull && e > 1023u - 500u && e < 1023u + 500u;
+    } else {
+      const unsigned u = __float_as_uint((float)span);
+      const unsigned e = (u >> 23) & 0xffu;
+      fast = (u & 0x7fffffu) != 0x7fffffu && e > 127u - 60u && e < 127u + 60u;
+    }
+  }
+  __device__ __forceinline__ R div(R a) const {
+    if (fast) {
+      const R q = rmul(a, y);
+      const R r = rfma(-span, q, a);
+      return rfma(r, y, q);
+    }
+    return rdiv(a, span);
+  }
+};
+
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4)+{0,1}].
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
