@@ -1,7 +1,9 @@
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-export BENCH_SHAPES="5x8,9x9,9x9x9"
-timeout 600 python tools/bench_configs.py 2>/dev/null | python -c "
-import sys, json
-for l in sys.stdin:
-    d = json.loads(l)
-    if d['algo']=='clenshaw' and ('shape' in d['config'] or 'cfg1' in d['config'] or 'cfg5' in d['config']): print(d['config'][:52].ljust(52), d['mode'], '%.3e pts/s' % d['points_per_s'], round(d['frac_of_fp_peak'], 3))"
+mkdir -p gpurun_out
+python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+python bench.py --steps 5 --warmup 3 --mode jac --no-cpu > gpurun_out/bench_jac.json 2>/dev/null
+python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+python -c "
+import json
+for f in ['bench_default','bench_jac','bench_ref']:
+    d=json.loads([l for l in open('gpurun_out/%s.json'%f) if l.startswith('{')][0]); print(f, d['value'], d.get('roofline',{}).get('frac'), d.get('e2e',{}).get('value'))"
