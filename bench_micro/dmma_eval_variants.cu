@@ -35,7 +35,7 @@ int main(int argc, char** argv) {
   #ifdef FC_PROFILE
   for (int warps : {16}) for (int tps : {1, 4}) for (int ns : {3}) {
 #else
-  for (int warps : {8, 12, 16}) for (int tps : {1, 2, 4}) for (int ns : {3, 4, 6}) {
+  for (int warps : {16, 20}) for (int tps : {4}) for (int ns : {3}) {
 #endif
     DmmaParams prm; memset(&prm, 0, sizeof prm);
     prm.frag = d_f; prm.pts = d_p; prm.out_v = d_o; prm.npts = npts; prm.v_stride = EC; prm.Etot = EC;
@@ -43,7 +43,7 @@ int main(int argc, char** argv) {
     prm.tabStride = tabStride;
     for (int d = 0; d < 3; ++d) { prm.lb[d] = -1; prm.ub[d] = 1; }
     const size_t smem = 128 + (size_t)ns * tps * TR * 8 + (size_t)warps * rows * tabStride * 8;
-    if (smem > prop.sharedMemPerBlockOptin || warps * 32 > 512) continue;
+    if (smem > prop.sharedMemPerBlockOptin || warps * 32 > dmma_max_threads(EC, KS, false)) continue;
 #ifdef FC_PROFILE
     long long* d_prof; CK(cudaMalloc(&d_prof, 16 * 4 * 8)); CK(cudaMemset(d_prof, 0, 16 * 4 * 8)); prm.prof = d_prof;
 #endif

@@ -375,6 +375,13 @@ __global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(con
     }
     auto fold = [&](auto ec) {  // fold the pending chain (component `ec`) with the weights in W
       constexpr int e = decltype(ec)::value;
+#if defined(FC_EXP) && (FC_EXP & 2)  // experiment (bench_micro/dmma_eval_variants.cu): no FP64 fold, results kept live
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+        acc[mt][e] = __hiloint2double(__double2hiint(acc[mt][e]) ^ __double2hiint(pg0[mt]),
+                                      __double2loint(acc[mt][e]) ^ __double2loint(pg1[mt]));
+      return;
+#endif
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         acc[mt][e] = fma(pg0[mt], W.w[mt][0], acc[mt][e]);
@@ -422,7 +429,9 @@ __global__ void __launch_bounds__(dmma_max_threads(EC, KS, JAC)) dmma_kernel(con
         }
         // the previous chain has long finished: fold it now, then this chain becomes the pending one
         fold(std::integral_constant<int, (e == 0 ? EC - 1 : e - 1)>{});
+#if !(defined(FC_EXP) && (FC_EXP & 1))  // experiment: weights never loaded / multiplied
         if constexpr (e == 0) weights(rec, W);  // the pending chain of the previous tile is folded: W moves on to this tile
+#endif
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           pg0[mt] = g0[mt];
