@@ -135,7 +135,7 @@ def cpu_reference_rate(mode: str, sample_pts: int, reps: int = 3):
     orc.set_num_threads()  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     poly = orc.OracleChebPoly(coefficients(), LB, UB)
     rng = np.random.default_rng(PTS_SEED)
-    pts = rng.uniform(-1.0, 1.0, (sample_pts, 3))
+    pts = rng.uniform(-1.0, 1.0, (sample_pts, len(DIMS)))
     # value mode: all K components of an element per pass (the SIMD the reference gets from SVector{3}); bit-identical
     # to the component-by-component restatement (tests/test_oracle_golden.py)
     f = poly.jacobian if mode == "jac" else poly.eval_simd
@@ -165,7 +165,7 @@ def run_reference(args):
     W = work_per_point(DIMS, K, jac=args.mode == "jac")
     line = {
         "impl": "reference",
-        "metric": "Float64 evals/sec (3D order-32 ChebPoly)", "value": rate, "unit": "points/s",
+        "metric": METRIC, "value": rate, "unit": "points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(t_all)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -360,7 +360,25 @@ def run_fit(args):
         dist.destroy_process_group()
 
 
+WORKLOAD = "eval3d"
+METRIC = "Float64 evals/sec (3D order-32 ChebPoly)"
+
+
+def select_workload(name):
+    """eval3d = BASELINE configs[2] (the headline); eval2d = configs[1]: 2-D order (64,64) real Float64, value or
+    value + chebgradient — the same bench contract on the second evaluation config."""
+    global WORKLOAD, METRIC, DIMS, K, LB, UB
+    WORKLOAD = name
+    if name == "eval2d":
+        DIMS, K = (65, 65), 1
+        LB, UB = np.array([-1.0, -1.0]), np.array([1.0, 1.0])
+        METRIC = "Float64 evals/sec (2D order-64 ChebPoly)"
+
+
 def workload_name(mode):
+    if WORKLOAD == "eval2d":
+        what = "value c.(ys)" if mode == "val" else "value + chebgradient"
+        return f"configs[1]: 2-D order (64,64) real Float64 ChebPoly, {what}, uniform random points"
     what = "value c.(ys)" if mode == "val" else "value + chebjacobian"
     return f"configs[2]: 3-D order (32,32,32) SVector{{3}} Float64 ChebPoly, {what}, uniform random points"
 
@@ -379,13 +397,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how values reach rank 0")
-    ap.add_argument("--workload", default="eval3d", choices=["eval3d", "fit1d"],
-                    help="eval3d = the headline (configs[2]); fit1d = configs[4] batched DCT-I fits (HBM-bound leg)")
+    ap.add_argument("--workload", default="eval3d", choices=["eval3d", "eval2d", "fit1d"],
+                    help="eval3d = the headline (configs[2]); eval2d = configs[1] (2-D order 64); "
+                         "fit1d = configs[4] batched DCT-I fits (HBM-bound leg)")
     ap.add_argument("--howmany", type=int, default=1 << 20, help="fit1d: fits per GPU per step")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="fit1d: element type")
     args = ap.parse_args()
     if args.workload == "fit1d":
         return run_fit(args)
+    select_workload(args.workload)
+    if args.workload == "eval2d" and args.cpu_sample == 200_000:
+        args.cpu_sample = 5_000_000  # a 2-D point is 26x cheaper than a headline point: keep the CPU sample in seconds
     if args.warmup < 3:
         args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -414,7 +436,7 @@ def main():
     L = _capi.lib()
     jac = args.mode == "jac"
     B = int(args.batch)
-    N, E = 3, K
+    N, E = len(DIMS), K
 
     # ---- the polynomial: rank 0 owns the coefficients, NCCL broadcasts them (north_star: eval sharding)
     if distributed:
@@ -565,7 +587,7 @@ def main():
                    "sample": f"{args.cpu_sample} uniform random points of the same workload, best of 3, "
                              "oracle/cheb_oracle.c (OpenMP over points, SIMD over the K components like the reference's SVector arithmetic)"}
         line = {
-            "metric": "Float64 evals/sec (3D order-32 ChebPoly)", "value": value, "unit": "points/s",
+            "metric": METRIC, "value": value, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.mode), "points_per_gpu_per_step": B,
@@ -578,7 +600,7 @@ def main():
                                          if do_gather else "results stay sharded")},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak,
-                         "traffic": measured_traffic("eval3d_jac" if jac else "eval3d_val", "launch_points", B),
+                         "traffic": measured_traffic(WORKLOAD + ("_jac" if jac else "_val"), "launch_points", B),
                          "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_traffic.json); algorithmic: "
                                          f"{B * 8 * (N + E * (1 + (N if jac else 0)))} B of points in + results out",
                          "flops_per_point": W, "kernel_ms": kern_ms, "peak_source": peak_src,
