@@ -98,3 +98,35 @@ def test_random_fits(fc, orc, seed):
             want = orc.chebcoefs(vals.astype(np.complex128 if cplx else np.float64), N)
         assert got.shape == want.shape and got.dtype == vals.dtype
         assert np.abs(got - want).max() <= tol * max(np.abs(want).max(), 1e-300), (shape, cplx, np.dtype(dt).name)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_domain_errors(fc, seed):
+    """The FIRST offending point (eval.jl:64: outside the closed box, or NaN) is what every kernel family reports,
+    wherever it sits in the batch (first / last unit, several bad points, large batches that use all warps)."""
+    rng = np.random.default_rng(3000 + seed)
+    for _ in range(6):
+        dims, K, cplx, dt = random_case(rng)
+        N = len(dims)
+        shape = dims + ((K,) if K else ())
+        c = rng.uniform(-1, 1, shape).astype(dt)
+        lb = rng.uniform(-3, 1, N).astype(dt)
+        ub = (lb + rng.uniform(0.25, 4, N)).astype(dt)
+        npts = int(rng.integers(1, 200_000 if rng.integers(0, 3) == 0 else 3000))
+        pts = (lb + (ub - lb) * rng.random((npts, N))).astype(dt)
+        pts = np.clip(pts, lb, ub)
+        bad_idx = sorted(set(int(v) for v in rng.integers(0, npts, int(rng.integers(1, 4)))))
+        for i in bad_idx:
+            d = int(rng.integers(0, N))
+            pts[i, d] = [np.nan, ub[d] + (ub[d] - lb[d]) * dt(0.01) + dt(1e-3), lb[d] - dt(1e-3)][int(rng.integers(0, 3))]
+        poly = fc.ChebPoly(c, lb, ub)
+        algos = [fc.ALGO_CLENSHAW, fc.ALGO_AUTO]
+        if N >= 2 and N <= 4 and dims[0] >= 5 and np.prod(dims[1:]) >= 8:
+            algos += [fc.ALGO_DMMA, fc.ALGO_DMMA_RING]
+        for algo in algos:
+            poly.set_algo(algo, dt)
+            for jac in (False, True):
+                with pytest.raises(fc.ArgumentError):
+                    fc.chebjacobian(poly, pts) if jac else poly(pts)
+                assert fc._capi.error_index() == bad_idx[0], (dims, K, np.dtype(dt).name, npts, algo, jac, bad_idx)
+        poly.close()
