@@ -247,8 +247,11 @@ def run_fit(args):
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL logs (e.g. the version banner under NCCL_DEBUG=VERSION) go to stderr: stdout carries the ONE JSON line
+        # stdout carries the ONE JSON line: NCCL's log file is stderr, and the bare version banner that
+        # NCCL_DEBUG=VERSION printf()s to stdout is switched off (an explicit INFO / TRACE setting is kept)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     L = _capi.lib()
     M = int(args.howmany)
@@ -429,8 +432,11 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL logs (e.g. the version banner under NCCL_DEBUG=VERSION) go to stderr: stdout carries the ONE JSON line
+        # stdout carries the ONE JSON line: NCCL's log file is stderr, and the bare version banner that
+        # NCCL_DEBUG=VERSION printf()s to stdout is switched off (an explicit INFO / TRACE setting is kept)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     L = _capi.lib()
