@@ -123,6 +123,27 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout carries the ONE JSON line.  Native libraries (NCCL's NCCL_DEBUG=VERSION banner is a bare printf) also
+    write to fd 1, so fd 1 is pointed at stderr for the lifetime of the process and the JSON line goes to a private
+    duplicate of the original stdout.  The driver's NCCL_DEBUG / NCCL_DEBUG_FILE settings are left untouched."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _REAL_STDOUT
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def cpu_reference_rate(mode: str, sample_pts: int, reps: int = 3):
     """The reference's algorithm on the host cores: the oracle's OpenMP C restatement of eval.jl
     (Threads.@threads-over-c(y) analogue).  Returns (points/s, threads)."""
@@ -176,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gflops_algorithmic": rate * W / 1e9,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def measured_traffic(key, units_key, units):
@@ -230,7 +251,7 @@ def run_fit(args):
         for _ in range(max(1, args.steps)):
             rr, th = cpu_fit_rate(n, hm, dt)
             r = max(r, rr)
-        print(json.dumps({"impl": "reference", "metric": "1-D order-64 DCT-I fits/sec", "value": r, "unit": "fits/s",
+        emit(({"impl": "reference", "metric": "1-D order-64 DCT-I fits/sec", "value": r, "unit": "fits/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                           "config": {"workload": f"configs[4]: {hm} independent 1-D order-64 fits per step"},
@@ -247,11 +268,7 @@ def run_fit(args):
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries the ONE JSON line: NCCL's log file is stderr, and the bare version banner that
-        # NCCL_DEBUG=VERSION printf()s to stdout is switched off (an explicit INFO / TRACE setting is kept)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        protect_stdout()   # NCCL's banner / log lines must not land in the JSON stream; its env is not touched
         dist.init_process_group("nccl", device_id=dev)
     L = _capi.lib()
     M = int(args.howmany)
@@ -348,7 +365,7 @@ def run_fit(args):
             cpu = {"value": r, "unit": "fits/s", "cores": th, "kind": "port",
                    "sample": f"{min(M, 200_000)} fits, best of 3, scipy/pocketfft dct(type=1, workers={th}) + normalisation "
                              "passes (stand-in for the reference's FFTW.r2r REDFT00; libfftw3 is not in this image)"}
-        print(json.dumps({
+        emit(({
             "metric": "1-D order-64 DCT-I fits/sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
@@ -399,6 +416,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="only the headline measurement (no `legs` object)")
+    ap.add_argument("--quick-legs", action="store_true", help="legs with 2 timed repetitions instead of 5")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N>1: how values reach rank 0")
     ap.add_argument("--workload", default="eval3d", choices=["eval3d", "eval2d", "fit1d"],
                     help="eval3d = the headline (configs[2]); eval2d = configs[1] (2-D order 64); "
@@ -432,11 +452,7 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries the ONE JSON line: NCCL's log file is stderr, and the bare version banner that
-        # NCCL_DEBUG=VERSION printf()s to stdout is switched off (an explicit INFO / TRACE setting is kept)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        protect_stdout()   # NCCL's banner / log lines must not land in the JSON stream; its env is not touched
         dist.init_process_group("nccl", device_id=dev)
 
     L = _capi.lib()
@@ -461,83 +477,124 @@ def main():
     g.manual_seed(PTS_SEED + 1000 * rank)
     pts = torch.rand((B, N), dtype=torch.float64, device=dev, generator=g) * 2.0 - 1.0
     out_v = torch.empty((B, E), dtype=torch.float64, device=dev)
-    out_J = torch.empty((B, N, E), dtype=torch.float64, device=dev) if jac else None
+    out_J = torch.empty((B, N, E), dtype=torch.float64, device=dev)
     status = torch.zeros(1, dtype=torch.int64, device=dev)
-    # N > 1: the values of all ranks land in ONE buffer on rank 0.  Default: fused eval + gather — every rank's kernel
-    # stores straight into rank 0's HBM through a CUDA-IPC mapping (NVLink peer stores, fastcheb.sharded.PeerGather);
-    # --gather nccl uses a torch.distributed gather after the kernel instead.
-    gathered, peer = None, None
-    do_gather = distributed and not args.no_gather and not jac
-    if do_gather and args.gather == "nccl":
-        gathered = [torch.empty_like(out_v) for _ in range(world)] if rank == 0 else None
-    elif do_gather:
-        from fastcheb import sharded
-        peer = sharded.PeerGather(total_rows=B * world, row_reals=E, itemsize=8, dst=0, device=local)
-        out_ptr = peer.slice_ptr(rank * B)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
-
-    def step():
-        if jac:
-            rc = L.fastcheb_eval_jac_async(h, pts.data_ptr(), B, out_v.data_ptr(), out_J.data_ptr(), status.data_ptr(), sp)
-        elif peer is not None:
-            rc = L.fastcheb_eval_async(h, pts.data_ptr(), B, out_ptr, status.data_ptr(), sp)  # stores go to rank 0's HBM
-        else:
-            rc = L.fastcheb_eval_async(h, pts.data_ptr(), B, out_v.data_ptr(), status.data_ptr(), sp)
-        if rc != 0:
-            raise RuntimeError(_capi.last_error())
-        if gathered is not None or (do_gather and args.gather == "nccl" and rank != 0):
-            dist.gather(out_v, gathered, dst=0)  # results gathered on rank 0 over NVLink (NCCL)
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    if int(status.item()) != 0x7FFFFFFFFFFFFFFF:
-        raise RuntimeError("out-of-domain point in the synthetic batch")
+    def measure(jac_mode: bool, steps: int, warmup: int, sample_clocks: bool):
+        """K steps of the hot path with device-resident inputs, CUDA events on the launching stream, max over ranks.
+        N > 1: the results of all ranks land in ONE buffer on rank 0 inside the timed region.  Default: fused eval +
+        gather — every rank's kernel stores straight into rank 0's HBM through a CUDA-IPC mapping (NVLink peer stores,
+        fastcheb.sharded.PeerGather; values and, in Jacobian mode, the 96 B/point Jacobians); --gather nccl uses a
+        torch.distributed gather after the kernel instead."""
+        do_gather = distributed and not args.no_gather
+        gathered_v = gathered_J = peer_v = peer_J = None
+        ov_ptr, oJ_ptr = out_v.data_ptr(), out_J.data_ptr()
+        if do_gather and args.gather == "nccl":
+            gathered_v = [torch.empty_like(out_v) for _ in range(world)] if rank == 0 else None
+            gathered_J = [torch.empty_like(out_J) for _ in range(world)] if (rank == 0 and jac_mode) else None
+        elif do_gather:
+            from fastcheb import sharded
+            peer_v = sharded.PeerGather(total_rows=B * world, row_reals=E, itemsize=8, dst=0, device=local)
+            ov_ptr = peer_v.slice_ptr(rank * B)
+            if jac_mode:
+                peer_J = sharded.PeerGather(total_rows=B * world, row_reals=E * N, itemsize=8, dst=0, device=local)
+                oJ_ptr = peer_J.slice_ptr(rank * B)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    l0 = L.fastcheb_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    launches = L.fastcheb_launch_count() - l0
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = B * world * args.steps / (ms_max * 1e-3)
+        def step():
+            if jac_mode:
+                rc = L.fastcheb_eval_jac_async(h, pts.data_ptr(), B, ov_ptr, oJ_ptr, status.data_ptr(), sp)
+            else:
+                rc = L.fastcheb_eval_async(h, pts.data_ptr(), B, ov_ptr, status.data_ptr(), sp)
+            if rc != 0:
+                raise RuntimeError(_capi.last_error())
+            if do_gather and args.gather == "nccl":
+                dist.gather(out_v, gathered_v, dst=0)  # results gathered on rank 0 over NVLink (NCCL)
+                if jac_mode:
+                    dist.gather(out_J, gathered_J, dst=0)
 
-    # kernel-only time (no gather) for the roofline: one kernel per step
-    if do_gather:
+        for _ in range(warmup):
+            step()
         barrier()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(stream)
-        for _ in range(args.steps):
-            L.fastcheb_eval_async(h, pts.data_ptr(), B, out_v.data_ptr(), status.data_ptr(), sp)
-        k1.record(stream)
+        if int(status.item()) != 0x7FFFFFFFFFFFFFFF:
+            raise RuntimeError("out-of-domain point in the synthetic batch")
+        sampler = ClockSampler(local)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+            time.sleep(0.3)
         barrier()
-        kern_ms = k0.elapsed_time(k1) / args.steps
-    else:
-        kern_ms = ms / args.steps
-    W = work_per_point(DIMS, K, jac=jac)
+        l0 = L.fastcheb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        launches = L.fastcheb_launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+        # kernel-only time (local output, no gather) for the roofline: one kernel per step
+        if do_gather:
+            barrier()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            for _ in range(steps):
+                if jac_mode:
+                    L.fastcheb_eval_jac_async(h, pts.data_ptr(), B, out_v.data_ptr(), out_J.data_ptr(), status.data_ptr(), sp)
+                else:
+                    L.fastcheb_eval_async(h, pts.data_ptr(), B, out_v.data_ptr(), status.data_ptr(), sp)
+            k1.record(stream)
+            barrier()
+            kern_ms = k0.elapsed_time(k1) / steps
+        else:
+            kern_ms = ms / steps
+        gather_check = None
+        if peer_v is not None:
+            # every rank's slice of the gathered buffers equals what that rank computes locally
+            if jac_mode:
+                L.fastcheb_eval_jac_async(h, pts.data_ptr(), B, out_v.data_ptr(), out_J.data_ptr(), status.data_ptr(), sp)
+            else:
+                L.fastcheb_eval_async(h, pts.data_ptr(), B, out_v.data_ptr(), status.data_ptr(), sp)
+            torch.cuda.synchronize(dev)
+            mine = (out_v[:4096].cpu().numpy(), out_J[:4096].cpu().numpy() if jac_mode else None)
+            lst = [None] * world
+            dist.all_gather_object(lst, mine)
+            if rank == 0:
+                gather_check = max(float(np.abs(peer_v.read(r * B, 4096).reshape(4096, E) - lst[r][0]).max()) for r in range(world))
+                if jac_mode:
+                    gather_check = max(gather_check, max(float(np.abs(peer_J.read(r * B, 4096).reshape(4096, N, E) - lst[r][1]).max())
+                                                         for r in range(world)))
+            peer_v.close()
+            if peer_J is not None:
+                peer_J.close()
+        W = work_per_point(DIMS, K, jac=jac_mode)
+        return {"value": B * world * steps / (ms_max * 1e-3), "ms_per_step": ms_max / steps, "kern_ms": kern_ms,
+                "launches": int(launches), "clocks": clocks, "gather_check": gather_check, "W": W,
+                "achieved": B * W / (kern_ms * 1e-3) / 1e12, "gathered": bool(do_gather)}
+
+    main_res = measure(jac, args.steps, args.warmup, True)
+    value, ms_max, kern_ms, launches, clocks = (main_res["value"], main_res["ms_per_step"] * args.steps, main_res["kern_ms"],
+                                                main_res["launches"], main_res["clocks"])
+    W, achieved, gather_check, do_gather = main_res["W"], main_res["achieved"], main_res["gather_check"], main_res["gathered"]
     peak, peak_src = fp64_peak_tflops()
-    achieved = B * W / (kern_ms * 1e-3) / 1e12
 
-    # ---- e2e: the public host API with pinned host buffers (H2D + kernel + D2H inside the timed region)
+    # The other mode of the same workload, all ranks, gather inside the timed region (configs[2]: "10^9 evals +
+    # chebjacobian sharded over 1/2/4/8 B200"): reported under legs.
+    other = None
+    if not args.no_legs:
+        other = measure(not jac, max(3, min(args.steps, 6)), 3, False)
+
+    # ---- e2e: the public host API with HOST buffers (H2D + kernel + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
         Be = min(B, 1 << 23)
@@ -546,45 +603,55 @@ def main():
         hv = torch.empty((Be, E), dtype=torch.float64).pin_memory()
         hJ = torch.empty((Be, N, E), dtype=torch.float64).pin_memory() if jac else None
 
-        def e2e_step():
+        def e2e_step(ip, iv, iJ):
             if jac:
-                rc = L.fastcheb_eval_jac(h, hp.data_ptr(), Be, hv.data_ptr(), hJ.data_ptr(), _capi.MEM_HOST, None)
+                rc = L.fastcheb_eval_jac(h, ip, Be, iv, iJ, _capi.MEM_HOST, None)
             else:
-                rc = L.fastcheb_eval(h, hp.data_ptr(), Be, hv.data_ptr(), _capi.MEM_HOST, None)
+                rc = L.fastcheb_eval(h, ip, Be, iv, _capi.MEM_HOST, None)
             if rc != 0:
                 raise RuntimeError(_capi.last_error())
-            return float(hv[0, 0])  # host read of the step's result
 
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        nst = max(3, min(args.steps, 10))
-        for _ in range(nst):
-            e2e_step()
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if distributed:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": Be * world * nst / float(tt.item()), "unit": "points/s",
-               "h2d_bytes_per_step": Be * N * 8, "d2h_bytes_per_step": Be * E * 8 * (1 + (N if jac else 0)),
-               "points_per_step_per_gpu": Be, "timer": "host wall clock around the synchronous C-ABI call, max over ranks"}
+        def e2e_time(ip, iv, iJ, read):
+            for _ in range(2):
+                e2e_step(ip, iv, iJ)
+            barrier()
+            t0 = time.perf_counter()
+            nst = max(3, min(args.steps, 10))
+            for _ in range(nst):
+                e2e_step(ip, iv, iJ)
+                read()  # host read of the step's result
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if distributed:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return Be * world * nst / float(tt.item())
+
+        e2e = {"value": e2e_time(hp.data_ptr(), hv.data_ptr(), hJ.data_ptr() if jac else None, lambda: float(hv[0, 0])),
+               "unit": "points/s", "h2d_bytes_per_step": Be * N * 8, "d2h_bytes_per_step": Be * E * 8 * (1 + (N if jac else 0)),
+               "points_per_step_per_gpu": Be, "buffers": "pinned host memory",
+               "timer": "host wall clock around the synchronous C-ABI call, max over ranks"}
         # spot-check e2e output against the device path
-        chk = float((hv[:1000] - out_v[:1000].cpu()).abs().max())
-        e2e["max_abs_diff_vs_device_path"] = chk
-
-    gather_check = None
-    if peer is not None:
-        # every rank's slice of the gathered buffer equals what that rank computes locally
         L.fastcheb_eval_async(h, pts.data_ptr(), B, out_v.data_ptr(), status.data_ptr(), sp)
         torch.cuda.synchronize(dev)
-        mine = out_v[:4096].cpu()
-        lst = [None] * world
-        dist.all_gather_object(lst, mine.numpy())
-        if rank == 0:
-            gather_check = max(float(np.abs(peer.read(r * B, 4096).reshape(4096, E) - lst[r]).max()) for r in range(world))
-        peer.close()
+        e2e["max_abs_diff_vs_device_path"] = float((hv[:1000] - out_v[:1000].cpu()).abs().max())
+        # the same call with PAGEABLE host buffers (plain malloc'ed numpy arrays: what a Julia Vector is)
+        pp = np.empty((Be, N), dtype=np.float64)
+        pp[...] = hp.numpy()
+        pv = np.empty((Be, E), dtype=np.float64)
+        pJ = np.empty((Be, N, E), dtype=np.float64) if jac else None
+        e2e["pageable"] = {"value": e2e_time(pp.ctypes.data, pv.ctypes.data, pJ.ctypes.data if jac else None, lambda: float(pv[0, 0])),
+                           "unit": "points/s", "buffers": "pageable host memory (numpy / malloc)"}
+        e2e["pageable"]["max_abs_diff_vs_pinned"] = float(np.abs(pv[:1000] - hv[:1000].numpy()).max())
+        del pp, pv, pJ
+        # N > 1: the same batch driven from ONE host process through fastcheb_multi_eval (rank 0 drives all N GPUs,
+        # the other ranks are idle at the barrier)
+        if distributed and not jac:
+            barrier()
+            if rank == 0:
+                e2e["single_process"] = single_process_e2e(L, _capi, carr, lb_, ub_, world, Be, N, E, hp)
+            barrier()
+
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -596,13 +663,14 @@ def main():
             "metric": METRIC, "value": value, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gpu_launches": int(launches),
             "config": {"workload": workload_name(args.mode), "points_per_gpu_per_step": B,
                        "coef_bytes": int(np.prod(DIMS)) * K * 8, "algo": algo_used,
                        "l2": f"inputs {B * N * 8 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2",
                        "parallelism": f"points sharded over {world} GPU(s), coefficients NCCL-broadcast, "
-                                      + (("values gathered on rank 0 inside the timed region: "
+                                      + (("results gathered on rank 0 inside the timed region: "
                                           + ("kernel stores straight into rank 0's HBM over NVLink (CUDA-IPC peer buffer, fused eval+gather)"
-                                             if peer is not None else "NCCL gather after the kernel"))
+                                             if args.gather == "peer" else "NCCL gather after the kernel"))
                                          if do_gather else "results stay sharded")},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak,
@@ -613,14 +681,99 @@ def main():
                          "note": "FP64 tensor-core (DMMA) pipe; algorithmic flops, not executed flops"},
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if gather_check is not None:
             line["gather_max_abs_diff_vs_local"] = gather_check
-        print(json.dumps(line))
+        if not args.no_parity:
+            line["parity"] = parity_record(fastcheb, poly, carr, lb_, ub_)
+        legs = {}
+        if other is not None:
+            nm = WORKLOAD + ("_val" if jac else "_jac")
+            legs[nm] = {"value": other["value"], "unit": "points/s", "ms_per_step": other["ms_per_step"], "n_gpus": world,
+                        "gathered_on_rank0": other["gathered"],
+                        "roofline": {"bound": "tensor", "achieved": other["achieved"], "peak": peak, "unit": "TFLOP/s",
+                                     "frac": other["achieved"] / peak, "flops_per_point": other["W"], "kernel_ms": other["kern_ms"]}}
+            if other["gather_check"] is not None:
+                legs[nm]["gather_max_abs_diff_vs_local"] = other["gather_check"]
+        line["legs"] = legs
+    del pts, out_v, out_J
+    poly.close()
+    torch.cuda.empty_cache()
+    if rank == 0 and not args.no_legs:
+        # every other leg of BASELINE.json's configs, short runs on this rank's GPU, each with its own roofline
+        import bench_legs
+        line["legs"].update(bench_legs.run_all(local, quick=args.quick_legs))
+    if rank == 0:
+        emit(line)
     if distributed:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def single_process_e2e(L, _capi, carr, lb_, ub_, world, Be, N, E, hp):
+    """`c.(ys)` on N GPUs from ONE host process: fastcheb_multi_create + fastcheb_multi_eval with pinned host buffers
+    holding world x Be points (the per-rank e2e batch replicated), H2D + kernels + D2H inside the timed region."""
+    import torch
+
+    h = ctypes.c_void_p()
+    import fastcheb
+    flat = np.ascontiguousarray(fastcheb._to_julia_flat(np.asarray(carr), N))
+    rc = L.fastcheb_multi_create(ctypes.byref(h), world, None, N, _capi.i64_array(DIMS), _capi.F64, 0, K, flat.ctypes.data,
+                                 _capi.MEM_HOST, _capi.dbl_array(lb_), _capi.dbl_array(ub_))
+    if rc != 0:
+        return {"error": _capi.last_error()}
+    tot = Be * world
+    big_p = torch.empty((tot, N), dtype=torch.float64).pin_memory()
+    for r in range(world):
+        big_p[r * Be:(r + 1) * Be].copy_(hp)
+    big_v = torch.empty((tot, E), dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        rc = L.fastcheb_multi_eval(h, big_p.data_ptr(), tot, big_v.data_ptr(), _capi.MEM_HOST)
+    t0 = time.perf_counter()
+    nst = 3
+    for _ in range(nst):
+        rc |= L.fastcheb_multi_eval(h, big_p.data_ptr(), tot, big_v.data_ptr(), _capi.MEM_HOST)
+        float(big_v[0, 0])
+    dt = time.perf_counter() - t0
+    same = bool(torch.equal(big_v[:1000], big_v[(world - 1) * Be:(world - 1) * Be + 1000]))
+    L.fastcheb_multi_destroy(h)
+    return {"value": tot * nst / dt, "unit": "points/s", "n_gpus": world, "points_per_step": tot, "rc": int(rc),
+            "replicated_blocks_agree": same, "entry": "fastcheb_multi_eval (one process, one worker thread + stream per GPU)"}
+
+
+def parity_record(fastcheb, poly, carr, lb_, ub_):
+    """Measured parity of the default path against the oracle on a seeded sample (faces and near-face points included):
+    worst |dv| / (16 eps sum|c|) and, per gradient entry, worst |dJ_d| over the differentiated-series bound
+    16 eps (sum_k |c_k| k_d^2) 2/(ub_d-lb_d) and over the literal 16 eps sum|c| 2/(ub_d-lb_d)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cheb_oracle as orc
+
+    rng = np.random.default_rng(123)
+    N = len(DIMS)
+    lb, ub = np.asarray(lb_, dtype=float), np.asarray(ub_, dtype=float)
+    n = 4096
+    p = lb + (ub - lb) * rng.random((n, N))
+    p[0], p[1] = lb, ub
+    m = n // 8
+    d = rng.integers(0, N, m)
+    p[np.arange(8, 8 + m), d] = np.where(rng.random(m) < 0.5, lb[d] + (ub - lb)[d] * 1e-4 * rng.random(m), ub[d] - (ub - lb)[d] * 1e-4 * rng.random(m))
+    v0, J0 = orc.OracleChebPoly(carr, lb, ub).jacobian(p)
+    v, J = fastcheb.chebjacobian(poly, p)
+    eps = np.finfo(np.float64).eps
+    sumc = float(np.abs(carr).sum())
+    wj, sj = [], []
+    for dd in range(N):
+        k2 = (np.arange(DIMS[dd], dtype=float) ** 2).reshape([-1 if i == dd else 1 for i in range(np.ndim(carr))])
+        dj = float(np.abs(np.asarray(J)[..., dd] - np.asarray(J0)[..., dd]).max())
+        sc = 2.0 / (ub[dd] - lb[dd])
+        wj.append(dj / (16 * eps * float((np.abs(carr) * k2).sum()) * sc))
+        sj.append(dj / (16 * eps * sumc * sc))
+    return {"points": n, "value_over_tol": float(np.abs(np.asarray(v) - np.asarray(v0)).max() / (16 * eps * sumc)),
+            "jac_over_weighted_tol": max(wj), "jac_over_literal_tol": max(sj),
+            "tolerances": "value: 16 eps sum|c|; gradient entries: 16 eps sum_k|c_k| k_d^2 * 2/(ub_d-lb_d) (weighted) and "
+                          "16 eps sum|c| * 2/(ub_d-lb_d) (literal; the oracle itself is 0.2-176x this bound from the long-double "
+                          "Jacobian, profiles/r02_jac_parity.jsonl)"}
 
 
 if __name__ == "__main__":

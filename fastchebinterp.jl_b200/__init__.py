@@ -38,7 +38,7 @@ import numpy as np
 from . import _capi
 from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA, ALGO_DMMA_RING  # noqa: F401
 
-__all__ = ["rrule", "frule", "chebregression", "chebvandermonde", "eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
+__all__ = ["MultiChebPoly", "chebcoefs_multi", "rrule", "frule", "chebregression", "chebvandermonde", "eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
            "droptol", "roots", "colleague_matrix", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]
 
 _capi.lib()  # fail loudly at import time if the CUDA library is missing
@@ -287,6 +287,147 @@ class ChebPoly:
         return self._eval(x, False)
 
 
+class MultiChebPoly:
+    """A ChebPoly replicated on several GPUs of the node and evaluated from ONE host process (fastcheb_multi_*):
+    `c.(ys)`, chebjacobian and chebgradient block-partition the points over the devices, results come back in one
+    array in point order, the ArgumentError names the first offending point of the whole batch (eval.jl:64).
+    numpy points -> host path (every device stages its block); torch CUDA points on devices[0] -> the other devices
+    read their block from, and write their results into, devices[0]'s memory over NVLink."""
+
+    def __init__(self, coefs, lb, ub, devices=None):
+        L = _capi.lib()
+        self.base = ChebPoly(coefs, lb, ub, device=(devices[0] if devices else 0))
+        ndev = L.fastcheb_device_count()
+        self.devices = list(range(ndev)) if devices is None else [int(d) for d in devices]
+        self._multi = {}
+
+    def _handle(self, rdt):
+        rdt = np.dtype(rdt)
+        h = self._multi.get(rdt)
+        if h is None:
+            b = self.base
+            flat = np.ascontiguousarray(_to_julia_flat(b.coefs, b.ndim).astype(rdt, copy=False))
+            h = ctypes.c_void_p()
+            devs = (ctypes.c_int * len(self.devices))(*self.devices)
+            rc = _capi.lib().fastcheb_multi_create(ctypes.byref(h), len(self.devices), devs, b.ndim, _capi.i64_array(b.dims),
+                                                   _dtype_code(rdt), int(b.is_complex), b.K or 1, flat.ctypes.data,
+                                                   _capi.MEM_HOST, _capi.dbl_array(b.lb), _capi.dbl_array(b.ub))
+            _check(rc, "fastcheb_multi_create: ")
+            self._multi[rdt] = h
+        return h
+
+    def close(self):
+        for h in self._multi.values():
+            _capi.lib().fastcheb_multi_destroy(h)
+        self._multi = {}
+        self.base.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _eval(self, x, jac: bool, grad: bool = False):
+        L = _capi.lib()
+        b = self.base
+        N, K, cplx = b.ndim, b.K, b.is_complex
+        E = (K or 1) * (2 if cplx else 1)
+        if _is_torch(x):
+            import torch
+
+            if not x.is_cuda or x.device.index != self.devices[0]:
+                raise ArgumentError(f"device-resident points must live on cuda:{self.devices[0]} (devices[0])")
+            rdt = b._compute_dtype(np.float32 if x.dtype == torch.float32 else np.float64)
+            tdt = torch.float32 if rdt == np.float32 else torch.float64
+            pts = x.to(tdt).reshape(-1, N).contiguous()
+            npts = pts.shape[0]
+            out = torch.empty((npts, E), dtype=tdt, device=x.device)
+            outJ = torch.empty((npts, N, E), dtype=tdt, device=x.device) if jac else None
+            torch.cuda.current_stream(x.device).synchronize()  # the workers use their own streams
+            p_in, p_v, p_J, mem = pts.data_ptr(), out.data_ptr(), (outJ.data_ptr() if jac else None), _capi.MEM_DEVICE
+        else:
+            xa = np.asarray(x)
+            rdt = b._compute_dtype(xa.dtype if xa.dtype.kind == "f" else np.float64)
+            pts = np.ascontiguousarray(xa.astype(rdt, copy=False).reshape(-1, N))
+            npts = pts.shape[0]
+            out = np.empty((npts, E), dtype=rdt)
+            outJ = np.empty((npts, N, E), dtype=rdt) if jac else None
+            p_in, p_v, p_J, mem = pts.ctypes.data, out.ctypes.data, (outJ.ctypes.data if jac else None), _capi.MEM_HOST
+        h = self._handle(rdt)
+        if jac:
+            fn = L.fastcheb_multi_eval_grad if grad else L.fastcheb_multi_eval_jac
+            rc = fn(h, p_in, npts, p_v, p_J, mem)
+        else:
+            rc = L.fastcheb_multi_eval(h, p_in, npts, p_v, mem)
+        if rc == _capi.EDOMAIN:
+            bad = _capi.error_index()
+            err = ArgumentError(f"{pts[bad].tolist()} not in domain {b.lb} to {b.ub}")  # eval.jl:64
+            err.index = bad
+            raise err
+        _check(rc, "fastcheb_multi_eval: ")
+        if _is_torch(x):
+            import torch
+
+            v = torch.view_as_complex(out.reshape(npts, -1, 2)) if cplx else out
+            v = v.reshape(npts) if K is None else v.reshape(npts, K)
+            if not jac:
+                return v
+            J = torch.view_as_complex(outJ.reshape(npts, N, -1, 2)) if cplx else outJ
+            return v, J.reshape(npts, N, K or 1).transpose(1, 2)
+        cdt = np.complex64 if rdt == np.float32 else np.complex128
+        v = out.view(cdt) if cplx else out
+        v = v.reshape(npts) if K is None else v.reshape(npts, K)
+        if not jac:
+            return v
+        J = outJ.view(cdt) if cplx else outJ
+        return v, np.swapaxes(J.reshape(npts, N, K or 1), 1, 2)
+
+    def __call__(self, x):
+        return self._eval(x, False)
+
+    # chebjacobian / chebgradient accept this type through the same functions
+    @property
+    def ndim(self):
+        return self.base.ndim
+
+    @property
+    def K(self):
+        return self.base.K
+
+    @property
+    def lb(self):
+        return self.base.lb
+
+    @property
+    def ub(self):
+        return self.base.ub
+
+
+def chebcoefs_multi(vals, devices=None, return_maxabs: bool = False):
+    """A batch of independent 1-D fits (leading batch axis) split over the GPUs of the node from one process
+    (fastcheb_multi_fit; SURVEY.md 8e: fits are sharded per GPU, a single fit is never split)."""
+    vals = _float_vals(vals)
+    if vals.ndim not in (2, 3):
+        raise DimensionMismatch("vals must be (howmany, n) or (howmany, n, K)")
+    L = _capi.lib()
+    devs = list(range(L.fastcheb_device_count())) if devices is None else [int(d) for d in devices]
+    howmany, n = vals.shape[:2]
+    K = vals.shape[2] if vals.ndim == 3 else None
+    cplx = np.iscomplexobj(vals)
+    rdt = _real_dtype(vals.dtype)
+    flat = np.ascontiguousarray(vals).reshape(-1)
+    flat = flat.view(rdt) if cplx else flat
+    out = np.empty_like(flat)
+    mx = np.zeros(howmany, dtype=np.float64) if return_maxabs else None
+    rc = L.fastcheb_multi_fit(len(devs), (ctypes.c_int * len(devs))(*devs), 1, _capi.i64_array((n,)), _dtype_code(rdt), int(cplx),
+                              K or 1, howmany, flat.ctypes.data, out.ctypes.data, mx.ctypes.data if return_maxabs else None,
+                              _capi.MEM_HOST)
+    _check(rc, "fastcheb_multi_fit: ")
+    res = (out.view(vals.dtype) if cplx else out).reshape(vals.shape)
+    return (res, mx) if return_maxabs else res
+
+
 def chebjacobian(c: ChebPoly, x):
     """(value, Jacobian) — eval.jl:147-155.  Jacobian shape (K, N) per point ((1, N) for scalar-valued c)."""
     return c._eval(x, True)
@@ -301,8 +442,8 @@ def chebgradient(c: ChebPoly, x):
     if c.K is not None:
         v = v[..., 0]
     g = J[..., 0, :]
-    if c.ndim == 1 and not _is_torch(x) and np.ndim(x) == 0:
-        return v, g[..., 0]  # eval.jl:174-177
+    if c.ndim == 1 and (x.dim() if _is_torch(x) else np.ndim(x)) <= 1:
+        return v, g[..., 0]  # eval.jl:174-177: a scalar derivative per scalar point (a 1-D array is a batch of them)
     return v, g
 
 
@@ -783,12 +924,15 @@ def frule(dx, c: ChebPoly, x, dself: ChebPoly | None = None, dlb=None, dub=None)
     """ChainRulesCore.frule((Δself, Δx), c, x) — chainrules.jl:18-39, batched: returns (y, ẏ) with ẏ = J Δx per point.
     `dself` (a ChebPoly holding Δcoefs on c's box), `dlb`, `dub` are the optional tangents of the polynomial itself:
     Δx' = Δx + (d2 - 1) Δlb - d2 Δub with d2 = (x - lb)/(ub - lb) (:31-32) and ẏ += Δcoefs(x) (:35-37)."""
-    xa = np.asarray(x, dtype=float)
-    dxa = np.broadcast_to(np.asarray(dx, dtype=float), xa.shape).copy()
+    xa = np.asarray(x)
+    if xa.dtype.kind != "f":
+        xa = xa.astype(np.float64)
+    fdt = xa.dtype  # Float32 points keep the Float32 promotion path (eval.jl:25)
+    dxa = np.broadcast_to(np.asarray(dx, dtype=fdt), xa.shape).copy()
     if dlb is not None or dub is not None:
-        lb, ub = c.lb.astype(float), c.ub.astype(float)
+        lb, ub = c.lb.astype(fdt), c.ub.astype(fdt)
         d2 = (xa - lb) / (ub - lb)
-        dxa = dxa + (d2 - 1) * (0.0 if dlb is None else np.asarray(dlb, dtype=float)) - d2 * (0.0 if dub is None else np.asarray(dub, dtype=float))
+        dxa = dxa + (d2 - 1) * (0.0 if dlb is None else np.asarray(dlb, dtype=fdt)) - d2 * (0.0 if dub is None else np.asarray(dub, dtype=fdt))
     y, ydot = _tangent_call(c, xa, dxa, 2)
     if dself is not None:
         ydot = ydot + dself(xa)

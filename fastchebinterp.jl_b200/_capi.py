@@ -25,6 +25,8 @@ SYMBOLS = [
     "fastcheb_is_complex", "fastcheb_ncomp", "fastcheb_device", "fastcheb_get_coefs", "fastcheb_set_algo",
     "fastcheb_get_algo", "fastcheb_eval", "fastcheb_eval_jac", "fastcheb_eval_grad", "fastcheb_eval_jac_tuple",
     "fastcheb_eval_async", "fastcheb_eval_jac_async", "fastcheb_eval_many", "fastcheb_eval_vjp", "fastcheb_eval_jvp", "fastcheb_fit", "fastcheb_fit_async", "fastcheb_droptol_shape", "fastcheb_interp", "fastcheb_reinterp", "fastcheb_vandermonde",
+    "fastcheb_multi_create", "fastcheb_multi_destroy", "fastcheb_multi_ngpus", "fastcheb_multi_device", "fastcheb_multi_poly",
+    "fastcheb_multi_eval", "fastcheb_multi_eval_jac", "fastcheb_multi_eval_grad", "fastcheb_multi_eval_jac_tuple", "fastcheb_multi_fit",
     "fastcheb_peer_alloc", "fastcheb_peer_free", "fastcheb_peer_open", "fastcheb_peer_close", "fastcheb_peer_read",
 ]
 
@@ -67,6 +69,16 @@ def lib() -> ctypes.CDLL:
         "fastcheb_eval_jac_async": (i32, [vp, vp, i64, vp, vp, vp, vp]),
         "fastcheb_fit": (i32, [i32, i64p, i32, i32, i32, i64, vp, vp, vp, i32, i32, vp]),
         "fastcheb_reinterp": (i32, [ctypes.POINTER(vp), vp, i64p, dblp, dblp, dbl, vp]),
+        "fastcheb_multi_create": (i32, [ctypes.POINTER(vp), i32, ctypes.POINTER(i32), i32, i64p, i32, i32, i32, vp, i32, dblp, dblp]),
+        "fastcheb_multi_destroy": (i32, [vp]),
+        "fastcheb_multi_ngpus": (i32, [vp]),
+        "fastcheb_multi_device": (i32, [vp, i32]),
+        "fastcheb_multi_poly": (vp, [vp, i32]),
+        "fastcheb_multi_eval": (i32, [vp, vp, i64, vp, i32]),
+        "fastcheb_multi_eval_jac": (i32, [vp, vp, i64, vp, vp, i32]),
+        "fastcheb_multi_eval_grad": (i32, [vp, vp, i64, vp, vp, i32]),
+        "fastcheb_multi_eval_jac_tuple": (i32, [vp, vp, i64, vp, i32]),
+        "fastcheb_multi_fit": (i32, [i32, ctypes.POINTER(i32), i32, i64p, i32, i32, i32, i64, vp, vp, vp, i32]),
         "fastcheb_peer_alloc": (i32, [ctypes.POINTER(vp), ctypes.c_size_t, vp, i32]),
         "fastcheb_peer_free": (i32, [vp, i32]),
         "fastcheb_peer_open": (i32, [ctypes.POINTER(vp), vp, i32]),

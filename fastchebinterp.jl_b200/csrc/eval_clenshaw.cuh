@@ -46,7 +46,7 @@ struct EvalParams {
   int T;                 // slabs per polynomial
   int compStride;        // elements per component plane of a slab
   int slabElems;         // EC * compStride
-  int nstage;            // shared-memory slab buffers
+  int nstage;            // shared-memory slab buffers (0: 1-D line read from global memory, GLOBAL instantiation)
   double lb[kMaxNdim], ub[kMaxNdim];
   // Jacobian contraction (AD rules, chainrules.jl:4-39): 0 = store J; 1 = pullback, out_J[p*N + d] (+)= sum_e J[e][d] *
   // tan[p*Etot + e] (accumulated over component groups, e0 == 0 writes); 2 = pushforward, out_J[p*Etot + e] =
@@ -69,7 +69,9 @@ template <> struct VecOf<float> {
   }
 };
 
-template <typename R, int N, int EC, int P, bool JAC>
+// GLOBAL (1-D only): the coefficient line does not fit shared memory (n1 > ~29 000 doubles); it is read straight from
+// global memory / L2 with the same warp-uniform vector loads.
+template <typename R, int N, int EC, int P, bool JAC, bool GLOBAL = false>
 struct ClenshawCta {
   using VT = VecOf<R>;
   using Vec = typename VT::type;
@@ -309,15 +311,19 @@ struct ClenshawCta {
     const long long my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
     total_visits = my_tiles * prm.T;
     visit = 0;
-    if (threadIdx.x == 0) {
-      for (int b = 0; b < prm.nstage; ++b) mbar_init(&full[b], 1);
-      fence_mbar_init();
-      for (int b = 0; b < prm.nstage && b < total_visits; ++b) issue(b);
-    }
-    __syncthreads();
-    if (prm.T == 1) {
-      mbar_wait(&full[0], 0);
-      slab = bufs;
+    if constexpr (GLOBAL) {
+      slab = reinterpret_cast<const R*>(prm.coefs);
+    } else {
+      if (threadIdx.x == 0) {
+        for (int b = 0; b < prm.nstage; ++b) mbar_init(&full[b], 1);
+        fence_mbar_init();
+        for (int b = 0; b < prm.nstage && b < total_visits; ++b) issue(b);
+      }
+      __syncthreads();
+      if (prm.T == 1) {
+        mbar_wait(&full[0], 0);
+        slab = bufs;
+      }
     }
     const R* __restrict__ pts = reinterpret_cast<const R*>(prm.pts);
     R* __restrict__ out_v = reinterpret_cast<R*>(prm.out_v);
@@ -408,10 +414,10 @@ struct ClenshawCta {
   }
 };
 
-template <typename R, int N, int EC, int P, bool JAC>
+template <typename R, int N, int EC, int P, bool JAC, bool GLOBAL = false>
 __global__ void __launch_bounds__((JAC || N * EC >= 9) ? 256 : 512) clenshaw_kernel(const __grid_constant__ EvalParams prm) {
   extern __shared__ __align__(128) unsigned char fastcheb_smem[];
-  ClenshawCta<R, N, EC, P, JAC> cta(prm);
+  ClenshawCta<R, N, EC, P, JAC, GLOBAL> cta(prm);
   cta.run(fastcheb_smem);
 }
 

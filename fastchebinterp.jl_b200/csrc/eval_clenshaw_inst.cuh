@@ -7,6 +7,15 @@ namespace {
 template <int N, int EC>
 cudaError_t go(int op, const EvalParams& prm, int threads, int grid, size_t smem, cudaStream_t st, int* bps) {
   constexpr int P = clenshaw_pts(N, EC, FC_JAC);
+  if constexpr (N == 1) {
+    if (prm.nstage == 0) {  // the coefficient line stays in global memory (plan_clenshaw, poly.cu)
+      auto kg = clenshaw_kernel<FC_REAL, N, EC, P, FC_JAC, true>;
+      if (op == kOpOccupancy) return cached_occupancy(bps, reinterpret_cast<const void*>(kg), threads, smem);
+      kg<<<grid, threads, smem, st>>>(prm);
+      note_launch();
+      return cudaGetLastError();
+    }
+  }
   auto kern = clenshaw_kernel<FC_REAL, N, EC, P, FC_JAC>;
   cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;

@@ -165,23 +165,33 @@ extern "C" int fastcheb_eval_many(int64_t howmany, int64_t n, int dtype, int is_
   prm.M = M;
   prm.n = (int)n;
   prm.bounds_per_poly = bounds_per_poly ? 1 : 0;
+  // The status flag: the synchronous host path borrows a slot of the per-device pool (released when the call returns,
+  // after the stream has been synchronised); the asynchronous device path writes only to the caller's status_dev
+  // (may be NULL: no status) — a pool slot must not outlive the call while the kernel is still running.
   FlagSlot fs;
-  FC_TRY(flag_acquire(device, &fs));
   struct Rel {
     FlagSlot& f;
     ~Rel() { flag_release(f); }
   } rel{fs};
-  long long* flag = status_dev && mem == FASTCHEB_MEM_DEVICE ? (long long*)status_dev : fs.dev;
-  FC_CUDA(set_flag_async(flag, kNoBad, st));
+  long long* flag = (long long*)status_dev;
+  if (mem == FASTCHEB_MEM_HOST) {
+    FC_TRY(flag_acquire(device, &fs));
+    flag = fs.dev;
+  }
+  if (flag) FC_CUDA(set_flag_async(flag, kNoBad, st));
   prm.bad = flag;
   void* scratch = nullptr;
   struct Free {
     int dev;
     void*& p;
+    cudaStream_t st;
     ~Free() {
-      if (p) ws_release(dev, p);
+      if (p) {
+        cudaStreamSynchronize(st);  // copies / kernels enqueued on the buffer (error paths return early) are done
+        ws_release(dev, p);
+      }
     }
-  } fr{device, scratch};
+  } fr{device, scratch, st};
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
   if (mem == FASTCHEB_MEM_HOST) {
     const size_t total = al(cbytes) + al(pbytes) + al(obytes) * (out_d ? 2 : 1) + 2 * al(nb * 8);

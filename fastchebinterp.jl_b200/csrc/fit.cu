@@ -46,6 +46,13 @@ int cos_table(int dev, int n, const double2** out) {
     h[r].x = (double)v;
     h[r].y = (double)(v - (long double)h[r].x);
   }
+  // adaptive order doubling and roots() visit a handful of sizes; a caller that sweeps many distinct n must not
+  // accumulate tables for ever: beyond 64 cached tables the cache is dropped (after the device has drained)
+  if (g_ctab.size() >= 64) {
+    cudaDeviceSynchronize();
+    for (auto& kv : g_ctab) cudaFree(kv.second);
+    g_ctab.clear();
+  }
   double2* d = nullptr;
   FC_CUDA(cudaMalloc(&d, h.size() * sizeof(double2)));
   FC_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice));
@@ -73,11 +80,14 @@ int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int
     return FASTCHEB_OK;
   }
   // ping-pong so that the last pass lands in `coefs`; `vals` is never written
+  // scratch comes from the device's stream-ordered pool and is freed in stream order: the call never blocks the host
   R* tmp = nullptr;
   R* tmp2 = nullptr;
   if (npass > 1 || (const void*)vals == (void*)coefs) {
-    tmp = (R*)ws_acquire(dev, (size_t)total * sizeof(R));
-    if (!tmp) return fail(FASTCHEB_ENOMEM, "fit scratch of %lld bytes", total * (long long)sizeof(R));
+    if (pool_alloc((void**)&tmp, (size_t)total * sizeof(R), st) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(FASTCHEB_ENOMEM, "fit scratch of %lld bytes", total * (long long)sizeof(R));
+    }
   }
   const R* src = vals;
   int rc = FASTCHEB_OK;
@@ -91,8 +101,9 @@ int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int
       R* dst = (remaining % 2 == 1) ? coefs : tmp;
       if ((const void*)dst == (const void*)src) {
         // only possible on pass 0 with vals == coefs and odd npass: move vals out of the way first
-        tmp2 = (R*)ws_acquire(dev, (size_t)total * sizeof(R));
-        if (!tmp2) {
+        if (pool_alloc((void**)&tmp2, (size_t)total * sizeof(R), st) != cudaSuccess) {
+          cudaGetLastError();
+          tmp2 = nullptr;
           rc = fail(FASTCHEB_ENOMEM, "fit scratch of %lld bytes", total * (long long)sizeof(R));
           break;
         }
@@ -116,9 +127,8 @@ int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int
     }
     inner *= n;
   }
-  if (tmp || tmp2) cudaStreamSynchronize(st);  // scratch goes back to the cache only once the work is done
-  if (tmp) ws_release(dev, tmp);
-  if (tmp2) ws_release(dev, tmp2);
+  if (tmp) cudaFreeAsync(tmp, st);
+  if (tmp2) cudaFreeAsync(tmp2, st);
   return rc;
 }
 
@@ -183,59 +193,81 @@ int check_args(int ndim, const int64_t* dims, int dtype, int ncomp, int mem) {
   return FASTCHEB_OK;
 }
 
-// droptol's shape decision from device coefficients (interp.jl:77-93)
-int droptol_device(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int dtype, int cplx, int K,
-                   const void* d_coefs, double tol, int64_t* newdims, double* maxabs_out, cudaStream_t st) {
+// stats[0] = max (init 0), stats[1] = min (init +inf), hyperplane maxima (init 0)
+__global__ void __launch_bounds__(256) norm_init_kernel(double* __restrict__ stats, int nd) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nd; i += gridDim.x * blockDim.x) stats[i] = i == 1 ? INFINITY : 0.0;
+}
+
+// droptol's shape decision from device coefficients (interp.jl:77-93), in two halves so that a caller can put other
+// work (and its own status read-back) between the enqueue and the single host synchronisation.
+struct DroptolJob {
+  NormParams np;
+  size_t nd = 0;
+  double* d_stats = nullptr;  // stream-ordered pool allocation
+  std::vector<double> h;
+};
+
+int droptol_enqueue(DroptolJob& job, const DeviceInfo* di, int ndim, const int64_t* dims, int dtype, int cplx, int K,
+                    const void* d_coefs, cudaStream_t st) {
   long long elems = 1;
   int hsum = 0;
-  NormParams np;
-  memset(&np, 0, sizeof np);
-  np.ndim = ndim;
+  memset(&job.np, 0, sizeof job.np);
+  job.np.ndim = ndim;
   for (int d = 0; d < ndim; ++d) {
     elems *= dims[d];
-    np.n[d] = (int)dims[d];
-    np.hoff[d] = hsum;
+    job.np.n[d] = (int)dims[d];
+    job.np.hoff[d] = hsum;
     hsum += (int)dims[d];
-    newdims[d] = dims[d];
   }
-  const size_t nd = 2 + (size_t)hsum;
-  double* d_stats = (double*)ws_acquire(dev, nd * sizeof(double));
-  if (!d_stats) return fail(FASTCHEB_ENOMEM, "droptol scratch");
-  std::vector<double> h(nd);
-  int rc = FASTCHEB_OK;
-  do {
-    // stats[0] = max (init 0), stats[1] = min (init +inf), hyperplane maxima (init 0)
-    std::vector<double> init(nd, 0.0);
-    init[1] = INFINITY;
-    if (cudaMemcpyAsync(d_stats, init.data(), nd * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess) {
-      rc = fail(FASTCHEB_ECUDA, "droptol init copy failed");
-      break;
-    }
-    cudaStreamSynchronize(st);  // `init` is pageable: finish the copy before it goes out of scope
-    const int grid = grid_for(elems, 256, di->sms);
-    if (dtype == FASTCHEB_F64)
-      coef_norm_kernel<double><<<grid, 256, 0, st>>>((const double*)d_coefs, elems, 1, K, cplx, d_stats, d_stats + 2, np);
-    else
-      coef_norm_kernel<float><<<grid, 256, 0, st>>>((const float*)d_coefs, elems, 1, K, cplx, d_stats, d_stats + 2, np);
-    if (cudaGetLastError() != cudaSuccess ||
-        cudaMemcpyAsync(h.data(), d_stats, nd * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaStreamSynchronize(st) != cudaSuccess) {
-      rc = fail(FASTCHEB_ECUDA, "droptol reduction failed: %s", cudaGetErrorString(cudaGetLastError()));
-      break;
-    }
-  } while (0);
-  ws_release(dev, d_stats);
-  if (rc != FASTCHEB_OK) return rc;
-  const double mx = h[0], mn = h[1];
+  job.nd = 2 + (size_t)hsum;
+  job.h.resize(job.nd);
+  if (pool_alloc((void**)&job.d_stats, job.nd * sizeof(double), st) != cudaSuccess) {
+    cudaGetLastError();
+    job.d_stats = nullptr;
+    return fail(FASTCHEB_ENOMEM, "droptol scratch");
+  }
+  norm_init_kernel<<<(int)std::min<size_t>((job.nd + 255) / 256, 64), 256, 0, st>>>(job.d_stats, (int)job.nd);
+  const int grid = grid_for(elems, 256, di->sms);
+  if (dtype == FASTCHEB_F64)
+    coef_norm_kernel<double><<<grid, 256, 0, st>>>((const double*)d_coefs, elems, 1, K, cplx, job.d_stats, job.d_stats + 2, job.np);
+  else
+    coef_norm_kernel<float><<<grid, 256, 0, st>>>((const float*)d_coefs, elems, 1, K, cplx, job.d_stats, job.d_stats + 2, job.np);
+  note_launch(2);
+  if (cudaGetLastError() != cudaSuccess) {
+    cudaFreeAsync(job.d_stats, st);
+    job.d_stats = nullptr;
+    return fail(FASTCHEB_ECUDA, "droptol reduction launch failed");
+  }
+  return FASTCHEB_OK;
+}
+
+// blocks until the statistics are on the host (the one synchronisation of droptol), then decides the shape
+int droptol_finish(DroptolJob& job, int ndim, const int64_t* dims, double tol, int64_t* newdims, double* maxabs_out,
+                   cudaStream_t st) {
+  cudaError_t e = cudaMemcpyAsync(job.h.data(), job.d_stats, job.nd * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(job.d_stats, st);
+  job.d_stats = nullptr;
+  if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "droptol reduction failed: %s", cudaGetErrorString(e));
+  for (int d = 0; d < ndim; ++d) newdims[d] = dims[d];
+  const double mx = job.h[0], mn = job.h[1];
   if (maxabs_out) *maxabs_out = mx;
-  const double abstol = mx * tol;  // interp.jl:78
+  const double abstol = mx * tol;        // interp.jl:78
   if (mn >= abstol) return FASTCHEB_OK;  // interp.jl:79: nothing to drop
-  for (int d = 0; d < ndim; ++d) {   // interp.jl:83-91
+  for (int d = 0; d < ndim; ++d) {       // interp.jl:83-91
     int64_t n = dims[d];
-    while (n > 1 && !(h[2 + np.hoff[d] + (n - 1)] >= abstol)) --n;
+    while (n > 1 && !(job.h[2 + job.np.hoff[d] + (n - 1)] >= abstol)) --n;
     newdims[d] = n;
   }
   return FASTCHEB_OK;
+}
+
+int droptol_device(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int dtype, int cplx, int K,
+                   const void* d_coefs, double tol, int64_t* newdims, double* maxabs_out, cudaStream_t st) {
+  (void)dev;
+  DroptolJob job;
+  FC_TRY(droptol_enqueue(job, di, ndim, dims, dtype, cplx, K, d_coefs, st));
+  return droptol_finish(job, ndim, dims, tol, newdims, maxabs_out, st);
 }
 
 // points of a tensor-product grid, AoS: pts[g*N + d] = axis_d[index of g along d] (g column-major over the grid)
@@ -258,12 +290,18 @@ __global__ void __launch_bounds__(256) grid_points_kernel(const double* __restri
   }
 }
 
+// A cached device buffer that goes back to the cache when the call returns.  The stream is synchronised first: on
+// the success paths it already is (cheap), on early error returns copies or kernels may still be using the buffer.
 struct HostStage {
   int dev;
+  cudaStream_t st;
   void* d = nullptr;
-  HostStage(int dev_) : dev(dev_) {}
+  HostStage(int dev_, cudaStream_t st_) : dev(dev_), st(st_) {}
   ~HostStage() {
-    if (d) ws_release(dev, d);
+    if (d) {
+      cudaStreamSynchronize(st);
+      ws_release(dev, d);
+    }
   }
 };
 
@@ -396,7 +434,7 @@ int fastcheb_droptol_shape(int ndim, const int64_t* dims, int dtype, int is_comp
   long long elems = 1;
   for (int d = 0; d < ndim; ++d) elems *= dims[d];
   const size_t bytes = (size_t)elems * E * real_size(dtype);
-  HostStage in(device);
+  HostStage in(device, st);
   const void* d_c = coefs;
   if (mem == FASTCHEB_MEM_HOST) {
     in.d = ws_acquire(device, bytes);
@@ -431,7 +469,7 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
     ~Rel() { flag_release(f); }
   } rel{fs};
   FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
-  HostStage in(device), co(device), blk(device);
+  HostStage in(device, st), co(device, st), blk(device, st);
   const void* d_vals = vals;
   if (mem == FASTCHEB_MEM_HOST) {
     in.d = ws_acquire(device, bytes);
@@ -442,14 +480,25 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
   co.d = ws_acquire(device, bytes);
   if (!co.d) return fail(FASTCHEB_ENOMEM, "device scratch of %zu bytes", bytes);
   FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, 1, d_vals, co.d, nullptr, fs.dev, st));
-  FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  FC_CUDA(cudaStreamSynchronize(st));
+  // one host synchronisation for both the finite flag (interp.jl:40) and droptol's statistics (interp.jl:77-91)
+  DroptolJob job;
+  const bool trim = tol > 0;  // tol == 0: abstol = 0 and nothing is ever dropped (interp.jl:78-79)
+  if (trim) FC_TRY(droptol_enqueue(job, di, ndim, dims, dtype, is_complex, ncomp, co.d, st));
+  if (cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+    if (job.d_stats) cudaFreeAsync(job.d_stats, st);
+    return fail(FASTCHEB_ECUDA, "status read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  int64_t newdims[FASTCHEB_MAX_NDIM];
+  if (trim) {
+    FC_TRY(droptol_finish(job, ndim, dims, tol, newdims, nullptr, st));
+  } else {
+    FC_CUDA(cudaStreamSynchronize(st));
+    for (int d = 0; d < ndim; ++d) newdims[d] = dims[d];
+  }
   if (*fs.host != kNoBad) {
     err_state().index = *fs.host;
     return fail(FASTCHEB_ENONFINITE, "non-finite interpolant value at flat index %lld (interp.jl:40)", *fs.host);
   }
-  int64_t newdims[FASTCHEB_MAX_NDIM];
-  FC_TRY(droptol_device(di, device, ndim, dims, dtype, is_complex, ncomp, co.d, tol, newdims, nullptr, st));
   bool same = true;
   long long new_elems = 1;
   for (int d = 0; d < ndim; ++d) {
@@ -525,13 +574,13 @@ int fastcheb_reinterp(fastcheb_poly** out, const fastcheb_poly* p, const int64_t
       }
       axes[gp.off[d] + i] = std::min(std::max(x, p->lb[d]), p->ub[d]);
     }
-  HostStage ax(dev), pts(dev), vals(dev);
+  HostStage ax(dev, st), pts(dev, st), vals(dev, st);
   ax.d = ws_acquire(dev, axes.size() * sizeof(double));
   pts.d = ws_acquire(dev, (size_t)total * N * rs);
   vals.d = ws_acquire(dev, (size_t)total * p->E * rs);
   if (!ax.d || !pts.d || !vals.d) return fail(FASTCHEB_ENOMEM, "re-interpolation scratch");
+  // `axes` is pageable host memory: cudaMemcpyAsync stages it before returning, so the vector may go out of scope
   FC_CUDA(cudaMemcpyAsync(ax.d, axes.data(), axes.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-  FC_CUDA(cudaStreamSynchronize(st));  // `axes` is pageable host memory
   const int grid = grid_for(total, 256, di->sms);
   if (p->dtype == FASTCHEB_F64)
     grid_points_kernel<double><<<grid, 256, 0, st>>>((const double*)ax.d, (double*)pts.d, total, gp);

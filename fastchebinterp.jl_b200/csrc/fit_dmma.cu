@@ -257,8 +257,10 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   if (smem > budget) return FASTCHEB_OK;
   double* linemax = nullptr;
   if (fit_max_dev) {
-    linemax = (double*)ws_acquire(dev, (size_t)nunits * lines * sizeof(double));
-    if (!linemax) return fail(FASTCHEB_ENOMEM, "fit line-maximum scratch");
+    if (pool_alloc((void**)&linemax, (size_t)nunits * lines * sizeof(double), st) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(FASTCHEB_ENOMEM, "fit line-maximum scratch");
+    }
   }
   prm.linemax = linemax;
   const int threads = warps * 32;
@@ -271,7 +273,7 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
   e = go(&bps, 0);
   if (e != cudaSuccess || bps < 1) {
     cudaGetLastError();
-    if (linemax) ws_release(dev, linemax);
+    if (linemax) cudaFreeAsync(linemax, st);
     return FASTCHEB_OK;  // not covered: the caller falls back to the generic kernel
   }
   const long long want = (nunits + warps - 1) / warps;
@@ -286,10 +288,7 @@ int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, 
     note_launch();
     if (cudaGetLastError() != cudaSuccess) rc = fail(FASTCHEB_ECUDA, "fit maximum kernel launch failed");
   }
-  if (linemax) {
-    cudaStreamSynchronize(st);  // scratch returns to the cache only once the work is done
-    ws_release(dev, linemax);
-  }
+  if (linemax) cudaFreeAsync(linemax, st);  // stream-ordered: the call stays asynchronous
   if (rc == FASTCHEB_OK) *done = nunits * U;
   return rc;
 }

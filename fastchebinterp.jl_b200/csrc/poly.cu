@@ -44,22 +44,35 @@ int plan_clenshaw(fastcheb_poly* p, cudaStream_t st) {
     const int left = p->E - e0;
     int ec = left <= kClenshawMaxEC ? left : (left == 5 ? 3 : (left % 4 == 0 ? 4 : (left % 3 == 0 ? 3 : 4)));
     ClenshawGroup g;
+    // the largest slab level that fits; when not even one dimension-1 line of `ec` components fits shared memory,
+    // retry with fewer components per launch
+    int s = 0;
+    for (;; ec = ec > 2 ? 2 : 1) {
+      for (s = p->ndim; s >= 1; --s) {
+        double elems = (double)ec * n1p;
+        for (int d = 1; d < s; ++d) elems *= (double)p->dims[d];
+        long long T = 1;
+        for (int d = s; d < p->ndim; ++d) T *= p->dims[d];
+        const double bytes = elems * rs;
+        if (T == 1 ? bytes <= (double)budget : 2 * bytes <= (double)budget) break;
+      }
+      if (s >= 1 || ec == 1) break;
+    }
     g.e0 = e0;
     g.ec = ec;
     g.n1p = n1p;
     g.nvec1 = n1p / V;
-    // the largest slab level that fits
-    int s = p->ndim;
-    for (; s >= 1; --s) {
-      double elems = (double)ec * n1p;
-      for (int d = 1; d < s; ++d) elems *= (double)p->dims[d];
-      long long T = 1;
-      for (int d = s; d < p->ndim; ++d) T *= p->dims[d];
-      const double bytes = elems * rs;
-      if (T == 1 ? bytes <= (double)budget : 2 * bytes <= (double)budget) break;
+    const bool global_line = s < 1;  // one line of ONE component exceeds shared memory (n1 > ~29 000 doubles)
+    if (global_line) {
+      if (p->ndim != 1) {
+        // The handle is still built (coefficients, droptol, fits and roots work); only evaluation is refused.
+        for (auto& q : p->groups) pool_free_all(&q.d_pp, 1);
+        p->groups.clear();
+        p->eval_ok = false;
+        return FASTCHEB_OK;
+      }
+      s = 1;  // 1-D: the GLOBAL instantiation reads the line from global memory / L2
     }
-    if (s < 1)
-      return fail(FASTCHEB_EUNSUPPORTED, "dimension 1 has %d coefficients: one line does not fit shared memory", n1);
     long long Ms = 1, T = 1;
     for (int d = 1; d < s; ++d) Ms *= p->dims[d];
     for (int d = s; d < p->ndim; ++d) T *= p->dims[d];
@@ -69,7 +82,7 @@ int plan_clenshaw(fastcheb_poly* p, cudaStream_t st) {
     g.compStride = (int)(Ms * n1p);
     g.slabElems = ec * g.compStride;
     const size_t slabBytes = (size_t)g.slabElems * rs;
-    g.nstage = T == 1 ? 1 : (int)std::min<long long>(std::min<long long>(4, T), (long long)(budget / slabBytes));
+    g.nstage = global_line ? 0 : (T == 1 ? 1 : (int)std::min<long long>(std::min<long long>(4, T), (long long)(budget / slabBytes)));
     g.smem = 128 + (size_t)g.nstage * slabBytes;
     long long str = 1;
     for (int d = 0; d < p->ndim; ++d) {
@@ -105,6 +118,11 @@ int eval_clenshaw(const fastcheb_poly* p, const void* pts, int64_t npts, void* o
                 const void* tan) {
   if (p->ndim > kMaxKernelNdim)
     return fail(FASTCHEB_EUNSUPPORTED, "ndim = %d: evaluation kernels cover ndim <= %d", p->ndim, kMaxKernelNdim);
+  if (!p->eval_ok)
+    return fail(FASTCHEB_EUNSUPPORTED,
+                "evaluation of an N-d polynomial whose dimension-1 line (%lld coefficients) exceeds shared memory is not "
+                "covered; coefficients, droptol and re-interpolation of this handle work",
+                (long long)p->dims[0]);
   ClenshawFn fn = clenshaw_fn(p->dtype, jac);
   for (const ClenshawGroup& g : p->groups) {
     const int P = clenshaw_pts(p->ndim, g.ec, jac);

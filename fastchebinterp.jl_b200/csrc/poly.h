@@ -48,6 +48,7 @@ struct fastcheb_poly {
   std::vector<fastcheb::ClenshawGroup> groups;
   fastcheb::DmmaPlan dmma;
   int algo = FASTCHEB_ALGO_AUTO;
+  bool eval_ok = true;  // false: N-d polynomial whose dimension-1 line does not fit shared memory (plan_clenshaw)
 };
 
 namespace fastcheb {

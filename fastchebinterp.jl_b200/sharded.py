@@ -134,9 +134,13 @@ class ShardedChebPoly:
                 res = chebjacobian(self.poly, pts_local) if hasattr(self.poly, "_eval") else self.poly.jacobian(pts_local)
             else:
                 res = self.poly(pts_local)
-        except ValueError as e:  # ArgumentError (domain) is a ValueError in both the product and the oracle
+        except ValueError as e:
+            # only the out-of-domain ArgumentError (it carries the index of the first offending point) takes part in the
+            # collective; a DimensionMismatch or any other ValueError is this rank's own error and propagates as is
+            if not hasattr(e, "index"):
+                raise
             err = e
-            local_bad = getattr(e, "index", 0)
+            local_bad = e.index
         dev = _comm_device(dist)
         n_local = len(pts_local)
         counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
@@ -154,10 +158,18 @@ class ShardedChebPoly:
 
     def eval_gather(self, pts_local, dst: int = 0):
         """c.(ys) with ys block-partitioned over the ranks; the values are gathered on `dst` in global point order
-        (None on the other ranks)."""
+        (None on the other ranks).
+
+        NCCL backend with device-resident points (torch CUDA tensors): the FUSED path that bench.py times — rank `dst`
+        owns one result buffer (PeerGather), every rank's evaluation kernel stores its block straight into it through
+        the CUDA-IPC mapping over NVLink, and `dst` gets a torch tensor that aliases the buffer (no staging copy, no
+        collective kernel; the out-of-domain status is an all-reduce(MIN) of the first offending global index).
+        Other backends / host points: evaluate locally, then point-to-point gather."""
         import torch
 
         dist = _dist()
+        if dist.get_backend() == "nccl" and isinstance(pts_local, torch.Tensor) and pts_local.is_cuda and hasattr(self.poly, "_handle"):
+            return self._eval_gather_fused(pts_local, dst)
         v = self.eval_local(pts_local)
         dev = _comm_device(dist)
         t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v)).to(dev)
@@ -180,6 +192,49 @@ class ShardedChebPoly:
                 out = torch.view_as_complex(out)
         else:
             dist.send(t.contiguous(), dst=dst)
+        return out
+
+    def _eval_gather_fused(self, pts, dst: int):
+        import ctypes
+
+        import torch
+
+        from . import ArgumentError, _capi, _check
+
+        dist = _dist()
+        poly = self.poly
+        N, K, cplx = poly.ndim, poly.K, poly.is_complex
+        E = (K or 1) * (2 if cplx else 1)
+        rdt = poly._compute_dtype(np.float32 if pts.dtype == torch.float32 else np.float64)
+        tdt = torch.float32 if rdt == np.float32 else torch.float64
+        p = pts.to(tdt).reshape(-1, N).contiguous()
+        n_local = p.shape[0]
+        dev = p.device
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        counts[self.rank] = n_local
+        dist.all_reduce(counts)
+        counts = [int(x) for x in counts.tolist()]
+        offset, total = sum(counts[: self.rank]), sum(counts)
+        peer = PeerGather(total_rows=total, row_reals=E, itemsize=np.dtype(rdt).itemsize, dst=dst, device=dev.index)
+        status = torch.empty(1, dtype=torch.int64, device=dev)
+        sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _check(_capi.lib().fastcheb_eval_async(poly._handle(rdt), p.data_ptr(), n_local, peer.slice_ptr(offset), status.data_ptr(), sp),
+               "fastcheb_eval_async: ")
+        flag = torch.where(status == NO_BAD, status, status + offset)       # first offending GLOBAL index
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                         # also orders every rank's kernel before the read
+        torch.cuda.current_stream(dev).synchronize()
+        dist.barrier()
+        first = int(flag.item())
+        if first != NO_BAD:
+            peer.close()
+            raise ArgumentError(f"point {first} not in domain {poly.lb} to {poly.ub}")
+        out = None
+        if self.rank == dst:
+            out = peer.as_tensor(tdt, (total, E)).clone()     # one device-to-device copy out of the IPC buffer
+            if cplx:
+                out = torch.view_as_complex(out.reshape(total, -1, 2))
+            out = out.reshape(total) if K is None else out.reshape(total, K)
+        peer.close()
         return out
 
 
@@ -216,12 +271,29 @@ def sharded_fit(vals_all, ndim: int = 1, src: int = 0, fit_fn=None):
             q.wait()
     else:
         dist.recv(mine, src=src)
-    if fit_fn is None:
-        from . import chebcoefs
+    if fit_fn is None and dev.type == "cuda" and ndim == 1:
+        # NCCL, batches of 1-D fits (configs[4]): the block never leaves the device — fastcheb_fit on the received tensor,
+        # coefficients into a device tensor.  (howmany, n[, K]) C-order is the Julia order of back-to-back 1-D fits.
+        import ctypes
 
-        fit_fn = lambda v: chebcoefs(v, ndim=ndim, howmany=v.shape[0], device=torch.cuda.current_device())  # noqa: E731
-    local = np.asarray(fit_fn(mine.cpu().numpy())) if hi > lo else np.empty((0,) + tuple(shape[1:]), dt)
-    lt = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+        from . import _capi, _check
+
+        mine = mine.contiguous()
+        lt = torch.empty_like(mine)
+        if hi > lo:
+            body = tuple(shape[1:])
+            K = body[1] if len(body) == 2 else 1
+            rcode = _capi.F64 if mine.dtype in (torch.float64, torch.complex128) else _capi.F32
+            sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _check(_capi.lib().fastcheb_fit(1, _capi.i64_array(body[:1]), rcode, int(mine.is_complex()), K, hi - lo, mine.data_ptr(),
+                                            lt.data_ptr(), None, _capi.MEM_DEVICE, dev.index, sp), "fastcheb_fit: ")
+    else:
+        if fit_fn is None:
+            from . import chebcoefs
+
+            fit_fn = lambda v: chebcoefs(v, ndim=ndim, howmany=v.shape[0], device=torch.cuda.current_device())  # noqa: E731
+        local = np.asarray(fit_fn(mine.cpu().numpy())) if hi > lo else np.empty((0,) + tuple(shape[1:]), dt)
+        lt = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
     if rank == src:
         outs = []
         reqs = []
@@ -277,6 +349,20 @@ class PeerGather:
     def slice_ptr(self, first_row: int) -> int:
         """Device pointer (valid on THIS rank) of row `first_row` of the gathered buffer."""
         return self.base + int(first_row) * self.row_bytes
+
+    def as_tensor(self, torch_dtype, shape):
+        """A torch tensor on the gathering rank that ALIASES the gathered buffer (no copy; valid until close())."""
+        import torch
+
+        if self.rank != self.dst:
+            raise RuntimeError("only the gathering rank owns the buffer")
+        typestr = {torch.float64: "<f8", torch.float32: "<f4"}[torch_dtype]
+
+        class _Alias:  # the CUDA array interface of the library-owned allocation
+            __cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(self.base), False),
+                                        "version": 2}
+
+        return torch.as_tensor(_Alias(), device=torch.device("cuda", self.device))
 
     def read(self, first_row: int, nrows: int, dtype=np.float64) -> np.ndarray:
         """Copy rows of the gathered buffer to the host (dst rank only)."""

@@ -199,7 +199,35 @@ int fastcheb_reinterp(fastcheb_poly** out, const fastcheb_poly* p, const int64_t
 int fastcheb_vandermonde(int ndim, const int64_t* dims, int dtype, const void* pts, int64_t m, const double* lb,
                          const double* ub, void* A, int64_t lda, int mem, int device, void* stream);
 
-/* ---- multi-GPU: fused evaluation + gather over NVLink ---------------------------------------------
+/* ---- multi-GPU from ONE host process --------------------------------------------------------------
+ * What `c.(ys)` on a multi-GPU node needs (the reference's user broadcasts in one process: eval.jl:63-70,
+ * FastChebInterp.jl:37): a fastcheb_multi replicates the polynomial on `ngpus` devices of the node
+ * (devices == NULL: 0..ngpus-1; coefficients uploaded from the host pointer once per device, or — coefs_mem ==
+ * FASTCHEB_MEM_DEVICE, coefficients on devices[0] — copied peer to peer over NVLink) and every batch is
+ * block-partitioned over them: one worker thread and one stream per device, results written straight into the caller's
+ * single array.  mem == FASTCHEB_MEM_HOST: host arrays (each device stages its block).  mem == FASTCHEB_MEM_DEVICE:
+ * points and results live on devices[0]; the other devices' kernels load their block of points from, and store their
+ * results into, devices[0]'s HBM through peer access (fused evaluation + gather over NVLink/NVSwitch; staged peer
+ * copies when peer access is unavailable).  Status and errors are those of the single-GPU calls; EDOMAIN reports the
+ * first offending GLOBAL point index (the minimum over the devices).  Calls on one handle are serialised. */
+typedef struct fastcheb_multi fastcheb_multi;
+int fastcheb_multi_create(fastcheb_multi** out, int ngpus, const int* devices, int ndim, const int64_t* dims, int dtype,
+                          int is_complex, int ncomp, const void* coefs, int coefs_mem, const double* lb, const double* ub);
+int fastcheb_multi_destroy(fastcheb_multi* m); /* NULL is a no-op */
+int fastcheb_multi_ngpus(const fastcheb_multi* m);
+int fastcheb_multi_device(const fastcheb_multi* m, int i);               /* CUDA device of replica i */
+const fastcheb_poly* fastcheb_multi_poly(const fastcheb_multi* m, int i); /* replica i (queries, fastcheb_set_algo) */
+/* c.(ys), chebjacobian.(Ref(c), ys), chebgradient.(Ref(c), ys) and the tuple layout — as the single-GPU entry points */
+int fastcheb_multi_eval(fastcheb_multi* m, const void* pts, int64_t npts, void* out, int mem);
+int fastcheb_multi_eval_jac(fastcheb_multi* m, const void* pts, int64_t npts, void* out_v, void* out_J, int mem);
+int fastcheb_multi_eval_grad(fastcheb_multi* m, const void* pts, int64_t npts, void* out_v, void* out_g, int mem);
+int fastcheb_multi_eval_jac_tuple(fastcheb_multi* m, const void* pts, int64_t npts, void* out_vJ, int mem);
+/* fastcheb_fit for a batch of `howmany` independent fits, block-partitioned by fit over the devices (a single fit is
+ * never split: interp.jl:39-57 per array).  MEM_DEVICE: vals / coefs / maxabs live on devices[0]. */
+int fastcheb_multi_fit(int ngpus, const int* devices, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
+                       int64_t howmany, const void* vals, void* coefs, double* maxabs, int mem);
+
+/* ---- multi-GPU, one process per GPU: fused evaluation + gather over NVLink ---------------------------
  * One process per GPU.  The reference has no counterpart (it has no parallelism at all); these
  * entry points exist so that `c.(ys)` sharded over the GPUs of a node returns ONE result array: the gathering
  * rank allocates the buffer (peer_alloc) and ships the 64-byte IPC handle; the other ranks map it (peer_open) and

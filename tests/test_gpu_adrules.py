@@ -31,7 +31,9 @@ def test_vjp_jvp_match_oracle_jacobian(fc, orc, dims, K, cplx):
     want_xbar = np.real(np.einsum("pkn,pk->pn", np.conj(J0), dy))
     want_ydot = np.einsum("pkn,pn->pk", J0, dx)
     p = fc.ChebPoly(c, lb, ub)
-    tol = 16 * EPS * np.abs(c).sum() * max(1, max(n - 1 for n in dims) ** 2) * (2 / (ub - lb)).max()
+    from parity_util import jac_tol
+    # contractions of the Jacobian: the value bound plus the per-column differentiated-series bounds
+    tol = 16 * EPS * np.abs(c).sum() + sum(jac_tol(c, N, d, lb, ub) for d in range(N))
     algos = [fc.ALGO_CLENSHAW] + ([fc.ALGO_DMMA] if (N >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8) else [])
     for algo in algos:
         p.set_algo(algo)

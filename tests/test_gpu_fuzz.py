@@ -5,6 +5,8 @@ picks (Clenshaw, ring DMMA, resident 2-D DMMA) must be within 16 eps sum|c| (val
 import numpy as np
 import pytest
 
+from parity_util import jac_tol
+
 pytestmark = pytest.mark.gpu
 
 
@@ -53,7 +55,7 @@ def test_random_shapes(fc, orc, seed):
         v, J = fc.chebjacobian(poly, pts)
         assert np.abs(v - v0).max() <= tol, tag
         for d, n in enumerate(dims):
-            told = tol * max(1, (n - 1) ** 2) * 2 / (ub[d] - lb[d])
+            told = jac_tol(c, len(dims), d, lb, ub, dt)
             assert np.abs(J[:, :, d] - J0[:, :, d]).max() <= told, (tag, d)
         if N >= 2 and dims[0] >= 5 and np.prod(dims[1:]) >= 8 and N <= 4:
             poly.set_algo(fc.ALGO_DMMA, dt)       # forced tensor-core path on shapes AUTO would leave to Clenshaw
@@ -61,7 +63,7 @@ def test_random_shapes(fc, orc, seed):
             v, J = fc.chebjacobian(poly, pts)
             assert np.abs(v - v0).max() <= tol, tag
             for d, n in enumerate(dims):
-                told = tol * max(1, (n - 1) ** 2) * 2 / (ub[d] - lb[d])
+                told = jac_tol(c, len(dims), d, lb, ub, dt)
                 assert np.abs(J[:, :, d] - J0[:, :, d]).max() <= told, (tag, d)
         poly.close()
 
