@@ -36,7 +36,7 @@ import ctypes
 import numpy as np
 
 from . import _capi
-from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA, ALGO_DMMA_RING  # noqa: F401
+from ._capi import ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA, ALGO_DMMA_RING, ALGO_PRODUCT  # noqa: F401
 
 __all__ = ["MultiChebPoly", "chebcoefs_multi", "rrule", "frule", "chebregression", "chebvandermonde", "eval_many", "ChebPoly", "chebinterp", "chebinterp_v1", "chebjacobian", "chebgradient", "chebpoints", "chebcoefs",
            "droptol", "roots", "colleague_matrix", "ArgumentError", "DomainError", "DimensionMismatch", "CudaError"]
@@ -179,6 +179,14 @@ class ChebPoly:
 
     def get_algo(self, jac: bool = False, rdt=np.float64) -> int:
         return int(_capi.lib().fastcheb_get_algo(self._handle(rdt), int(jac)))
+
+    def product_check(self, rdt=np.float64):
+        """Self-check of the 1-D product-basis path against the Clenshaw kernel (fastcheb_product_check): worst value
+        difference over 16 eps sum|c| and worst derivative difference over 16 eps sum|c_k| k^2 2/(ub-lb); AUTO uses the
+        path when they are <= 0.25."""
+        dv, dj = ctypes.c_double(0), ctypes.c_double(0)
+        _check(_capi.lib().fastcheb_product_check(self._handle(rdt), ctypes.byref(dv), ctypes.byref(dj)), "fastcheb_product_check: ")
+        return dv.value, dj.value
 
     def close(self):
         for h in self._handles.values():

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libfastcheb_cuda.so")
 F32, F64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 OK, EDOMAIN, ENONFINITE, EDIMMISMATCH, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = range(8)
-ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA, ALGO_DMMA_RING = 0, 1, 2, 3
+ALGO_AUTO, ALGO_CLENSHAW, ALGO_DMMA, ALGO_DMMA_RING, ALGO_PRODUCT = 0, 1, 2, 3, 4
 MAX_NDIM = 6
 
 # every symbol include/fastcheb.h declares (tests check the library exports all of them)
@@ -23,7 +23,7 @@ SYMBOLS = [
     "fastcheb_version", "fastcheb_launch_count", "fastcheb_device_count", "fastcheb_last_error", "fastcheb_error_index",
     "fastcheb_create", "fastcheb_destroy", "fastcheb_ndim", "fastcheb_dims", "fastcheb_dtype",
     "fastcheb_is_complex", "fastcheb_ncomp", "fastcheb_device", "fastcheb_get_coefs", "fastcheb_set_algo",
-    "fastcheb_get_algo", "fastcheb_eval", "fastcheb_eval_jac", "fastcheb_eval_grad", "fastcheb_eval_jac_tuple",
+    "fastcheb_get_algo", "fastcheb_product_check", "fastcheb_eval", "fastcheb_eval_jac", "fastcheb_eval_grad", "fastcheb_eval_jac_tuple",
     "fastcheb_eval_async", "fastcheb_eval_jac_async", "fastcheb_eval_many", "fastcheb_eval_vjp", "fastcheb_eval_jvp", "fastcheb_fit", "fastcheb_fit_async", "fastcheb_droptol_shape", "fastcheb_interp", "fastcheb_reinterp", "fastcheb_vandermonde",
     "fastcheb_multi_create", "fastcheb_multi_destroy", "fastcheb_multi_ngpus", "fastcheb_multi_device", "fastcheb_multi_poly",
     "fastcheb_multi_eval", "fastcheb_multi_eval_jac", "fastcheb_multi_eval_grad", "fastcheb_multi_eval_jac_tuple", "fastcheb_multi_fit",
@@ -61,6 +61,7 @@ def lib() -> ctypes.CDLL:
         "fastcheb_get_coefs": (i32, [vp, vp, i32]),
         "fastcheb_set_algo": (i32, [vp, i32]),
         "fastcheb_get_algo": (i32, [vp, i32]),
+        "fastcheb_product_check": (i32, [vp, dblp, dblp]),
         "fastcheb_eval": (i32, [vp, vp, i64, vp, i32, vp]),
         "fastcheb_eval_jac": (i32, [vp, vp, i64, vp, vp, i32, vp]),
         "fastcheb_eval_grad": (i32, [vp, vp, i64, vp, vp, i32, vp]),

@@ -1,0 +1,247 @@
+// Host side of the 1-D product-basis evaluation path (eval_pb1d.cuh): coefficient rewrite, plan-time self-check,
+// launch.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "eval_pb1d.cuh"
+#include "poly.h"
+
+namespace fastcheb {
+namespace {
+
+template <typename R, int AMAX, int EC, int P, bool JAC>
+cudaError_t launch_p(const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
+  auto kern = eval_pb1d_kernel<R, AMAX, EC, P, JAC>;
+  constexpr int CAP = pb_cap(AMAX, EC);
+  if (d_count > (size_t)CAP) return cudaErrorInvalidValue;
+  Pb1dArgs<R, CAP> args;
+  args.p = prm;
+  memcpy(args.D, h_D, d_count * sizeof(R));
+  int threads = 256;
+  if (const char* t = getenv("FASTCHEB_PB_THREADS")) {
+    const int v = atoi(t);
+    if (v >= 32 && v <= 256 && v % 32 == 0) threads = v;
+  }
+  const long long per_sm = (prm.npts + (long long)sms * P - 1) / ((long long)sms * P);
+  if (per_sm < threads) threads = (int)std::max<long long>(32, (per_sm + 31) / 32 * 32);
+  int bps = 1;
+  cudaError_t e = cached_occupancy(&bps, reinterpret_cast<const void*>(kern), threads, 0);
+  if (e != cudaSuccess) return e;
+  const long long tile = (long long)threads * P;
+  const long long ntiles = (prm.npts + tile - 1) / tile;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)sms * std::max(1, bps)));
+  kern<<<grid, threads, 0, st>>>(args);
+  note_launch();
+  return cudaGetLastError();
+}
+
+template <typename R, int AMAX, int EC, bool JAC>
+cudaError_t launch(const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
+  // points per thread: the T_a(w) tables are AMAX (2 AMAX with derivatives) registers per point
+  constexpr int P = JAC ? (AMAX == 8 ? 2 : 1) : (AMAX == 8 ? 4 : 2);
+  if constexpr (P > 1 && EC == 1) {
+    static const int forced = [] {  // experiments: FASTCHEB_PB_P=1 runs one point per thread
+      const char* t = getenv("FASTCHEB_PB_P");
+      return t ? atoi(t) : 0;
+    }();
+    if (forced == 1) return launch_p<R, AMAX, EC, 1, JAC>(prm, h_D, d_count, sms, st);
+  }
+  return launch_p<R, AMAX, EC, P, JAC>(prm, h_D, d_count, sms, st);
+}
+
+template <typename R, int AMAX, bool JAC>
+cudaError_t launch_ec(int ec, const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
+  switch (ec) {
+    case 1: return launch<R, AMAX, 1, JAC>(prm, h_D, d_count, sms, st);
+    case 2: return launch<R, AMAX, 2, JAC>(prm, h_D, d_count, sms, st);
+    case 3: return launch<R, AMAX, 3, JAC>(prm, h_D, d_count, sms, st);
+    case 4: return launch<R, AMAX, 4, JAC>(prm, h_D, d_count, sms, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename R>
+cudaError_t launch_any(int amax, int ec, bool jac, const Pb1dParams& prm, const void* h_D, size_t d_count, int sms,
+                       cudaStream_t st) {
+  if (amax == 8)
+    return jac ? launch_ec<R, 8, true>(ec, prm, h_D, d_count, sms, st) : launch_ec<R, 8, false>(ec, prm, h_D, d_count, sms, st);
+  if (amax == 16)
+    return jac ? launch_ec<R, 16, true>(ec, prm, h_D, d_count, sms, st) : launch_ec<R, 16, false>(ec, prm, h_D, d_count, sms, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+bool pb1d_shape_ok(const fastcheb_poly* p) {
+  return p->ndim == 1 && p->dims[0] >= kPbMinN && p->dims[0] <= kPbMaxN && p->E <= 4;
+}
+
+int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
+              const void* tan) {
+  const PbPlan& pb = p->pb;
+  Pb1dParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.pts = pts;
+  prm.out_v = out_v;
+  prm.out_J = out_J;
+  prm.bad = bad_dev;
+  prm.npts = npts;
+  prm.idx_base = idx_base;
+  prm.v_stride = v_stride;
+  prm.J_stride = J_stride;
+  prm.e0 = 0;
+  prm.Etot = p->E;
+  prm.M = pb.M;
+  prm.lb = p->lb[0];
+  prm.ub = p->ub[0];
+  prm.tan = tan;
+  prm.mode = mode;
+  const size_t d_count = pb.h_D.size() / real_size(p->dtype);
+  const cudaError_t e = p->dtype == FASTCHEB_F64
+                            ? launch_any<double>(pb.AMAX, p->E, jac, prm, pb.h_D.data(), d_count, p->di->sms, st)
+                            : launch_any<float>(pb.AMAX, p->E, jac, prm, pb.h_D.data(), d_count, p->di->sms, st);
+  if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "product-basis kernel launch failed: %s", cudaGetErrorString(e));
+  return FASTCHEB_OK;
+}
+
+// Build the product-basis coefficients (and, unless `forced`, run the self-check that lets AUTO use them).
+// Thread-safe and idempotent; the handle's observable state (coefficients, box) never changes.
+int pb1d_plan(const fastcheb_poly* cp, bool forced) {
+  fastcheb_poly* p = const_cast<fastcheb_poly*>(cp);
+  PbPlan& pb = p->pb;
+  std::lock_guard<std::mutex> lk(pb.mu);
+  if (pb.state.load() != kPbNone && (pb.checked || forced)) return FASTCHEB_OK;
+  if (!pb1d_shape_ok(p)) {
+    pb.state.store(kPbRejected);
+    pb.checked = true;
+    return FASTCHEB_OK;
+  }
+  DeviceGuard dg(p->device);
+  const int n = (int)p->dims[0], E = p->E;
+  const size_t rs = real_size(p->dtype);
+  cudaStream_t st = cudaStreamPerThread;
+  if (pb.h_D.empty()) {
+    int A = n <= 128 ? 8 : 16;
+    if (const char* t = getenv("FASTCHEB_PB_A")) {  // experiments: force the table size
+      const int v = atoi(t);
+      if (v == 8 || v == 16) A = v;
+    }
+    const int M = (n + A - 1) / A;
+    std::vector<unsigned char> raw((size_t)n * E * rs);
+    FC_CUDA(cudaMemcpyAsync(raw.data(), p->d_coefs, raw.size(), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(cudaStreamSynchronize(st));
+    auto coef = [&](int k, int e) -> long double {
+      if (k >= n) return 0.0L;
+      return p->dtype == FASTCHEB_F64 ? (long double)((const double*)raw.data())[(size_t)k * E + e]
+                                      : (long double)((const float*)raw.data())[(size_t)k * E + e];
+    };
+    std::vector<long double> D((size_t)(A + 1) * M);
+    // kernel layout (eval_pb1d.cuh): full groups of G rows interleaved [group][a][j][e] from offset 0, the M % G
+    // remaining rows [t][a][e] from the fixed offset pb_tail_base
+    const int G = pb_group(E), ngroups = M / G;
+    const size_t count = ngroups * G == M ? (size_t)M * A * E : (size_t)pb_tail_base(A, E) + (size_t)(M - ngroups * G) * A * E;
+    std::vector<unsigned char> out(count * rs, 0);
+    long double sum_abs = 0, sum_k2 = 0;
+    for (int e = 0; e < E; ++e) {
+      std::fill(D.begin(), D.end(), 0.0L);
+      for (int a = A - 1; a >= 0; --a)
+        for (int b = 0; b < M; ++b) {
+          const long double c = coef(M * a + b, e);
+          long double v;
+          if (b == 0)
+            v = c;
+          else if (a == 0)
+            v = c - 0.5L * D[(size_t)1 * M + (M - b)];
+          else
+            v = 2.0L * c - D[(size_t)(a + 1) * M + (M - b)];
+          D[(size_t)a * M + b] = v;
+        }
+      for (int b = 0; b < M; ++b)
+        for (int a = 0; a < A; ++a) {
+          const size_t o = b < ngroups * G
+                               ? (((size_t)(b / G) * A + a) * G + (size_t)(b % G)) * E + e
+                               : (size_t)pb_tail_base(A, E) + ((size_t)(b - ngroups * G) * A + a) * E + e;
+          if (p->dtype == FASTCHEB_F64)
+            ((double*)out.data())[o] = (double)D[(size_t)a * M + b];
+          else
+            ((float*)out.data())[o] = (float)D[(size_t)a * M + b];
+        }
+      for (int k = 0; k < n; ++k) {
+        sum_abs += fabsl(coef(k, e));
+        sum_k2 += fabsl(coef(k, e)) * (long double)k * (long double)k;
+      }
+    }
+    pb.h_D = out;  // the launches pass the coefficients in the kernel parameters
+    pb.AMAX = A;
+    pb.M = M;
+    pb.sum_abs = (double)sum_abs;
+    pb.sum_k2 = (double)sum_k2;
+    pb.state.store(kPbBuilt);
+  }
+  if (forced || pb.checked) return FASTCHEB_OK;
+
+  // Self-check against the bit-exact Clenshaw kernel on probe points: a uniform grid, Chebyshev-clustered points
+  // and points at distances 2^-1 .. 2^-53 of the span from both end points (where both algorithms are least accurate).
+  // AUTO uses this path only if values stay within a quarter of the north_star tolerance 16 eps sum|c| of the
+  // Clenshaw kernel (derivatives: of the differentiated-series bound 16 eps sum|c_k| k^2 * 2/(ub-lb)).
+  const int NP = 3 * 2048;
+  std::vector<double> x((size_t)NP);
+  const double lb = p->lb[0], ub = p->ub[0], span = ub - lb;
+  for (int i = 0; i < 2048; ++i) {
+    x[i] = lb + span * (double)i / 2047.0;
+    x[2048 + i] = lb + span * 0.5 * (1.0 + cos(M_PI * (i + 0.5) / 2048.0));
+    const double d = ldexp(1.0, -(1 + (52 * (i / 2)) / 1024)) * (1.0 + (i % 7) / 7.0) * 0.5;
+    x[4096 + i] = (i & 1) ? ub - span * d : lb + span * d;
+  }
+  std::vector<unsigned char> hx((size_t)NP * rs);
+  for (int i = 0; i < NP; ++i) {
+    const double xi = std::min(std::max(x[i], lb), ub);
+    if (p->dtype == FASTCHEB_F64) {
+      ((double*)hx.data())[i] = xi;
+    } else {
+      float f = (float)xi;
+      if ((double)f < lb) f = nextafterf(f, INFINITY);
+      if ((double)f > ub) f = nextafterf(f, -INFINITY);
+      ((float*)hx.data())[i] = f;
+    }
+  }
+  const size_t vb = (size_t)NP * E * rs;
+  unsigned char* dbuf = nullptr;
+  FC_CUDA(pool_alloc((void**)&dbuf, hx.size() + 4 * vb, st));
+  unsigned char *d_x = dbuf + 4 * vb, *d_v0 = dbuf, *d_J0 = dbuf + vb, *d_v1 = dbuf + 2 * vb, *d_J1 = dbuf + 3 * vb;
+  std::vector<unsigned char> h((size_t)4 * vb);
+  int rc = FASTCHEB_OK;
+  cudaError_t ce = cudaMemcpyAsync(d_x, hx.data(), hx.size(), cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) rc = eval_clenshaw_device(p, d_x, NP, d_v0, E, d_J0, E, true, nullptr, 0, st, 0, nullptr);
+  if (ce == cudaSuccess && rc == FASTCHEB_OK) rc = pb1d_eval(p, d_x, NP, d_v1, E, d_J1, E, true, nullptr, 0, st, 0, nullptr);
+  if (ce == cudaSuccess && rc == FASTCHEB_OK) ce = cudaMemcpyAsync(h.data(), dbuf, 4 * vb, cudaMemcpyDeviceToHost, st);
+  const cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFreeAsync(dbuf, st);
+  if (rc != FASTCHEB_OK) return rc;
+  if (ce != cudaSuccess || e2 != cudaSuccess)
+    return fail(FASTCHEB_ECUDA, "product-basis self-check failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : e2));
+  double dv = 0, dJ = 0;
+  auto get = [&](size_t off, size_t i) -> double {
+    return p->dtype == FASTCHEB_F64 ? ((const double*)(h.data() + off))[i] : (double)((const float*)(h.data() + off))[i];
+  };
+  bool finite = true;
+  for (size_t i = 0; i < (size_t)NP * E; ++i) {
+    const double a = fabs(get(2 * vb, i) - get(0, i)), b = fabs(get(3 * vb, i) - get(vb, i));
+    finite = finite && std::isfinite(a) && std::isfinite(b);
+    dv = std::max(dv, a);
+    dJ = std::max(dJ, b);
+  }
+  const double eps = p->dtype == FASTCHEB_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+  pb.ok_val = finite && dv <= 0.25 * 16 * eps * pb.sum_abs;
+  pb.ok_jac = finite && pb.ok_val && dJ <= 0.25 * 16 * eps * pb.sum_k2 * 2.0 / span;
+  pb.check_dv = pb.sum_abs > 0 ? dv / (16 * eps * pb.sum_abs) : 0;
+  pb.check_dJ = pb.sum_k2 > 0 ? dJ / (16 * eps * pb.sum_k2 * 2.0 / span) : 0;
+  pb.checked = true;
+  pb.state.store((pb.ok_val || pb.ok_jac) ? kPbAccepted : kPbRejected);
+  return FASTCHEB_OK;
+}
+
+}  // namespace fastcheb

@@ -1,0 +1,328 @@
+// 1-D evaluation in a PRODUCT BASIS: one FP64 multiply-add per coefficient instead of the Clenshaw recurrence's
+// multiply-add + subtract, i.e. past the 50 %-of-peak ceiling of the reference's algorithm.
+//
+// Replaces, for batches of points of a 1-D polynomial (BASELINE.json configs[0]: order 200),
+//   (c::ChebPoly{1})(x)            /root/reference/src/eval.jl:63-70 -> evaluate, eval.jl:19-31
+//   chebgradient(c, x)             eval.jl:168-177 -> Jevaluate, eval.jl:82-101 (scale :151)
+//
+// Mathematics.  With k = M a + b (0 <= b < M, 0 <= a < A, A M >= n) and w = T_M(z):
+//     T_{Ma}(z) = T_a(w),      T_{Ma}(z) T_b(z) = (T_{Ma+b}(z) + T_{|Ma-b|}(z)) / 2,
+// so the functions T_a(w) T_b(z) have the distinct degrees Ma + b: a basis of the polynomials of degree < A M.  The
+// plan (eval_pb1d.cu, long double on the host) rewrites the Chebyshev coefficients once,
+//     sum_k c_k T_k(z) = sum_b T_b(z) * ( sum_a D[a][b] T_a(w) ),
+// by the triangular recursion  D[a][0] = c_{Ma},  D[a][b] = 2 c_{Ma+b} - D[a+1][M-b]  (a >= 1),
+// D[0][b] = c_b - D[1][M-b] / 2.  A thread keeps T_0..T_{A-1}(w) of its points in registers; the inner sums are one
+// DFMA per coefficient with the coefficient broadcast from shared memory, the outer sum one DFMA per b:
+//     n + A + 3 M  FP64 operations per point instead of 2 n   (order 200, A = 16, M = 13: 263 instead of 402).
+// The gradient needs T_a'(w), T_b'(z) and w' = T_M'(z):  dv/dz = sum_b T_b' g_b + w' sum_b T_b g'_b.
+//
+// Numerics.  z is the oracle's z (same IEEE sequence, eval.jl:65); the summation order differs from Clenshaw's, so
+// results agree with the oracle within rounding, not bit for bit.  Both algorithms lose accuracy like k^2 eps next
+// to the end points; for coefficient vectors that do not decay (dense random) the two can differ there by more than
+// 16 eps sum|c| (so does the oracle from the exact value).  AUTO therefore takes this path only after a plan-time
+// self-check against the bit-exact Clenshaw kernel on probe points clustered at the end points (eval_pb1d.cu).
+#pragma once
+#include <cstdint>
+#include "ptx_util.cuh"
+
+namespace fastcheb {
+
+// rows b of D processed together (their coefficients are interleaved, see the kernel): 8 independent accumulation
+// chains per thread whatever the number of components
+__host__ __device__ constexpr int pb_group(int ec) { return ec == 1 ? 4 : (ec == 2 ? 2 : 1); }
+
+struct Pb1dParams {
+  const void* pts;  // npts reals
+  void* out_v;      // values:      out_v[p * v_stride + e0 + e]
+  void* out_J;      // derivatives: out_J[p * J_stride + e0 + e]   (mode 0)
+  long long* bad;   // first out-of-domain point index (atomicMin), may be null
+  long long npts, idx_base, v_stride, J_stride;
+  int e0, Etot, M;
+  double lb, ub;
+  // Jacobian contraction (AD rules, chainrules.jl:4-39), as in the other evaluation kernels: 0 = store J;
+  // 1 = pullback out_J[p] = sum_e J[e] tan[p*Etot + e]; 2 = pushforward out_J[p*Etot + e] = J[e] tan[p]
+  const void* tan;
+  int mode;
+};
+
+// The coefficients travel IN THE KERNEL PARAMETERS (constant bank 0; up to 18 KB of the 32 KB parameter space): every
+// multiply-add of a warp uses the same coefficient, and a constant-bank / uniform-register operand costs no
+// register-file write, whereas a broadcast LDS writes the value into all 32 lanes' registers — measured
+// (profiles/r01_micro_fp64.jsonl, lds128_dfma_p2) that return path caps DFMAs fed two per loaded double at 69 % of the
+// FP64 peak, which is where the first version of this kernel sat (63 % pipe utilisation, profiles/r02_pb1d_*).
+// Layout of D: floor(M / pb_group(EC)) groups [group][a][j][e] (b = pb_group(EC) * group + j) from offset 0, the
+// M % pb_group(EC) remaining rows [t][a][e] from pb_tail_base (a fixed offset: all offsets are compile-time).
+// M <= pb_mmax(AMAX) rows; the groups sit at compile-time offsets, the M % BU single rows after the LAST POSSIBLE group
+__host__ __device__ constexpr int pb_mmax(int amax) { return amax == 8 ? 16 : 32; }
+__host__ __device__ constexpr int pb_tail_base(int amax, int ec) { return pb_mmax(amax) * amax * ec; }
+__host__ __device__ constexpr int pb_cap(int amax, int ec) { return (pb_mmax(amax) + pb_group(ec) - 1) * amax * ec; }
+
+template <typename R, int CAP>
+struct Pb1dArgs {
+  Pb1dParams p;
+  R D[CAP];
+};
+
+template <typename R, int AMAX, int EC, int P, bool JAC>
+__global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant__ Pb1dArgs<R, pb_cap(AMAX, EC)> args) {
+  const Pb1dParams& prm = args.p;
+  const R* Ds = args.D;
+  const int M = prm.M;
+  const R* __restrict__ pts = reinterpret_cast<const R*>(prm.pts);
+  R* __restrict__ out_v = reinterpret_cast<R*>(prm.out_v);
+  R* __restrict__ out_J = reinterpret_cast<R*>(prm.out_J);
+  const R lb = (R)prm.lb, ub = (R)prm.ub;
+  SpanDiv<R> sdiv;
+  sdiv.init(lb, ub);
+  const long long tile_pts = (long long)blockDim.x * P;
+  const long long ntiles = (prm.npts + tile_pts - 1) / tile_pts;
+  // the coordinates of the next tile are loaded while the current one is computed (a tile is ~1000 pipe cycles per
+  // warp; an unprefetched global load at its head leaves the FP64 pipe idle for a quarter of the time)
+  R xn[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const long long i = (long long)blockIdx.x * tile_pts + (long long)p * blockDim.x + threadIdx.x;
+    xn[p] = i < prm.npts ? pts[i] : lb;
+  }
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long idx[P];
+    bool live[P];
+    R z[P], w[P];
+    [[maybe_unused]] R dw[P];
+    long long first_bad = 0x7fffffffffffffffLL;
+    R xc[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      xc[p] = xn[p];
+      const long long i = (tile + gridDim.x) * tile_pts + (long long)p * blockDim.x + threadIdx.x;
+      xn[p] = i < prm.npts ? pts[i] : lb;
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      idx[p] = tile * tile_pts + (long long)p * blockDim.x + threadIdx.x;
+      live[p] = idx[p] < prm.npts;
+      const R x = xc[p];
+      const bool ok = (lb <= x) && (x <= ub);                                 // eval.jl:64 (closed box, NaN fails)
+      z[p] = ok ? rsub(sdiv.div(rmul(rsub(x, lb), R(2))), R(1)) : R(0);       // eval.jl:65, the oracle's operation order
+      if (live[p] && !ok) {
+        live[p] = false;
+        if (idx[p] < first_bad) first_bad = idx[p];
+      }
+    }
+    if (first_bad != 0x7fffffffffffffffLL && prm.bad) atomicMin(prm.bad, first_bad + prm.idx_base);
+
+    // w = T_M(z), w' = T_M'(z): the points' recurrences advance together (independent chains interleave).  (Doubling
+    // formulas T_{2m} = 2 T_m^2 - 1 would cut the dependency depth to log2 M but measured less accurate — they failed
+    // the 16 eps sum|c| check on the order-200 README polynomial — and no faster.)
+    {
+      R z2[P], tkm[P], tk[P];
+      [[maybe_unused]] R dkm[P], dk[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        z2[p] = rmul(R(2), z[p]);
+        tkm[p] = R(1);
+        tk[p] = z[p];
+        if constexpr (JAC) {
+          dkm[p] = R(0);
+          dk[p] = R(1);
+        }
+      }
+      for (int k = 1; k < M; ++k) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const R tn = rfma(z2[p], tk[p], -tkm[p]);
+          if constexpr (JAC) {
+            const R dn = rsub(rfma(z2[p], dk[p], rmul(R(2), tk[p])), dkm[p]);
+            dkm[p] = dk[p];
+            dk[p] = dn;
+          }
+          tkm[p] = tk[p];
+          tk[p] = tn;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        w[p] = tk[p];
+        if constexpr (JAC) dw[p] = dk[p];
+      }
+    }
+    // T_a(w) (and T_a'(w)) of every point, in registers
+    R Ta[P][AMAX];
+    [[maybe_unused]] R dTa[JAC ? P : 1][JAC ? AMAX : 1];
+    {
+      R w2[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        w2[p] = rmul(R(2), w[p]);
+        Ta[p][0] = R(1);
+        Ta[p][1] = w[p];
+        if constexpr (JAC) {
+          dTa[p][0] = R(0);
+          dTa[p][1] = R(1);
+        }
+      }
+#pragma unroll
+      for (int a = 2; a < AMAX; ++a)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          Ta[p][a] = rfma(w2[p], Ta[p][a - 1], -Ta[p][a - 2]);
+          if constexpr (JAC) dTa[p][a] = rsub(rfma(w2[p], dTa[p][a - 1], rmul(R(2), Ta[p][a - 1])), dTa[p][a - 2]);
+        }
+    }
+
+    // sums over b, two interleaved accumulators each (even / odd rows) so that consecutive rows do not chain
+    R v[2][P][EC];
+    [[maybe_unused]] R dv1[2][JAC ? P : 1][EC], dv2[2][JAC ? P : 1][EC];  // sum_b T_b' g_b and sum_b T_b g'_b
+    R tbm[P], tb[P], z2[P];                                                // T_{b-1}(z), T_b(z)
+    [[maybe_unused]] R dbm[JAC ? P : 1], db[JAC ? P : 1];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+      for (int e = 0; e < EC; ++e) {
+        v[0][p][e] = v[1][p][e] = R(0);
+        if constexpr (JAC) dv1[0][p][e] = dv1[1][p][e] = dv2[0][p][e] = dv2[1][p][e] = R(0);
+      }
+      z2[p] = rmul(R(2), z[p]);
+      tbm[p] = z[p];  // T_{-1} = T_1: the recurrence T_{b+1} = 2 z T_b - T_{b-1} then also yields T_1 from T_0
+      tb[p] = R(1);
+      if constexpr (JAC) {
+        dbm[p] = R(1);  // T_{-1}' = T_1' = 1: the derivative recurrence T_{b+1}' = 2 T_b + 2 z T_b' - T_{b-1}' then gives
+        db[p] = R(0);   // T_1' = 2 - 1 = 1 from T_0' = 0
+      }
+    }
+    // T_b(z), T_b'(z) of the next row: taken BEFORE the row's contraction, so the recurrence step overlaps it
+    auto next_tb = [&](R (&t)[P], [[maybe_unused]] R (&d)[JAC ? P : 1]) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        t[p] = tb[p];
+        const R tn = rfma(z2[p], tb[p], -tbm[p]);
+        if constexpr (JAC) {
+          d[p] = db[p];
+          const R dn = rsub(rfma(z2[p], db[p], rmul(R(2), tb[p])), dbm[p]);
+          dbm[p] = db[p];
+          db[p] = dn;
+        }
+        tbm[p] = tb[p];
+        tb[p] = tn;
+      }
+    };
+    // fold g (and g') of one row into the sums
+    auto fold = [&](int par, const R (&t)[P], [[maybe_unused]] const R (&d)[JAC ? P : 1], const R (&g)[P][EC],
+                    [[maybe_unused]] const R (&gd)[JAC ? P : 1][EC]) {
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+          v[par][p][e] = rfma(t[p], g[p][e], v[par][p][e]);
+          if constexpr (JAC) {
+            dv1[par][p][e] = rfma(d[p], g[p][e], dv1[par][p][e]);
+            dv2[par][p][e] = rfma(t[p], gd[p][e], dv2[par][p][e]);
+          }
+        }
+    };
+    constexpr int BU = pb_group(EC), MAXG = pb_mmax(AMAX) / BU;
+    const int ngroups = M / BU;
+    // the group loop is unrolled completely (with a uniform exit), so that every coefficient is a constant-bank
+    // operand at a compile-time offset
+#pragma unroll
+    for (int gi = 0; gi < MAXG; ++gi) {
+      if (gi >= ngroups) break;
+      const R* Dg = Ds + gi * BU * AMAX * EC;
+      R g[BU][P][EC];
+      [[maybe_unused]] R gd[BU][JAC ? P : 1][EC];
+      R tbv[BU][P];
+      [[maybe_unused]] R dbv[BU][JAC ? P : 1];
+#pragma unroll
+      for (int j = 0; j < BU; ++j) next_tb(tbv[j], dbv[j]);
+#pragma unroll
+      for (int j = 0; j < BU; ++j)
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+          for (int e = 0; e < EC; ++e) {
+            g[j][p][e] = Dg[j * EC + e];  // a = 0: T_0(w) = 1, T_0'(w) = 0
+            if constexpr (JAC) gd[j][p][e] = R(0);
+          }
+#pragma unroll
+      for (int a = 1; a < AMAX; ++a) {
+#pragma unroll
+        for (int j = 0; j < BU; ++j)
+#pragma unroll
+          for (int e = 0; e < EC; ++e) {
+            const R d = Dg[(a * BU + j) * EC + e];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              g[j][p][e] = rfma(d, Ta[p][a], g[j][p][e]);
+              if constexpr (JAC) gd[j][p][e] = rfma(d, dTa[p][a], gd[j][p][e]);
+            }
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < BU; ++j) fold((gi * BU + j) & 1, tbv[j], dbv[j], g[j], gd[j]);
+    }
+    // the M % BU remaining rows, one at a time ([t][a][e] at pb_tail_base)
+    if constexpr (BU > 1) {
+      const int ntail = M - ngroups * BU;
+#pragma unroll
+      for (int t = 0; t < BU - 1; ++t) {
+        if (t >= ntail) break;
+        const R* Dt = Ds + pb_tail_base(AMAX, EC) + t * AMAX * EC;
+        R g[P][EC];
+        [[maybe_unused]] R gd[JAC ? P : 1][EC];
+        R tbt[P];
+        [[maybe_unused]] R dbt[JAC ? P : 1];
+        next_tb(tbt, dbt);
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+          for (int e = 0; e < EC; ++e) {
+            g[p][e] = Dt[e];
+            if constexpr (JAC) gd[p][e] = R(0);
+          }
+#pragma unroll
+        for (int a = 1; a < AMAX; ++a) {
+#pragma unroll
+          for (int e = 0; e < EC; ++e) {
+            const R d = Dt[a * EC + e];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              g[p][e] = rfma(d, Ta[p][a], g[p][e]);
+              if constexpr (JAC) gd[p][e] = rfma(d, dTa[p][a], gd[p][e]);
+            }
+          }
+        }
+        fold(t & 1, tbt, dbt, g, gd);
+      }
+    }
+
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      if (!live[p]) continue;
+#pragma unroll
+      for (int e = 0; e < EC; ++e) out_v[idx[p] * prm.v_stride + prm.e0 + e] = v[0][p][e] + v[1][p][e];
+      if constexpr (JAC) {
+        const R span = sdiv.span;
+        R Js[EC];
+#pragma unroll
+        for (int e = 0; e < EC; ++e)
+          Js[e] = rdiv(rmul(rfma(dw[p], dv2[0][p][e] + dv2[1][p][e], dv1[0][p][e] + dv1[1][p][e]), R(2)), span);  // eval.jl:151
+        if (prm.mode == 0) {
+#pragma unroll
+          for (int e = 0; e < EC; ++e) out_J[idx[p] * prm.J_stride + prm.e0 + e] = Js[e];
+        } else if (prm.mode == 1) {  // pullback: real(J' dy), chainrules.jl:7,14
+          const R* dy = reinterpret_cast<const R*>(prm.tan) + idx[p] * prm.Etot + prm.e0;
+          R acc = R(0);
+#pragma unroll
+          for (int e = 0; e < EC; ++e) acc = rfma(Js[e], dy[e], acc);
+          out_J[idx[p]] = acc;
+        } else {  // pushforward: J dx, chainrules.jl:24
+          const R dx = reinterpret_cast<const R*>(prm.tan)[idx[p]];
+#pragma unroll
+          for (int e = 0; e < EC; ++e) out_J[idx[p] * prm.Etot + prm.e0 + e] = rmul(Js[e], dx);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace fastcheb

@@ -1,6 +1,11 @@
 #include "host_util.h"
 #include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
+#include <thread>
 
 namespace fastcheb {
 
@@ -162,6 +167,167 @@ void ws_release(int dev, void* p) {
       }
   }
   if (to_free) cudaFree(to_free);
+}
+
+namespace {
+std::map<int, std::vector<StreamPair>> g_idle_streams;
+struct PinBuf {
+  void* p;
+  size_t bytes;
+  bool busy;
+};
+std::vector<PinBuf> g_pin;
+
+// a tiny persistent pool for par_memcpy; never destroyed (threads are detached: no static-destruction order issues)
+struct CopyPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::function<void()>> q;
+  int nthreads = 0;
+  void start() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    nthreads = (int)std::min<unsigned>(3, hw > 1 ? hw - 1 : 0);
+    for (int i = 0; i < nthreads; ++i)
+      std::thread([this] {
+        for (;;) {
+          std::function<void()> job;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [this] { return !q.empty(); });
+            job = std::move(q.front());
+            q.pop_front();
+          }
+          job();
+        }
+      }).detach();
+  }
+};
+CopyPool* copy_pool() {
+  static CopyPool* pool = [] {
+    CopyPool* p = new CopyPool();
+    p->start();
+    return p;
+  }();
+  return pool;
+}
+}  // namespace
+
+int streams_acquire(int dev, StreamPair* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto& v = g_idle_streams[dev];
+    if (!v.empty()) {
+      *out = v.back();
+      v.pop_back();
+      return FASTCHEB_OK;
+    }
+  }
+  StreamPair sp;
+  sp.dev = dev;
+  for (int i = 0; i < 2; ++i)
+    if (cudaStreamCreateWithFlags(&sp.s[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sp.ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      for (int j = 0; j < 2; ++j) {
+        if (sp.s[j]) cudaStreamDestroy(sp.s[j]);
+        if (sp.ev[j]) cudaEventDestroy(sp.ev[j]);
+      }
+      return fail(FASTCHEB_ECUDA, "cudaStreamCreate failed");
+    }
+  *out = sp;
+  return FASTCHEB_OK;
+}
+
+void streams_release(const StreamPair& sp) {
+  if (sp.dev < 0) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_idle_streams[sp.dev].push_back(sp);
+}
+
+void* pin_acquire(size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pin.size(); ++i)
+      if (!g_pin[i].busy && g_pin[i].bytes >= bytes && (best < 0 || g_pin[i].bytes < g_pin[best].bytes)) best = i;
+    if (best >= 0) {
+      g_pin[best].busy = true;
+      return g_pin[best].p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_pin.push_back({p, bytes, true});
+  return p;
+}
+
+void pin_release(void* p) {
+  if (!p) return;
+  void* to_free = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int idle = 0;
+    for (auto& b : g_pin) idle += !b.busy;
+    for (size_t i = 0; i < g_pin.size(); ++i)
+      if (g_pin[i].p == p) {
+        if (idle >= 8) {  // keep at most 8 idle staging buffers
+          to_free = p;
+          g_pin.erase(g_pin.begin() + i);
+        } else {
+          g_pin[i].busy = false;
+        }
+        break;
+      }
+  }
+  if (to_free) cudaFreeHost(to_free);
+}
+
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void par_memcpy(void* dst, const void* src, size_t bytes) {
+  CopyPool* pool = bytes >= (size_t(4) << 20) ? copy_pool() : nullptr;
+  const int parts = pool ? pool->nthreads + 1 : 1;
+  if (parts <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t slice = ((bytes / parts) + 4095) & ~size_t(4095);
+  std::mutex mu;
+  std::condition_variable cv;
+  int left = 0;
+  for (int i = 1; i < parts; ++i) {
+    const size_t off = slice * i;
+    if (off >= bytes) break;
+    const size_t len = std::min(slice, bytes - off);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      ++left;
+    }
+    {
+      std::lock_guard<std::mutex> lk(pool->mu);
+      pool->q.push_back([=, &mu, &cv, &left] {
+        memcpy((char*)dst + off, (const char*)src + off, len);
+        std::lock_guard<std::mutex> lk2(mu);
+        if (--left == 0) cv.notify_all();
+      });
+    }
+    pool->cv.notify_one();
+  }
+  memcpy(dst, src, std::min(slice, bytes));
+  std::unique_lock<std::mutex> lk(mu);
+  cv.wait(lk, [&] { return left == 0; });
 }
 
 int flag_acquire(int dev, FlagSlot* out) {

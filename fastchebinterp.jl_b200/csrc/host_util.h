@@ -65,6 +65,26 @@ void ws_release(int dev, void* p);
 cudaError_t pool_alloc(void** p, size_t bytes, cudaStream_t st);
 void pool_free_all(void* const* ptrs, int n);
 
+// Host-staged calls (caller buffers in host memory) that are cut into chunks run on a cached pair of non-blocking streams
+// with one event each, instead of creating and destroying streams per call.
+struct StreamPair {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  int dev = -1;
+};
+int streams_acquire(int dev, StreamPair* out);
+void streams_release(const StreamPair& sp);
+
+// grow-only cache of PINNED host staging buffers: pageable caller memory (a Julia Vector, a numpy array) is copied
+// through them by the calling thread so that the DMA transfers stay asynchronous and overlap the kernels.
+void* pin_acquire(size_t bytes);
+void pin_release(void* p);
+// true when `p` is page-locked (cudaHostAlloc / cudaHostRegister) or managed memory, i.e. cudaMemcpyAsync from / to it
+// does not block the host
+bool is_pinned_host(const void* p);
+// memcpy split over a small persistent pool of host threads (large pageable <-> pinned staging copies)
+void par_memcpy(void* dst, const void* src, size_t bytes);
+
 // one int64 device flag (+ pinned host mirror) per in-flight synchronous call
 struct FlagSlot {
   long long* dev = nullptr;

@@ -172,9 +172,23 @@ int eval_clenshaw(const fastcheb_poly* p, const void* pts, int64_t npts, void* o
   return FASTCHEB_OK;
 }
 
+// 1-D product basis: forced by fastcheb_set_algo, or (AUTO) accepted by the plan-time self-check; the plan is built on
+// the first batch of at least kPbMinBatch points
+bool use_pb(const fastcheb_poly* p, bool jac, int64_t npts) {
+  const int algo = p->algo.load();
+  if (algo == FASTCHEB_ALGO_PRODUCT) return p->pb.state.load() != kPbNone && p->pb.state.load() != kPbRejected;
+  if (algo != FASTCHEB_ALGO_AUTO || !pb1d_shape_ok(p)) return false;
+  int st = p->pb.state.load();
+  if ((st == kPbNone || st == kPbBuilt) && npts >= kPbMinBatch) {
+    if (pb1d_plan(p, false) != FASTCHEB_OK) return false;
+    st = p->pb.state.load();
+  }
+  return st == kPbAccepted && (jac ? p->pb.ok_jac : p->pb.ok_val);
+}
+
 bool use_dmma(const fastcheb_poly* p, bool jac) {
   if (!p->dmma.ok) return false;
-  if (p->algo == FASTCHEB_ALGO_CLENSHAW) return false;
+  if (p->algo == FASTCHEB_ALGO_CLENSHAW || p->algo == FASTCHEB_ALGO_PRODUCT) return false;
   (void)jac;
   if (p->algo == FASTCHEB_ALGO_AUTO) {
     // Measured on B200 (tools/bench_configs.py with BENCH_SHAPES): the MMA K extent is padded to 4 KS = 16, 32 or 64
@@ -191,10 +205,18 @@ bool use_dmma(const fastcheb_poly* p, bool jac) {
 
 namespace fastcheb {
 
+int eval_clenshaw_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+                         int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
+                         const void* tan) {
+  return eval_clenshaw(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
+}
+
 int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
                 int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
                 const void* tan) {
   if (npts == 0) return FASTCHEB_OK;
+  if (use_pb(p, jac, npts))
+    return pb1d_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
   if (use_dmma(p, jac))
     return dmma_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
   return eval_clenshaw(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
@@ -340,16 +362,32 @@ int fastcheb_set_algo(fastcheb_poly* p, int algo) {
   if (!p) return fail(FASTCHEB_EINVAL, "null handle");
   if ((algo == FASTCHEB_ALGO_DMMA || algo == FASTCHEB_ALGO_DMMA_RING) && !p->dmma.ok)
     return fail(FASTCHEB_EUNSUPPORTED, "the DMMA path needs ndim >= 2, n1 >= 5 and at least 8 coefficient columns");
-  if (algo != FASTCHEB_ALGO_AUTO && algo != FASTCHEB_ALGO_CLENSHAW && algo != FASTCHEB_ALGO_DMMA &&
-      algo != FASTCHEB_ALGO_DMMA_RING)
+  if (algo == FASTCHEB_ALGO_PRODUCT) {
+    if (!pb1d_shape_ok(p))
+      return fail(FASTCHEB_EUNSUPPORTED, "the product-basis path covers 1-D polynomials with %d <= n <= %d and at most 4 real components",
+                  kPbMinN, kPbMaxN);
+    FC_TRY(pb1d_plan(p, true));
+  } else if (algo != FASTCHEB_ALGO_AUTO && algo != FASTCHEB_ALGO_CLENSHAW && algo != FASTCHEB_ALGO_DMMA &&
+             algo != FASTCHEB_ALGO_DMMA_RING) {
     return fail(FASTCHEB_EINVAL, "bad algo %d", algo);
-  p->algo = algo;
+  }
+  p->algo.store(algo);
   return FASTCHEB_OK;
 }
 
 int fastcheb_get_algo(const fastcheb_poly* p, int jac) {
   if (!p) return -1;
+  if (use_pb(p, jac != 0, kPbMinBatch)) return FASTCHEB_ALGO_PRODUCT;  // AUTO: builds and self-checks the plan if needed
   return use_dmma(p, jac != 0) ? FASTCHEB_ALGO_DMMA : FASTCHEB_ALGO_CLENSHAW;
+}
+
+int fastcheb_product_check(const fastcheb_poly* p, double* dv_over_tol, double* dJ_over_tol) {
+  if (!p) return fail(FASTCHEB_EINVAL, "null handle");
+  if (!pb1d_shape_ok(p)) return fail(FASTCHEB_EUNSUPPORTED, "not a shape of the product-basis path");
+  FC_TRY(pb1d_plan(p, false));
+  if (dv_over_tol) *dv_over_tol = p->pb.check_dv;
+  if (dJ_over_tol) *dJ_over_tol = p->pb.check_dJ;
+  return FASTCHEB_OK;
 }
 
 }  // extern "C"
@@ -398,7 +436,7 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
     return check_flag(*fs.host, p);
   }
 
-  // host buffers: chunked H2D -> kernel -> D2H pipeline on two internal streams
+  // host buffers: chunked H2D -> kernel -> D2H pipeline on two cached internal streams
   const int N = p->ndim, E = p->E;
   const size_t in_pp = (size_t)N * rs;
   size_t out_pp;  // bytes per point of output, all buffers
@@ -410,70 +448,123 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
   // the call, large enough (>= 1 M points) that the persistent kernel stays efficient
   int64_t chunk = std::min<int64_t>(npts, std::max<int64_t>(1 << 16, (int64_t)((size_t(64) << 20) / (in_pp + out_pp))));
   const int nbuf = npts > chunk ? 2 : 1;
-  cudaStream_t ss[2] = {nullptr, nullptr};
-  void* dbuf[2] = {nullptr, nullptr};
-  int rc = FASTCHEB_OK;
   const size_t in_bytes = (size_t)chunk * in_pp;
-  const size_t v_bytes = o.interleaved ? (size_t)chunk * out_pp : (size_t)chunk * E * rs;
+  const size_t v_pp = o.interleaved ? out_pp : (size_t)E * rs, J_pp = (!o.interleaved && jac) ? (size_t)E * N * rs : 0;
+  const size_t v_bytes = (size_t)chunk * v_pp, J_bytes = (size_t)chunk * J_pp;
   const size_t in_al = (in_bytes + 255) / 256 * 256, v_al = (v_bytes + 255) / 256 * 256;
-  const size_t J_bytes = (!o.interleaved && jac) ? (size_t)chunk * E * N * rs : 0;
+
+  // a call that fits one chunk (single points, small batches) runs on the caller's stream with plain copies: setting up
+  // the pipeline costs more than such a call itself
+  if (nbuf == 1) {
+    void* dbuf = ws_acquire(p->device, in_al + v_al + J_bytes);
+    if (!dbuf) return fail(FASTCHEB_ENOMEM, "device staging buffer of %zu bytes", in_al + v_al + J_bytes);
+    char* d_in = (char*)dbuf;
+    char* d_v = d_in + in_al;
+    char* d_J = d_v + v_al;
+    int rc = FASTCHEB_OK;
+    cudaError_t ce = set_flag_async(fs.dev, kNoBad, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_in, pts, (size_t)npts * in_pp, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) {
+      if (o.interleaved)
+        rc = eval_device(p, d_in, npts, d_v, o.v_stride, (char*)d_v + (size_t)E * rs, o.J_stride, jac, fs.dev, 0, st);
+      else
+        rc = eval_device(p, d_in, npts, d_v, E, d_J, (int64_t)E * N, jac, fs.dev, 0, st);
+    }
+    if (rc == FASTCHEB_OK && ce == cudaSuccess) ce = cudaMemcpyAsync(o.v, d_v, (size_t)npts * v_pp, cudaMemcpyDeviceToHost, st);
+    if (rc == FASTCHEB_OK && ce == cudaSuccess && J_pp)
+      ce = cudaMemcpyAsync(o.J, d_J, (size_t)npts * J_pp, cudaMemcpyDeviceToHost, st);
+    if (rc == FASTCHEB_OK && ce == cudaSuccess) ce = cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
+    const cudaError_t e2 = cudaStreamSynchronize(st);  // one synchronisation for the whole call
+    if (ce == cudaSuccess) ce = e2;
+    ws_release(p->device, dbuf);
+    if (rc != FASTCHEB_OK) return rc;
+    if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged evaluation failed: %s", cudaGetErrorString(ce));
+    return check_flag(*fs.host, p);
+  }
+
+  // Large batches.  PAGEABLE caller memory (a Julia Vector, a numpy array) would make every cudaMemcpyAsync block the
+  // host (H2D until staged, D2H until complete), which serialises upload, kernel and download; it is therefore copied
+  // by this thread (par_memcpy) through cached PINNED staging buffers, so that the DMA transfers of chunk i overlap the
+  // kernel of chunk i-1 exactly as they do for pinned caller memory.
+  const bool stage_in = !is_pinned_host(pts);
+  const bool stage_out = !is_pinned_host(o.v) || (J_pp && !is_pinned_host(o.J));
+  StreamPair sp;
+  FC_TRY(streams_acquire(p->device, &sp));
+  void* dbuf[2] = {nullptr, nullptr};
+  char* hin[2] = {nullptr, nullptr};
+  char* hout[2] = {nullptr, nullptr};
   auto cleanup = [&]() {
     for (int i = 0; i < 2; ++i) {
-      if (ss[i]) cudaStreamDestroy(ss[i]);
+      cudaStreamSynchronize(sp.s[i]);
       if (dbuf[i]) ws_release(p->device, dbuf[i]);
+      pin_release(hin[i]);
+      pin_release(hout[i]);
     }
+    streams_release(sp);
   };
-  // a call that fits one chunk (single points, small batches) runs on the caller's stream: creating streams costs
-  // more than such a call itself
-  const bool own_streams = nbuf > 1;
-  for (int i = 0; i < nbuf; ++i) {
-    if (own_streams && cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) != cudaSuccess) {
-      cleanup();
-      return fail(FASTCHEB_ECUDA, "cudaStreamCreate failed");
-    }
+  for (int i = 0; i < 2; ++i) {
     dbuf[i] = ws_acquire(p->device, in_al + v_al + J_bytes);
-    if (!dbuf[i]) {
+    if (stage_in) hin[i] = (char*)pin_acquire(in_bytes);
+    if (stage_out) hout[i] = (char*)pin_acquire(v_al + J_bytes);
+    if (!dbuf[i] || (stage_in && !hin[i]) || (stage_out && !hout[i])) {
       cleanup();
-      return fail(FASTCHEB_ENOMEM, "device staging buffer of %zu bytes", in_al + v_al + J_bytes);
+      return fail(FASTCHEB_ENOMEM, "staging buffers of %zu bytes", in_al + v_al + J_bytes);
     }
   }
-  auto stream_of = [&](int b) { return own_streams ? ss[b] : st; };
-  cudaError_t ce = set_flag_async(fs.dev, kNoBad, stream_of(0));
-  if (ce == cudaSuccess && own_streams) ce = cudaStreamSynchronize(ss[0]);  // ordered before the second stream's work
+  int rc = FASTCHEB_OK;
+  cudaError_t ce = set_flag_async(fs.dev, kNoBad, sp.s[0]);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(sp.s[0]);  // ordered before the second stream's work
+  struct Pending {
+    int64_t first = 0, m = 0;
+    bool live = false;
+  } pend[2];
+  // results of the chunk that last used buffer b: wait for its download, then (pageable output) copy them out
+  auto retire = [&](int b) {
+    if (!pend[b].live) return;
+    pend[b].live = false;
+    const cudaError_t e = cudaEventSynchronize(sp.ev[b]);
+    if (ce == cudaSuccess) ce = e;
+    if (stage_out && e == cudaSuccess) {
+      par_memcpy((char*)o.v + (size_t)pend[b].first * v_pp, hout[b], (size_t)pend[b].m * v_pp);
+      if (J_pp) par_memcpy((char*)o.J + (size_t)pend[b].first * J_pp, hout[b] + v_al, (size_t)pend[b].m * J_pp);
+    }
+  };
   int64_t done = 0;
   for (int it = 0; ce == cudaSuccess && rc == FASTCHEB_OK && done < npts; ++it) {
-    const int b = it % nbuf;
+    const int b = it & 1;
     const int64_t m = std::min<int64_t>(chunk, npts - done);
+    retire(b);
+    if (ce != cudaSuccess) break;
     char* d_in = (char*)dbuf[b];
     char* d_v = d_in + in_al;
     char* d_J = d_v + v_al;
-    ce = cudaMemcpyAsync(d_in, (const char*)pts + (size_t)done * in_pp, (size_t)m * in_pp, cudaMemcpyHostToDevice, stream_of(b));
-    if (ce != cudaSuccess) break;
-    if (o.interleaved) {
-      rc = eval_device(p, d_in, m, d_v, o.v_stride, (char*)d_v + (size_t)E * rs, o.J_stride, jac, fs.dev, done, stream_of(b));
-      if (rc != FASTCHEB_OK) break;
-      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * out_pp, d_v, (size_t)m * out_pp, cudaMemcpyDeviceToHost, stream_of(b));
-    } else {
-      rc = eval_device(p, d_in, m, d_v, E, d_J, (int64_t)E * N, jac, fs.dev, done, stream_of(b));
-      if (rc != FASTCHEB_OK) break;
-      ce = cudaMemcpyAsync((char*)o.v + (size_t)done * E * rs, d_v, (size_t)m * E * rs, cudaMemcpyDeviceToHost, stream_of(b));
-      if (ce == cudaSuccess && jac)
-        ce = cudaMemcpyAsync((char*)o.J + (size_t)done * E * N * rs, d_J, (size_t)m * E * N * rs,
-                             cudaMemcpyDeviceToHost, stream_of(b));
+    const char* src = (const char*)pts + (size_t)done * in_pp;
+    if (stage_in) {
+      par_memcpy(hin[b], src, (size_t)m * in_pp);
+      src = hin[b];
     }
+    ce = cudaMemcpyAsync(d_in, src, (size_t)m * in_pp, cudaMemcpyHostToDevice, sp.s[b]);
+    if (ce != cudaSuccess) break;
+    if (o.interleaved)
+      rc = eval_device(p, d_in, m, d_v, o.v_stride, (char*)d_v + (size_t)E * rs, o.J_stride, jac, fs.dev, done, sp.s[b]);
+    else
+      rc = eval_device(p, d_in, m, d_v, E, d_J, (int64_t)E * N, jac, fs.dev, done, sp.s[b]);
+    if (rc != FASTCHEB_OK) break;
+    ce = cudaMemcpyAsync(stage_out ? hout[b] : (char*)o.v + (size_t)done * v_pp, d_v, (size_t)m * v_pp, cudaMemcpyDeviceToHost, sp.s[b]);
+    if (ce == cudaSuccess && J_pp)
+      ce = cudaMemcpyAsync(stage_out ? hout[b] + v_al : (char*)o.J + (size_t)done * J_pp, d_J, (size_t)m * J_pp,
+                           cudaMemcpyDeviceToHost, sp.s[b]);
+    if (ce == cudaSuccess) ce = cudaEventRecord(sp.ev[b], sp.s[b]);
+    pend[b].first = done;
+    pend[b].m = m;
+    pend[b].live = ce == cudaSuccess;
     done += m;
   }
-  if (own_streams) {
-    for (int i = 0; i < nbuf; ++i) {
-      cudaError_t e2 = cudaStreamSynchronize(ss[i]);
-      if (ce == cudaSuccess) ce = e2;
-    }
-    if (ce == cudaSuccess) ce = cudaMemcpy(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost);
-  } else {
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
-    cudaError_t e2 = cudaStreamSynchronize(st);  // one synchronisation for the whole call
-    if (ce == cudaSuccess) ce = e2;
-  }
+  // drain in issue order
+  const int last = (int)(((npts + chunk - 1) / chunk - 1) & 1);
+  retire(last ^ 1);
+  retire(last);
+  if (ce == cudaSuccess && rc == FASTCHEB_OK) ce = cudaMemcpy(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost);
   cleanup();
   if (rc != FASTCHEB_OK) return rc;
   if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged evaluation failed: %s", cudaGetErrorString(ce));

@@ -1,5 +1,7 @@
 // The device-resident ChebPoly handle (mirrors struct ChebPoly{N,T,Td}, FastChebInterp.jl:37-41).
 #pragma once
+#include <atomic>
+#include <mutex>
 #include <vector>
 #include "host_util.h"
 
@@ -33,6 +35,21 @@ struct DmmaPlan {
   std::vector<DmmaGroup> groups;
 };
 
+// 1-D product-basis plan (eval_pb1d.cuh), built lazily on the first large batch and guarded by a self-check against
+// the Clenshaw kernel; internally synchronised, never changes what the handle evaluates to beyond rounding
+constexpr int kPbMinN = 40, kPbMaxN = 512;   // dimension-1 sizes the path covers
+constexpr int64_t kPbMinBatch = 8192;        // AUTO plans it on the first batch of at least this many points
+enum PbState { kPbNone = 0, kPbBuilt = 1, kPbAccepted = 2, kPbRejected = 3 };
+struct PbPlan {
+  std::mutex mu;
+  std::atomic<int> state{kPbNone};
+  bool checked = false, ok_val = false, ok_jac = false;
+  std::vector<unsigned char> h_D;  // product-basis coefficients (kernel layout, eval_pb1d.cuh), passed as kernel parameters
+  int AMAX = 0, M = 0;
+  double sum_abs = 0, sum_k2 = 0;      // sum |c_k|, sum |c_k| k^2 over all components
+  double check_dv = 0, check_dJ = 0;   // self-check result: worst difference over the tolerance
+};
+
 }  // namespace fastcheb
 
 struct fastcheb_poly {
@@ -47,7 +64,8 @@ struct fastcheb_poly {
   int64_t nelems = 0;  // prod dims
   std::vector<fastcheb::ClenshawGroup> groups;
   fastcheb::DmmaPlan dmma;
-  int algo = FASTCHEB_ALGO_AUTO;
+  std::atomic<int> algo{FASTCHEB_ALGO_AUTO};
+  mutable fastcheb::PbPlan pb;
   bool eval_ok = true;  // false: N-d polynomial whose dimension-1 line does not fit shared memory (plan_clenshaw)
 };
 
@@ -56,6 +74,15 @@ namespace fastcheb {
 int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
                 int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode = 0,
                 const void* tan = nullptr);
+// the CUDA-core Clenshaw path regardless of the handle's algorithm selection (self-checks of the other paths)
+int eval_clenshaw_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+                         int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
+                         const void* tan);
+// 1-D product-basis path (eval_pb1d.cu)
+bool pb1d_shape_ok(const fastcheb_poly* p);
+int pb1d_plan(const fastcheb_poly* p, bool forced);
+int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
+              int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode, const void* tan);
 // build the handle from coefficients already on the device (Julia layout); takes no ownership of d_src
 int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
                        const void* d_src, const double* lb, const double* ub, int device, cudaStream_t st);

@@ -62,6 +62,7 @@ extern "C" {
 #define FASTCHEB_ALGO_CLENSHAW 1 /* CUDA-core Clenshaw, one thread per point            */
 #define FASTCHEB_ALGO_DMMA 2     /* FP64 tensor-core first-dimension contraction (F64)   */
 #define FASTCHEB_ALGO_DMMA_RING 3 /* same, but never the shared-memory-resident 2-D kernel */
+#define FASTCHEB_ALGO_PRODUCT 4  /* 1-D, 40 <= n <= 512: product-basis contraction, one DFMA per coefficient       */
 
 typedef struct fastcheb_poly fastcheb_poly; /* device-resident ChebPoly{N,T,Td} (FastChebInterp.jl:37-41) */
 
@@ -95,10 +96,17 @@ int fastcheb_ncomp(const fastcheb_poly* p);
 int fastcheb_device(const fastcheb_poly* p);
 /* copy the coefficients back in Julia layout (dst on host or device per dst_mem) */
 int fastcheb_get_coefs(const fastcheb_poly* p, void* dst, int dst_mem);
-/* force an evaluation algorithm (default AUTO); returns EUNSUPPORTED if the handle cannot run it */
+/* force an evaluation algorithm (default AUTO); returns EUNSUPPORTED if the handle cannot run it.  A diagnostic /
+ * benchmarking switch: it selects among kernels that agree within the stated tolerance and may be called at any time
+ * (the selection is an atomic), but results of evaluations racing with it may come from either kernel. */
 int fastcheb_set_algo(fastcheb_poly* p, int algo);
 /* which algorithm AUTO resolves to for value (jac=0) / Jacobian (jac=1) calls */
 int fastcheb_get_algo(const fastcheb_poly* p, int jac);
+/* The 1-D product-basis path (FASTCHEB_ALGO_PRODUCT) is taken by AUTO only after a plan-time self-check against the
+ * bit-exact Clenshaw kernel on 6144 probe points (uniform, Chebyshev-clustered, and 2^-1..2^-53 of the span from both
+ * end points): this returns the check's worst |dv| / (16 eps sum|c|) and worst |dv'| / (16 eps sum|c_k| k^2 2/(ub-lb));
+ * AUTO accepts values (derivatives) at <= 0.25. */
+int fastcheb_product_check(const fastcheb_poly* p, double* dv_over_tol, double* dJ_over_tol);
 
 /* ---- batched evaluation -----------------------------------------------------------------------
  * fastcheb_eval      : c.(ys)                       — (::ChebPoly{N})(x) eval.jl:63-70 per point
