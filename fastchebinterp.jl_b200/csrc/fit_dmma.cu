@@ -39,30 +39,23 @@ int fit_slot_map(int n, int dtype) {
   return (n == 65 && !plain && dtype == FASTCHEB_F32) ? 1 : 0;
 }
 
-// map != 0 implies the split odd half (parts P, Q), map == 0 the unsplit one (part O)
-int get_afrag(int dev, int n, int map, AFrag* out) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto key = std::make_pair(dev, 4 * n + map);
+}  // namespace
+
+// Folded, normalised REDFT00 matrices of size n in A-fragment order (parts O | B | C, or P | Q | B | C when map != 0):
+// the host-side builder shared by the batched 1-D kernel (fit_dmma.cuh) and the resident N-d kernel (fit_nd.cuh).
+void fit_afrag_host(int n, int map, std::vector<double>& h, int* ko_out, int* kb_out, int* kc_out) {
   const bool split = map != 0;
-  auto it = g_afrag.find(key);
-  if (it != g_afrag.end()) {
-    *out = it->second;
-    return FASTCHEB_OK;
-  }
   const int N = n - 1, H = N / 2;
   const bool two = N >= 4 && N % 4 == 0;  // the even half folds once more
   // folded inputs (= outputs) of each part
   const int Jo = (N + 1) / 2;
   const int Jb = two ? H / 2 + 1 : N / 2 + 1;
   const int Jc = two ? H / 2 : 0;
-  AFrag a;
-  a.ko = (Jo + 3) / 4;
-  a.kb = (Jb + 3) / 4;
-  a.kc = (Jc + 3) / 4;
-  const int mo = (a.ko + 1) / 2, mb = (a.kb + 1) / 2, mc = (a.kc + 1) / 2;
+  const int ko = (Jo + 3) / 4, kb = (Jb + 3) / 4, kc = (Jc + 3) / 4;
+  const int mo = (ko + 1) / 2, mb = (kb + 1) / 2, mc = (kc + 1) / 2;
   // two folds: the odd half is split once more by the parity of j (parts P and Q, fit_dmma.cuh) and replaces part O
-  a.doubles = (size_t)(split ? 2 * mc * a.kc : mo * a.ko) * 32 + (size_t)(mb * a.kb + mc * a.kc) * 32;
-  std::vector<double> h(a.doubles, 0.0);
+  const size_t doubles = (size_t)(split ? 2 * mc * kc : mo * ko) * 32 + (size_t)(mb * kb + mc * kc) * 32;
+  h.assign(doubles, 0.0);
   // REDFT00 (interp.jl:44) with the scaling of interp.jl:49-54 folded in: output k, folded input j carrying REDFT00
   // weight w (end points and self-paired middle elements count once, everything else twice)
   auto entry = [&](int k, int j, bool once) -> double {
@@ -82,24 +75,44 @@ int get_afrag(int dev, int n, int map, AFrag* out) {
     // parts P, Q: row l (k = 2l+1, l < N/4), column i: b_{2i} resp. b_{2i+1}; b_0 = x_0 - x_N carries weight 1
     for (int odd = 0; odd < 2; ++odd) {
       for (int mt = 0; mt < mc; ++mt)
-        for (int ks = 0; ks < a.kc; ++ks)
+        for (int ks = 0; ks < kc; ++ks)
           for (int l = 0; l < 32; ++l) {
             const int row = 8 * mt + l / 4, i = fit_map_i(map, ks, l % 4), j = 2 * i + odd;
-            if (row < Jc && i < Jc) h[off + (size_t)(mt * a.kc + ks) * 32 + l] = entry(2 * row + 1, j, j == 0);
+            if (row < Jc && i < Jc) h[off + (size_t)(mt * kc + ks) * 32 + l] = entry(2 * row + 1, j, j == 0);
           }
-      off += (size_t)mc * a.kc * 32;
+      off += (size_t)mc * kc * 32;
     }
   } else {
-    fill(off, a.ko, mo, Jo, 2, 1, -1);                                  // part O: k = 2l+1, b_j
-    off += (size_t)mo * a.ko * 32;
+    fill(off, ko, mo, Jo, 2, 1, -1);                                  // part O: k = 2l+1, b_j
+    off += (size_t)mo * ko * 32;
   }
   if (two) {
-    fill(off, a.kb, mb, Jb, 4, 0, H / 2);                               // part B: k = 4l, aa_j (self-paired at j = N/4)
-    off += (size_t)mb * a.kb * 32;
-    fill(off, a.kc, mc, Jc, 4, 2, -1);                                  // part C: k = 4l+2, ab_j
+    fill(off, kb, mb, Jb, 4, 0, H / 2);                               // part B: k = 4l, aa_j (self-paired at j = N/4)
+    off += (size_t)mb * kb * 32;
+    fill(off, kc, mc, Jc, 4, 2, -1);                                  // part C: k = 4l+2, ab_j
   } else {
-    fill(off, a.kb, mb, Jb, 2, 0, N % 2 == 0 ? H : -1);                 // part B: k = 2l, a_j (self-paired at j = N/2)
+    fill(off, kb, mb, Jb, 2, 0, N % 2 == 0 ? H : -1);                 // part B: k = 2l, a_j (self-paired at j = N/2)
   }
+  *ko_out = ko;
+  *kb_out = kb;
+  *kc_out = kc;
+}
+
+namespace {
+
+// map != 0 implies the split odd half (parts P, Q), map == 0 the unsplit one (part O)
+int get_afrag(int dev, int n, int map, AFrag* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_pair(dev, 4 * n + map);
+  auto it = g_afrag.find(key);
+  if (it != g_afrag.end()) {
+    *out = it->second;
+    return FASTCHEB_OK;
+  }
+  AFrag a;
+  std::vector<double> h;
+  fit_afrag_host(n, map, h, &a.ko, &a.kb, &a.kc);
+  a.doubles = h.size();
   FC_CUDA(cudaMalloc(&a.d, h.size() * sizeof(double)));
   FC_CUDA(cudaMemcpy(a.d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
   g_afrag[key] = a;

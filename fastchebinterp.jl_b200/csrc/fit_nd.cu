@@ -1,0 +1,240 @@
+// Host side of the resident N-d / long-line DCT-I fit (fit_nd.cuh): matrices, planning, launch.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+#include "fit_dmma_launch.h"
+#include "fit_nd.cuh"
+
+namespace fastcheb {
+namespace {
+
+struct NdMatrices {
+  double* d = nullptr;  // the matrices of every distinct n of a shape, back to back
+  int doubles = 0;
+  std::vector<int> ns, off, ko, kb, kc;
+};
+std::mutex g_mu;
+std::map<std::pair<int, std::vector<int>>, NdMatrices> g_mats;  // (device, sorted distinct n > 1)
+
+int get_matrices(int dev, std::vector<int> ns, const NdMatrices** out) {
+  std::sort(ns.begin(), ns.end());
+  ns.erase(std::unique(ns.begin(), ns.end()), ns.end());
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_pair(dev, ns);
+  auto it = g_mats.find(key);
+  if (it != g_mats.end()) {
+    *out = &it->second;
+    return FASTCHEB_OK;
+  }
+  if (g_mats.size() >= 128) {  // a caller sweeping many shapes must not accumulate matrices for ever
+    cudaDeviceSynchronize();
+    for (auto& kv : g_mats) cudaFree(kv.second.d);
+    g_mats.clear();
+  }
+  NdMatrices m;
+  m.ns = ns;
+  std::vector<double> all;
+  for (int n : ns) {
+    std::vector<double> h;
+    int ko, kb, kc;
+    fit_afrag_host(n, 0, h, &ko, &kb, &kc);
+    m.off.push_back((int)all.size());
+    m.ko.push_back(ko);
+    m.kb.push_back(kb);
+    m.kc.push_back(kc);
+    all.insert(all.end(), h.begin(), h.end());
+  }
+  m.doubles = (int)all.size();
+  FC_CUDA(cudaMalloc(&m.d, std::max<size_t>(all.size(), 1) * sizeof(double)));
+  FC_CUDA(cudaMemcpy(m.d, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice));
+  auto ins = g_mats.emplace(key, std::move(m));
+  *out = &ins.first->second;
+  return FASTCHEB_OK;
+}
+
+template <typename R, int MTO, int MTB, int MTC, bool AFG = false>
+cudaError_t launch(const FitNdParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
+  auto kern = fit_nd_kernel<R, MTO, MTB, MTC, AFG>;
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
+  if (e != cudaSuccess) return e;
+  if (bps) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
+  kern<<<grid, threads, smem, st>>>(prm);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// size class of the accumulators: 0: n <= 65 (any n), 1: n <= 129, 2: n <= 257 (classes 1, 2: 4 | n-1 only)
+template <typename R>
+cudaError_t dispatch(int cls, const FitNdParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
+  switch (cls) {
+    case 0: return launch<R, 4, 4, 2>(prm, grid, threads, smem, st, bps);
+    case 1: return launch<R, 8, 5, 4>(prm, grid, threads, smem, st, bps);
+    case 2: return launch<R, 16, 9, 8, true>(prm, grid, threads, smem, st, bps);  // matrices from global memory / L2
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, int cplx, long long howmany, int dtype,
+           const void* vals, void* coefs, long long* bad_dev, long long idx_base, double* maxabs_dev, cudaStream_t st,
+           bool* handled) {
+  *handled = false;
+  static const bool off = [] {  // experiments: FASTCHEB_FIT_ND=0 keeps the generic per-dimension kernels
+    const char* e = getenv("FASTCHEB_FIT_ND");
+    return e && atoi(e) == 0;
+  }();
+  if (off || howmany < 1 || ndim > kFitNdMaxDims) return FASTCHEB_OK;
+  const int E = K * (cplx ? 2 : 1);
+  const size_t rs = real_size(dtype);
+  long long reals = E;
+  int nmax = 1;
+  std::vector<int> ns;
+  for (int d = 0; d < ndim; ++d) {
+    reals *= dims[d];
+    if (reals > (1LL << 26)) return FASTCHEB_OK;
+    nmax = std::max<int>(nmax, (int)dims[d]);
+    if (dims[d] > 1) ns.push_back((int)dims[d]);
+  }
+  if (ns.empty()) return FASTCHEB_OK;  // nothing to transform: the caller copies
+  int cls = nmax <= 65 ? 0 : (nmax <= 129 ? 1 : (nmax <= 257 ? 2 : -1));
+  if (cls < 0) return FASTCHEB_OK;
+  if (cls > 0)
+    for (int n : ns)
+      if (n > 65 && (n - 1) % 4 != 0) return FASTCHEB_OK;  // the larger classes are sized for the twice-folded form
+  // batches of 1-D lines: a CTA takes LB lines at a time as one (n x LB) array whose second dimension is not
+  // transformed, so that all of its warps have line groups to work on
+  long long arrays = howmany, per_array = reals;
+  const bool lines = ndim == 1;
+  long long LB = 1;
+  if (lines) {
+    LB = std::min<long long>(howmany, cls == 0 ? 128 : 64);
+    arrays = howmany / LB;
+    per_array = reals * LB;
+  }
+  const NdMatrices* mats = nullptr;
+  FC_TRY(get_matrices(dev, ns, &mats));
+  const size_t af_bytes = cls == 2 ? 0 : (((size_t)mats->doubles * 8 + 15) / 16) * 16;  // class 2 reads them from L2
+  const size_t budget = std::min<size_t>(di->smem_optin, kSmemOptinMax) - 2048;
+  if (lines) {  // as many lines per block as fit next to the matrices (a multiple of the 16- / 32-line MMA blocks)
+    const long long room = ((long long)budget - (long long)af_bytes - 256) / (long long)(reals * rs);
+    if (room < LB) LB = room / 32 * 32;
+    if (LB < 32 && LB < howmany) return FASTCHEB_OK;
+    arrays = howmany / LB;
+    per_array = reals * LB;
+  }
+  if (af_bytes + (size_t)per_array * rs + 256 > budget) return FASTCHEB_OK;
+
+  auto run = [&](const void* src, void* dst, long long narr, long long arr_reals, long long first_fit, long long fits_per_arr) -> int {
+    FitNdParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.src = src;
+    prm.dst = dst;
+    prm.afrag = mats->d;
+    prm.afragDoubles = mats->doubles;
+    prm.howmany = narr;
+    prm.bad = bad_dev;
+    prm.idx_base = idx_base + first_fit * reals;
+    prm.maxabs = (maxabs_dev && fits_per_arr == 1) ? maxabs_dev + first_fit : nullptr;
+    prm.ndim = ndim;
+    prm.E = E;
+    prm.K = K;
+    prm.cplx = cplx;
+    prm.reals = (int)arr_reals;
+    prm.fits = (int)fits_per_arr;
+    prm.fit_reals = (int)reals;
+    int stride = E;
+    for (int d = 0; d < ndim; ++d) {
+      FitNdDim& fd = prm.dim[d];
+      fd.n = (int)dims[d];
+      fd.stride = stride;
+      stride *= (int)dims[d];
+      if (fd.n > 1) {
+        const int i = (int)(std::lower_bound(mats->ns.begin(), mats->ns.end(), fd.n) - mats->ns.begin());
+        fd.KO = mats->ko[i];
+        fd.KB = mats->kb[i];
+        fd.KC = mats->kc[i];
+        fd.two = fd.KC > 0;
+        fd.afrag = mats->off[i];
+      }
+    }
+    // warps per CTA: the passes are separated by CTA barriers, so the line groups of a pass should divide evenly among
+    // the warps (65 lines = 10 groups: 5 warps, not 8); FASTCHEB_FITND_WARPS overrides (experiments)
+    const int gb = dtype == FASTCHEB_F64 ? 2 : 4;
+    int warps = 8;
+    {
+      long long best = -1;
+      for (int w = 8; w >= 4; --w) {
+        long long slots = 0;
+        for (int d = 0; d < ndim; ++d)
+          if (dims[d] > 1) {
+            const long long nlines = arr_reals / dims[d];
+            const long long groups = (nlines + 8 * gb - 1) / (8 * gb) * gb;
+            slots += (groups + w - 1) / w * w * (long long)dims[d];  // rounds x warps, weighted by the work of a line
+          }
+        if (best < 0 || slots < best) {
+          best = slots;
+          warps = w;
+        }
+      }
+      if (const char* t = getenv("FASTCHEB_FITND_WARPS")) {
+        const int v = atoi(t);
+        if (v >= 1 && v <= 8) warps = v;
+      }
+    }
+    const int threads = warps * 32;
+    const size_t bufBytes = (((size_t)arr_reals * rs + 15) / 16) * 16 + 16;
+    // two buffers (the next array loads during the transform) when both fit and leave room for a second CTA per SM
+    int nbuf = (128 + af_bytes + 2 * bufBytes <= budget / 2 + 1024 || (narr > 2LL * di->sms && 128 + af_bytes + 2 * bufBytes <= budget)) ? 2 : 1;
+    if (const char* t = getenv("FASTCHEB_FITND_NBUF")) {
+      const int v = atoi(t);
+      if (v == 1 || (v == 2 && 128 + af_bytes + 2 * bufBytes <= budget)) nbuf = v;
+    }
+    prm.nbuf = nbuf;
+    const size_t smem = 128 + af_bytes + (size_t)nbuf * bufBytes;
+    int bps = 0;
+    cudaError_t e = dtype == FASTCHEB_F64 ? dispatch<double>(cls, prm, 0, threads, smem, st, &bps)
+                                          : dispatch<float>(cls, prm, 0, threads, smem, st, &bps);
+    if (e != cudaSuccess || bps < 1) {
+      cudaGetLastError();
+      if (getenv("FASTCHEB_DEBUG")) fprintf(stderr, "fit_nd: not launchable (%s, %d CTAs/SM, %zu B)\n", cudaGetErrorString(e), bps, smem);
+      return -1;  // not launchable: the caller falls back
+    }
+    const int grid = (int)std::max<long long>(1, std::min<long long>(narr, (long long)di->sms * bps));
+    e = dtype == FASTCHEB_F64 ? dispatch<double>(cls, prm, grid, threads, smem, st, nullptr)
+                              : dispatch<float>(cls, prm, grid, threads, smem, st, nullptr);
+    if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "resident DCT-I kernel launch failed: %s", cudaGetErrorString(e));
+    return FASTCHEB_OK;
+  };
+
+  if (!lines) {
+    const int rc = run(vals, coefs, howmany, reals, 0, 1);
+    if (rc == -1) return FASTCHEB_OK;
+    FC_TRY(rc);
+    *handled = true;
+    return FASTCHEB_OK;
+  }
+  // 1-D: blocks of LB lines, then the remaining lines as one smaller block
+  if (maxabs_dev) return FASTCHEB_OK;  // per-line maxima of line blocks are not produced here: generic path
+  long long done = 0;
+  if (arrays > 0) {
+    const int rc = run(vals, coefs, arrays, per_array, 0, LB);
+    if (rc == -1) return FASTCHEB_OK;
+    FC_TRY(rc);
+    done = arrays * LB;
+  }
+  if (done < howmany) {
+    const long long rest = howmany - done;
+    const int rc = run((const char*)vals + (size_t)done * reals * rs, (char*)coefs + (size_t)done * reals * rs, 1, reals * rest, done, rest);
+    if (rc == -1) return fail(FASTCHEB_ECUDA, "resident DCT-I kernel: tail block not launchable");
+    FC_TRY(rc);
+  }
+  *handled = true;
+  return FASTCHEB_OK;
+}
+
+}  // namespace fastcheb

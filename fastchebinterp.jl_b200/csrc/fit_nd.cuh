@@ -1,0 +1,318 @@
+// N-d DCT-I fit with the WHOLE ARRAY RESIDENT IN SHARED MEMORY: one HBM round trip for all dimensions.
+//
+// Replaces chebcoefs for multidimensional arrays and for longer 1-D lines
+// (/root/reference/src/interp.jl:39-57: FFTW.r2r(vals, REDFT00) over every dimension :43-44, the 1/prod 2(n-1)
+// scale :49, the interior doubling :50-54) — BASELINE.json configs[1] (65 x 65) and the 33^3 / 17^4 arrays of
+// configs[2..3], single fits (`chebinterp(vals, lb, ub)`) and batches of them alike.
+//
+// A CTA (several per SM for small arrays) owns one array at a time: it loads the array into shared memory, transforms
+// it in place along dimension 1, 2, ... (a CTA barrier between dimensions), and writes the coefficients back.  A pass
+// along dimension d treats the array as lines of n_d elements with element stride s_d = E n_1 .. n_{d-1}; 8 lines
+// form the N extent of an FP64 tensor-core MMA (mma.sync m8n8k4, SASS DMMA), exactly as in the batched 1-D kernel
+// (fit_dmma.cuh): REDFT00's symmetry splits the transform into odd outputs from b_j = x_j - x_{N-j} (part O) and
+// even outputs from a_j = x_j + x_{N-j}, folded once more when 4 | N (parts B: k = 4l, C: k = 4l+2); the folded,
+// normalised cosine matrices of every distinct n are A fragments in shared memory.  A warp takes 8 lines, forms the
+// folds, runs the three small dense products and stores the outputs over the inputs (all reads of a line group
+// happen before its writes; different warps own different lines).
+//
+// The k-step and m-tile counts are RUNTIME values here (one instantiation serves every n up to 8 MT_O + 1), so a
+// 65 x 33 x 17 array needs no kernel of its own; the accumulators are sized for the largest case.
+//
+// Shared-memory banks: for n = 2^m + 1 every stride s_d (and the distance between neighbouring lines) is 1 modulo the
+// number of banks, so element j of line L sits in bank (L + j).  The 8 lines of an MMA are therefore taken 4 apart
+// from a block of 16 (Float64: column q <-> line 4 (q%4) + q/4 + 2t, t = 0, 1) or 32 lines (Float32: column q <-> line
+// 4 q + t, t = 0..3): with contraction slot (k-step ks, lane%4 = c) <-> folded input j = 4 ks + c, the 16 (32) lanes of
+// a shared-memory wavefront read banks 4 q' + c — all distinct — in every pass.
+#pragma once
+#include <cstdint>
+#include "ptx_util.cuh"
+
+namespace fastcheb {
+
+constexpr int kFitNdMaxDims = 6;
+
+struct FitNdDim {
+  int n;        // size of this dimension (1: skipped)
+  int stride;   // element stride of a line, in reals
+  int KO, KB, KC, two;  // k-steps of parts O, B, C; two = even half folded twice
+  int afrag;    // offset (doubles) of this dimension's A fragments in the shared-memory matrix area
+};
+
+struct FitNdParams {
+  const void* src;
+  void* dst;
+  const double* afrag;  // all distinct matrices back to back
+  int afragDoubles;
+  long long howmany;
+  long long* bad;       // first non-finite flat real index (atomicMin), may be null
+  long long idx_base;
+  double* maxabs;       // optional: max_k infnorm(C_k) per array
+  int ndim, E, K, cplx;
+  int reals;            // reals per array = E prod n (x lines per block for batches of 1-D lines)
+  int fits, fit_reals;  // independent fits in one array (1-D line blocks: > 1) and reals per fit
+  int nbuf;             // array buffers in shared memory (2: the next array loads while this one is transformed)
+  FitNdDim dim[kFitNdMaxDims];
+};
+
+// One pass over 8 lines.  x: the array in shared memory; lane (c = lane%4, q = lane/4) feeds line `bl` (B operand,
+// column q) and receives lines dl[0], dl[1] (D operand, columns 2c, 2c+1; dlive: the line exists).
+// CKO / CKB / CKC != 0: the k-step counts are compile-time (the common sizes n = 17, 33, 65, 129): the k loop is then one
+// straight-line block, every operand load of a k-step is issued before its DMMAs and the loads of the next k-step
+// overlap them.  0: runtime counts from `d` (any n), with the loads of a k-step hoisted by hand.
+template <typename R, int MTO, int MTB, int MTC, int CKO, int CKB, int CKC>
+__device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const double* __restrict__ af, int bl, const int (&dl)[2],
+                                             const bool (&dlive)[2], int lane) {
+  constexpr bool CT = CKO != 0;
+  const int c = lane & 3, q = lane >> 2;
+  const int N = d.n - 1, H = N / 2, s = d.stride;
+  const int KO = CT ? CKO : d.KO, KB = CT ? CKB : d.KB, KC = CT ? CKC : d.KC;
+  const int MO = (KO + 1) / 2, MB = (KB + 1) / 2, MC = (KC + 1) / 2;
+  const bool two = CT ? (CKC > 0) : (d.two != 0);
+  const int Jo = (N + 1) / 2;                  // inputs of part O: j < Jo
+  const int Jb = two ? H / 2 + 1 : N / 2 + 1;  // inputs of part B
+  double accO[MTO][2], accB[MTB][2], accC[MTC][2];
+#pragma unroll
+  for (int m = 0; m < MTO; ++m) accO[m][0] = accO[m][1] = 0.0;
+#pragma unroll
+  for (int m = 0; m < MTB; ++m) accB[m][0] = accB[m][1] = 0.0;
+#pragma unroll
+  for (int m = 0; m < MTC; ++m) accC[m][0] = accC[m][1] = 0.0;
+  const double* aO = af + lane;
+  const double* aB = aO + MO * KO * 32;
+  const double* aC = aB + MB * KB * 32;
+  const R* z = x + bl;
+  const int KMAX = KO > KB ? KO : KB;
+  auto step = [&](int ks) {
+    const int j = 4 * ks + c;
+    // beyond the folded range the matrix columns are zero: the operand only has to be finite, read element 0
+    const int jj = (j < Jo || j < Jb) ? j : 0;
+    const R r1 = z[jj * s], r2 = z[(N - jj) * s];
+    R r3 = R(0), r4 = R(0);
+    if (two) {
+      const int j2 = j <= H ? j : 0;
+      r3 = z[(H - j2) * s];
+      r4 = z[(H + j2) * s];
+    }
+    // the A fragments of this k-step, all loaded before the first DMMA (the first entry of the matrices where the part
+    // has no such tile: a once-folded n has no part C at all; those values are never used)
+    double vO[MTO], vB[MTB], vC[MTC];
+#pragma unroll
+    for (int m = 0; m < MTO; ++m) vO[m] = *((m < MO && ks < KO) ? aO + (m * KO + ks) * 32 : aO);
+#pragma unroll
+    for (int m = 0; m < MTB; ++m) vB[m] = *((m < MB && ks < KB) ? aB + (m * KB + ks) * 32 : aO);
+#pragma unroll
+    for (int m = 0; m < MTC; ++m) vC[m] = *((m < MC && ks < KC) ? aC + (m * KC + ks) * 32 : aO);
+    const double x1 = (double)r1, x2 = (double)r2;
+    const double fo = __dsub_rn(x1, x2);
+    double fb = __dadd_rn(x1, x2), fc = 0.0;
+    if (two) {
+      const double a2 = __dadd_rn((double)r3, (double)r4);
+      fc = __dsub_rn(fb, a2);
+      fb = __dadd_rn(fb, a2);
+    }
+    if (ks < KO) {
+#pragma unroll
+      for (int m = 0; m < MTO; ++m)
+        if (m < MO) dmma884(accO[m][0], accO[m][1], vO[m], fo);
+    }
+    if (ks < KB) {
+#pragma unroll
+      for (int m = 0; m < MTB; ++m)
+        if (m < MB) dmma884(accB[m][0], accB[m][1], vB[m], fb);
+    }
+    if (ks < KC) {
+#pragma unroll
+      for (int m = 0; m < MTC; ++m)
+        if (m < MC) dmma884(accC[m][0], accC[m][1], vC[m], fc);
+    }
+  };
+  if constexpr (CT) {
+#pragma unroll
+    for (int ks = 0; ks < (CKO > CKB ? CKO : CKB); ++ks) step(ks);
+  } else {
+#pragma unroll 2
+    for (int ks = 0; ks < KMAX; ++ks) step(ks);
+  }
+  __syncwarp();  // every lane has read its inputs: transform in place
+  const int SB = two ? 4 : 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (!dlive[h]) continue;
+    R* y = x + dl[h];
+#pragma unroll
+    for (int m = 0; m < MTO; ++m) {
+      const int k = 2 * (8 * m + q) + 1;
+      if (m < MO && k <= N) y[k * s] = (R)accO[m][h];
+    }
+#pragma unroll
+    for (int m = 0; m < MTB; ++m) {
+      const int k = SB * (8 * m + q);
+      if (m < MB && k <= N) y[k * s] = (R)accB[m][h];
+    }
+#pragma unroll
+    for (int m = 0; m < MTC; ++m) {
+      const int k = 4 * (8 * m + q) + 2;
+      if (m < MC && k <= N) y[k * s] = (R)accC[m][h];
+    }
+  }
+}
+
+// Asynchronous copy of one array into shared memory (cp.async, SASS LDGSTS): the destination is shifted so that it has
+// the source's alignment modulo 16 bytes, the body then moves in 16-byte pieces and only the ragged head / tail element
+// by element — arrays of an odd number of reals (65 x 65 doubles = 33 800 B) start at every other 8-byte offset.
+// Returns the shifted base.  Every thread commits one group.
+template <typename R>
+__device__ __forceinline__ R* fit_nd_load_async(unsigned char* buf16, const R* g, int reals) {
+  const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(g) & 15u);
+  R* x = reinterpret_cast<R*>(buf16 + mis);
+  int head = (int)(((16u - mis) & 15u) / sizeof(R));
+  if (head > reals) head = reals;
+  const int nvec = (int)(((size_t)(reals - head) * sizeof(R)) / 16);
+  const int per = 16 / (int)sizeof(R);
+  const int tail0 = head + nvec * per;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(x + head + i * per)), "l"(g + head + i * per) : "memory");
+  for (int i = threadIdx.x; i < head + (reals - tail0); i += blockDim.x) {
+    const int e = i < head ? i : tail0 + (i - head);
+    if constexpr (sizeof(R) == 8)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(x + e)), "l"(g + e) : "memory");
+    else
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(x + e)), "l"(g + e) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  return x;
+}
+
+// MTO/MTB/MTC: accumulator m-tiles of parts O / B / C the instantiation provides (n <= 16 MTO + 1).
+// AFG: the matrices are too large for shared memory next to the array (n > 129: 130-200 KB) and are read from global
+// memory instead — they are shared by every CTA and stay in L2.
+// Two array buffers when they fit (prm.nbuf == 2): the next array's copy is in flight while the current one is
+// transformed.
+template <typename R, int MTO, int MTB, int MTC, bool AFG>
+__global__ void __launch_bounds__(256) fit_nd_kernel(const __grid_constant__ FitNdParams prm) {
+  extern __shared__ __align__(16) unsigned char fastcheb_smem[];
+  // [128-byte header: 8 partial maxima | flag] [matrices unless AFG] [array buffers, 16-byte aligned, 16 bytes of slack]
+  // (no static shared memory: the kernel is launched with the opt-in maximum of dynamic shared memory)
+  double* s_red = reinterpret_cast<double*>(fastcheb_smem);
+  int& s_flag = *reinterpret_cast<int*>(fastcheb_smem + 64);
+  double* af_s = reinterpret_cast<double*>(fastcheb_smem + 128);
+  unsigned char* bufs = fastcheb_smem + 128 + (AFG ? 0 : (((size_t)prm.afragDoubles * 8 + 15) / 16) * 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if constexpr (!AFG)
+    for (int i = tid; i < prm.afragDoubles; i += blockDim.x) af_s[i] = prm.afrag[i];
+  const int reals = prm.reals;
+  const R* src = reinterpret_cast<const R*>(prm.src);
+  R* dst = reinterpret_cast<R*>(prm.dst);
+  const size_t bufBytes = (((size_t)reals * sizeof(R) + 15) / 16) * 16 + 16;
+  const bool dbl = prm.nbuf == 2;
+  R* xnext = nullptr;
+  if ((long long)blockIdx.x < prm.howmany) xnext = fit_nd_load_async<R>(bufs, src + (long long)blockIdx.x * reals, reals);
+  int it = 0;
+  for (long long f = blockIdx.x; f < prm.howmany; f += gridDim.x, ++it) {
+    const R* g = src + f * (long long)reals;
+    R* x = xnext;
+    const long long fn = f + gridDim.x;
+    if (dbl && fn < prm.howmany) {
+      // the other buffer was stored in the previous iteration (all threads passed that iteration's last barrier)
+      xnext = fit_nd_load_async<R>(bufs + (size_t)((it + 1) & 1) * bufBytes, src + fn * (long long)reals, reals);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // the array (and, first time, the matrices) are in shared memory
+    for (int dd = 0; dd < prm.ndim; ++dd) {
+      const FitNdDim& d = prm.dim[dd];
+      if (d.n <= 1) continue;  // DHT of length 1 = identity (interp.jl:43)
+      const int s = d.stride;
+      const int nlines = reals / d.n;
+      constexpr int GB = sizeof(R) == 8 ? 2 : 4;  // groups per block of 8 GB lines
+      const int ngroups = (nlines + 8 * GB - 1) / (8 * GB) * GB;
+      for (int gi = warp; gi < ngroups; gi += nwarps) {
+        // line L -> (outer o, inner i): base = o * n * s + i
+        auto base_of = [&](int L) {
+          const int o = L / s, i = L - o * s;
+          return o * d.n * s + i;
+        };
+        const int c = lane & 3, q = lane >> 2;
+        const int blk = (gi / GB) * 8 * GB, t = gi % GB;
+        auto line_of = [&](int col) { return blk + (GB == 2 ? 4 * (col & 3) + (col >> 2) + 2 * t : 4 * col + t); };
+        const int Lb = line_of(q);
+        const int bl = base_of(Lb < nlines ? Lb : 0);
+        int dl[2];
+        bool dlive[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int Ld = line_of(2 * c + h);
+          dlive[h] = Ld < nlines;
+          dl[h] = base_of(dlive[h] ? Ld : 0);
+        }
+        // matrices: shared memory (the address space stays visible to the compiler) or, AFG, global memory / L2
+        const double* afd;
+        if constexpr (AFG)
+          afd = prm.afrag + d.afrag;
+        else
+          afd = af_s + d.afrag;
+        // the common sizes run a fully unrolled copy of the pass
+        if (MTO >= 4 && d.KO == 8 && d.KB == 5 && d.KC == 4)        // n = 65
+          fit_nd_lines<R, 4, 3, 2, 8, 5, 4>(x, d, afd, bl, dl, dlive, lane);
+        else if (d.KO == 4 && d.KB == 3 && d.KC == 2)               // n = 33
+          fit_nd_lines<R, 2, 2, 1, 4, 3, 2>(x, d, afd, bl, dl, dlive, lane);
+        else if (d.KO == 2 && d.KB == 2 && d.KC == 1)               // n = 17
+          fit_nd_lines<R, 1, 1, 1, 2, 2, 1>(x, d, afd, bl, dl, dlive, lane);
+        else if (MTO >= 8 && d.KO == 16 && d.KB == 9 && d.KC == 8)  // n = 129
+          fit_nd_lines<R, 8, 5, 4, 16, 9, 8>(x, d, afd, bl, dl, dlive, lane);
+        else
+          fit_nd_lines<R, MTO, MTB, MTC, 0, 0, 0>(x, d, afd, bl, dl, dlive, lane);
+      }
+      __syncthreads();
+    }
+    // Finite check (interp.jl:40): c_{0..0} carries a non-zero weight of every input, so it is non-finite iff some
+    // input is.  Rare path: the CTA scans the (not yet overwritten) input array for the first offending real.
+    if (prm.bad) {
+      if (tid == 0) s_flag = 0;
+      __syncthreads();
+      for (int i = tid; i < prm.fits * prm.E; i += blockDim.x) {
+        const int fi = i / prm.E, e = i - fi * prm.E;
+        if (!(fabs((double)x[(size_t)fi * prm.fit_reals + e]) <= 1.79769313486231570815e308)) s_flag = 1;
+      }
+      __syncthreads();
+      if (s_flag) {
+        long long first = 0x7fffffffffffffffLL;
+        for (int i = tid; i < reals; i += blockDim.x)
+          if (!(fabs((double)g[i]) <= 1.79769313486231570815e308)) {
+            first = i;
+            break;
+          }
+        if (first != 0x7fffffffffffffffLL) atomicMin(prm.bad, prm.idx_base + f * (long long)reals + first);
+      }
+    }
+    R* o = dst + f * (long long)reals;
+    double mx = 0.0;
+    if (prm.maxabs) {
+      // infnorm of every element (interp.jl:74-75): complex modulus, max over the K components
+      const int E = prm.E;
+      for (int el = tid; el < reals / E; el += blockDim.x) {
+        const R* ce = x + (size_t)el * E;
+        for (int k = 0; k < prm.K; ++k) {
+          const double a = prm.cplx ? hypot((double)ce[2 * k], (double)ce[2 * k + 1]) : fabs((double)ce[k]);
+          mx = a > mx ? a : mx;
+        }
+      }
+    }
+    for (int i = tid; i < reals; i += blockDim.x) o[i] = x[i];
+    if (prm.maxabs) {
+      for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      if (lane == 0) s_red[warp] = mx;
+      __syncthreads();
+      if (tid == 0) {
+        double m = 0.0;
+        for (int w = 0; w < nwarps; ++w) m = fmax(m, s_red[w]);
+        prm.maxabs[f] = m;
+      }
+    }
+    __syncthreads();  // every thread has read this buffer: it may be refilled
+    if (!dbl && fn < prm.howmany) xnext = fit_nd_load_async<R>(bufs, src + fn * (long long)reals, reals);
+  }
+}
+
+}  // namespace fastcheb
