@@ -648,8 +648,14 @@ def main():
         # the other ranks are idle at the barrier)
         if distributed and not jac:
             barrier()
+            # the other ranks wait on the rendezvous store (a CPU-side wait): an NCCL barrier would keep a spinning kernel
+            # resident on their GPUs, which are about to be driven by rank 0
+            store = dist.distributed_c10d._get_default_store()
             if rank == 0:
                 e2e["single_process"] = single_process_e2e(L, _capi, carr, lb_, ub_, world, Be, N, E, hp)
+                store.set("fastcheb_single_process_done", "1")
+            else:
+                store.wait(["fastcheb_single_process_done"])
             barrier()
 
     if rank == 0:

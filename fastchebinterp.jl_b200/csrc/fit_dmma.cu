@@ -43,10 +43,10 @@ int fit_slot_map(int n, int dtype) {
 
 // Folded, normalised REDFT00 matrices of size n in A-fragment order (parts O | B | C, or P | Q | B | C when map != 0):
 // the host-side builder shared by the batched 1-D kernel (fit_dmma.cuh) and the resident N-d kernel (fit_nd.cuh).
-void fit_afrag_host(int n, int map, std::vector<double>& h, int* ko_out, int* kb_out, int* kc_out) {
-  const bool split = map != 0;
+void fit_afrag_host(int n, int map, bool split, std::vector<double>& h, int* ko_out, int* kb_out, int* kc_out) {
   const int N = n - 1, H = N / 2;
   const bool two = N >= 4 && N % 4 == 0;  // the even half folds once more
+  split = split && two;                   // parts P, Q exist for the twice-folded form only
   // folded inputs (= outputs) of each part
   const int Jo = (N + 1) / 2;
   const int Jb = two ? H / 2 + 1 : N / 2 + 1;
@@ -111,7 +111,7 @@ int get_afrag(int dev, int n, int map, AFrag* out) {
   }
   AFrag a;
   std::vector<double> h;
-  fit_afrag_host(n, map, h, &a.ko, &a.kb, &a.kc);
+  fit_afrag_host(n, map, map != 0, h, &a.ko, &a.kb, &a.kc);
   a.doubles = h.size();
   FC_CUDA(cudaMalloc(&a.d, h.size() * sizeof(double)));
   FC_CUDA(cudaMemcpy(a.d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));

@@ -12,9 +12,10 @@ namespace fastcheb {
 // only): max |c| of every handled fit.
 int fit_dmma_1d(const DeviceInfo* di, int dev, int n, int E, long long howmany, int dtype, const void* vals,
                 void* coefs, long long* bad_dev, long long idx_base, double* fit_max_dev, cudaStream_t st, long long* done);
-// Folded, normalised REDFT00 matrices of size n in mma.sync A-fragment order (map 0: parts O | B | C; see fit_dmma.cuh)
-// and the k-step counts of the parts (kc == 0: the even half is folded once only).
-void fit_afrag_host(int n, int map, std::vector<double>& h, int* ko, int* kb, int* kc);
+// Folded, normalised REDFT00 matrices of size n in mma.sync A-fragment order (parts O | B | C, or — split, 4 | n-1 —
+// P | Q | B | C; slot map `map`, see fit_dmma.cuh) and the k-step counts of the parts (kc == 0: the even half is folded
+// once only, and there is no split).
+void fit_afrag_host(int n, int map, bool split, std::vector<double>& h, int* ko, int* kb, int* kc);
 
 // Resident N-d / long-line fit (fit_nd.cuh): `howmany` arrays of dims[0] x .. x dims[ndim-1] elements of E inline reals.
 // *handled = false when the shape is not covered (an array does not fit shared memory, a dimension is too long); the

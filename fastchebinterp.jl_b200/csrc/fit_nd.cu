@@ -41,7 +41,7 @@ int get_matrices(int dev, std::vector<int> ns, const NdMatrices** out) {
   for (int n : ns) {
     std::vector<double> h;
     int ko, kb, kc;
-    fit_afrag_host(n, 0, h, &ko, &kb, &kc);
+    fit_afrag_host(n, 0, true, h, &ko, &kb, &kc);  // twice-folded sizes: the odd half as parts P, Q (fit_nd.cuh)
     m.off.push_back((int)all.size());
     m.ko.push_back(ko);
     m.kb.push_back(kb);
@@ -67,13 +67,14 @@ cudaError_t launch(const FitNdParams& prm, int grid, int threads, size_t smem, c
   return cudaGetLastError();
 }
 
-// size class of the accumulators: 0: n <= 65 (any n), 1: n <= 129, 2: n <= 257 (classes 1, 2: 4 | n-1 only)
+// size class of the accumulators: 0: n <= 65 (any n), 1: n <= 129, 2: n <= 257 (sizes above 65: 4 | n-1 only, so that
+// part O — MTO tiles — is needed for once-folded sizes n <= 65 only; twice-folded sizes use MTC tiles for P, Q, C)
 template <typename R>
 cudaError_t dispatch(int cls, const FitNdParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
   switch (cls) {
     case 0: return launch<R, 4, 4, 2>(prm, grid, threads, smem, st, bps);
-    case 1: return launch<R, 8, 5, 4>(prm, grid, threads, smem, st, bps);
-    case 2: return launch<R, 16, 9, 8, true>(prm, grid, threads, smem, st, bps);  // matrices from global memory / L2
+    case 1: return launch<R, 4, 5, 4>(prm, grid, threads, smem, st, bps);
+    case 2: return launch<R, 4, 9, 8, true>(prm, grid, threads, smem, st, bps);  // matrices from global memory / L2
   }
   return cudaErrorInvalidValue;
 }
@@ -119,7 +120,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
   const NdMatrices* mats = nullptr;
   FC_TRY(get_matrices(dev, ns, &mats));
   const size_t af_bytes = cls == 2 ? 0 : (((size_t)mats->doubles * 8 + 15) / 16) * 16;  // class 2 reads them from L2
-  const size_t budget = std::min<size_t>(di->smem_optin, kSmemOptinMax) - 2048;
+  const size_t budget = std::min<size_t>(di->smem_optin, kSmemOptinMax) - 3072;
   if (lines) {  // as many lines per block as fit next to the matrices (a multiple of the 16- / 32-line MMA blocks)
     const long long room = ((long long)budget - (long long)af_bytes - 256) / (long long)(reals * rs);
     if (room < LB) LB = room / 32 * 32;
@@ -139,7 +140,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     prm.howmany = narr;
     prm.bad = bad_dev;
     prm.idx_base = idx_base + first_fit * reals;
-    prm.maxabs = (maxabs_dev && fits_per_arr == 1) ? maxabs_dev + first_fit : nullptr;
+    prm.maxabs = maxabs_dev ? maxabs_dev + first_fit : nullptr;  // indexed by array (N-d) or by array * fits + fit (line blocks)
     prm.ndim = ndim;
     prm.E = E;
     prm.K = K;
@@ -162,40 +163,67 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
         fd.afrag = mats->off[i];
       }
     }
-    // warps per CTA: the passes are separated by CTA barriers, so the line groups of a pass should divide evenly among
-    // the warps (65 lines = 10 groups: 5 warps, not 8); FASTCHEB_FITND_WARPS overrides (experiments)
+    // Team geometry.  The passes of an array are separated by barriers of the team that owns it, so the line groups
+    // of a pass should divide evenly among the team's warps (65 lines = 10 groups: 2 or 5 warps, not 4 or 8), and an
+    // SM wants ~12-16 warps in flight: small arrays run several teams per CTA (one copy of the matrices), large ones
+    // one team of up to 8 warps.  FASTCHEB_FITND_WARPS / _TEAMS / _NBUF override (experiments).
     const int gb = dtype == FASTCHEB_F64 ? 2 : 4;
-    int warps = 8;
+    const size_t bufBytes = (((size_t)arr_reals * rs + 15) / 16) * 16 + 16;
+    const size_t fixed = 1024 + af_bytes;
+    const int max_warps = 8;  // launch bounds of the kernel: 256 threads
+    if (fixed + bufBytes > budget) return -1;
+    auto waste = [&](int w) {
+      long long slots = 0, work = 0;
+      for (int d = 0; d < ndim; ++d)
+        if (dims[d] > 1) {
+          const long long nlines = arr_reals / dims[d];
+          const long long groups = (nlines + 8 * gb - 1) / (8 * gb) * gb;
+          slots += (groups + w - 1) / w * w * (long long)dims[d];  // rounds x warps, weighted by the work of a line
+          work += groups * (long long)dims[d];
+        }
+      return (double)slots / (double)std::max<long long>(work, 1);
+    };
+    // Measured on B200 (65 x 65 Float64 batches, tools/probe_fit_nd.py): one team per CTA with 4-5 warps and as many
+    // CTAs per SM as shared memory allows (4) gives 37-38 % of HBM bandwidth; 6 teams of 2 warps in one CTA 32 %, 8 warps
+    // with two buffers 30-32 %.  So: one team per CTA, the warp count in 4..8 with the fewest idle barrier rounds
+    // (small arrays: 4 or 5, so that several CTAs share an SM).
+    int warps = 4, teams = 1, nbuf = 1;
     {
-      long long best = -1;
-      for (int w = 8; w >= 4; --w) {
-        long long slots = 0;
-        for (int d = 0; d < ndim; ++d)
-          if (dims[d] > 1) {
-            const long long nlines = arr_reals / dims[d];
-            const long long groups = (nlines + 8 * gb - 1) / (8 * gb) * gb;
-            slots += (groups + w - 1) / w * w * (long long)dims[d];  // rounds x warps, weighted by the work of a line
-          }
-        if (best < 0 || slots < best) {
-          best = slots;
+      // small arrays: 4 warps (128 threads x 128 registers: four CTAs share an SM; 5 warps would balance 10 line groups
+      // exactly but leave room for three CTAs only — measured 34 % against 38 %)
+      const bool small = fixed + bufBytes <= budget / 4;
+      double best = 1e30;
+      for (int w = small ? 4 : 8; w >= 4; --w) {
+        const double cost = waste(w);
+        if (cost < best - 1e-9) {
+          best = cost;
           warps = w;
         }
       }
-      if (const char* t = getenv("FASTCHEB_FITND_WARPS")) {
-        const int v = atoi(t);
-        if (v >= 1 && v <= 8) warps = v;
+    }
+    if (const char* t = getenv("FASTCHEB_FITND_WARPS")) {
+      const int v = atoi(t);
+      if (v >= 1 && v <= 8) {
+        warps = v;
+        teams = std::max<int>(1, std::min<int>({(int)((budget - fixed) / bufBytes), max_warps / v, 15}));
       }
     }
-    const int threads = warps * 32;
-    const size_t bufBytes = (((size_t)arr_reals * rs + 15) / 16) * 16 + 16;
-    // two buffers (the next array loads during the transform) when both fit and leave room for a second CTA per SM
-    int nbuf = (128 + af_bytes + 2 * bufBytes <= budget / 2 + 1024 || (narr > 2LL * di->sms && 128 + af_bytes + 2 * bufBytes <= budget)) ? 2 : 1;
+    if (const char* t = getenv("FASTCHEB_FITND_TEAMS")) {
+      const int v = atoi(t);
+      if (v >= 1 && v <= 15 && v * warps <= max_warps && fixed + (size_t)v * bufBytes <= budget) teams = v;
+    }
+    // a second buffer (the next array loads during the transform) only when the array is too large for a second CTA
+    // on the SM anyway
+    if (fixed + bufBytes > budget / 2 && fixed + (size_t)teams * 2 * bufBytes <= budget && narr > (long long)di->sms * teams) nbuf = 2;
     if (const char* t = getenv("FASTCHEB_FITND_NBUF")) {
       const int v = atoi(t);
-      if (v == 1 || (v == 2 && 128 + af_bytes + 2 * bufBytes <= budget)) nbuf = v;
+      if (v == 1 || (v == 2 && fixed + (size_t)teams * 2 * bufBytes <= budget)) nbuf = v;
     }
     prm.nbuf = nbuf;
-    const size_t smem = 128 + af_bytes + (size_t)nbuf * bufBytes;
+    prm.teams = teams;
+    prm.team_warps = warps;
+    const int threads = warps * teams * 32;
+    const size_t smem = fixed + (size_t)teams * nbuf * bufBytes;
     int bps = 0;
     cudaError_t e = dtype == FASTCHEB_F64 ? dispatch<double>(cls, prm, 0, threads, smem, st, &bps)
                                           : dispatch<float>(cls, prm, 0, threads, smem, st, &bps);
@@ -204,7 +232,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
       if (getenv("FASTCHEB_DEBUG")) fprintf(stderr, "fit_nd: not launchable (%s, %d CTAs/SM, %zu B)\n", cudaGetErrorString(e), bps, smem);
       return -1;  // not launchable: the caller falls back
     }
-    const int grid = (int)std::max<long long>(1, std::min<long long>(narr, (long long)di->sms * bps));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((narr + teams - 1) / teams, (long long)di->sms * bps));
     e = dtype == FASTCHEB_F64 ? dispatch<double>(cls, prm, grid, threads, smem, st, nullptr)
                               : dispatch<float>(cls, prm, grid, threads, smem, st, nullptr);
     if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "resident DCT-I kernel launch failed: %s", cudaGetErrorString(e));
@@ -219,7 +247,6 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     return FASTCHEB_OK;
   }
   // 1-D: blocks of LB lines, then the remaining lines as one smaller block
-  if (maxabs_dev) return FASTCHEB_OK;  // per-line maxima of line blocks are not produced here: generic path
   long long done = 0;
   if (arrays > 0) {
     const int rc = run(vals, coefs, arrays, per_array, 0, LB);

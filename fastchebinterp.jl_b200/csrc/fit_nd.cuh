@@ -51,6 +51,7 @@ struct FitNdParams {
   int reals;            // reals per array = E prod n (x lines per block for batches of 1-D lines)
   int fits, fit_reals;  // independent fits in one array (1-D line blocks: > 1) and reals per fit
   int nbuf;             // array buffers in shared memory (2: the next array loads while this one is transformed)
+  int teams, team_warps;  // a CTA = teams x team_warps warps; a team owns one array at a time
   FitNdDim dim[kFitNdMaxDims];
 };
 
@@ -68,49 +69,74 @@ __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const doub
   const int KO = CT ? CKO : d.KO, KB = CT ? CKB : d.KB, KC = CT ? CKC : d.KC;
   const int MO = (KO + 1) / 2, MB = (KB + 1) / 2, MC = (KC + 1) / 2;
   const bool two = CT ? (CKC > 0) : (d.two != 0);
-  const int Jo = (N + 1) / 2;                  // inputs of part O: j < Jo
+  const int Jo = (N + 1) / 2;                  // inputs of part O (once-folded): j < Jo
   const int Jb = two ? H / 2 + 1 : N / 2 + 1;  // inputs of part B
-  double accO[MTO][2], accB[MTB][2], accC[MTC][2];
+  // once-folded: accO = part O (MO tiles).  twice-folded: the odd half is split by the parity of the input index,
+  //   P_l = sum_i Mp[l][i] b_{2i},  Q_l = sum_i Mq[l][i] b_{2i+1}  (l, i < N/4),   C[2l+1] = P_l + Q_l,  C[N-2l-1] = P_l - Q_l
+  // (cos(pi (N-k) j / N) = (-1)^j cos(pi k j / N)): accO[0..MC) = P, accQ = Q — 39 instead of 55 DMMAs per 8 lines at n = 65.
+  constexpr int MTP = MTO > MTC ? MTO : MTC;  // accO holds part O (MTO tiles) or part P (MTC tiles)
+  double accO[MTP][2], accQ[MTC][2], accB[MTB][2], accC[MTC][2];
 #pragma unroll
-  for (int m = 0; m < MTO; ++m) accO[m][0] = accO[m][1] = 0.0;
+  for (int m = 0; m < MTP; ++m) accO[m][0] = accO[m][1] = 0.0;
 #pragma unroll
   for (int m = 0; m < MTB; ++m) accB[m][0] = accB[m][1] = 0.0;
 #pragma unroll
-  for (int m = 0; m < MTC; ++m) accC[m][0] = accC[m][1] = 0.0;
-  const double* aO = af + lane;
-  const double* aB = aO + MO * KO * 32;
+  for (int m = 0; m < MTC; ++m) accC[m][0] = accC[m][1] = accQ[m][0] = accQ[m][1] = 0.0;
+  const double* aO = af + lane;  // once-folded: O | B;  twice-folded: P | Q | B | C
+  const double* aQ = aO + MC * KC * 32;
+  const double* aB = two ? aQ + MC * KC * 32 : aO + MO * KO * 32;
   const double* aC = aB + MB * KB * 32;
   const R* z = x + bl;
-  const int KMAX = KO > KB ? KO : KB;
+  const int KMAX = two ? KB : (KO > KB ? KO : KB);  // twice-folded: KC <= KB
   auto step = [&](int ks) {
     const int j = 4 * ks + c;
     // beyond the folded range the matrix columns are zero: the operand only has to be finite, read element 0
-    const int jj = (j < Jo || j < Jb) ? j : 0;
+    const int jj = ((!two && j < Jo) || j < Jb) ? j : 0;
     const R r1 = z[jj * s], r2 = z[(N - jj) * s];
-    R r3 = R(0), r4 = R(0);
+    R r3 = R(0), r4 = R(0), p1 = R(0), p2 = R(0), q1 = R(0), q2 = R(0);
     if (two) {
-      const int j2 = j <= H ? j : 0;
-      r3 = z[(H - j2) * s];
-      r4 = z[(H + j2) * s];
+      r3 = z[(H - jj) * s];
+      r4 = z[(H + jj) * s];
+      const int i2 = (ks < KC && 4 * j < N) ? 2 * j : 0;  // parts P, Q: slot i = j carries b_{2i}, b_{2i+1}
+      p1 = z[i2 * s];
+      p2 = z[(N - i2) * s];
+      q1 = z[(i2 + 1) * s];
+      q2 = z[(N - i2 - 1) * s];
     }
     // the A fragments of this k-step, all loaded before the first DMMA (the first entry of the matrices where the part
-    // has no such tile: a once-folded n has no part C at all; those values are never used)
-    double vO[MTO], vB[MTB], vC[MTC];
+    // has no such tile; those values are never used)
+    double vO[MTP], vQ[MTC], vB[MTB], vC[MTC];
+    if (two) {
 #pragma unroll
-    for (int m = 0; m < MTO; ++m) vO[m] = *((m < MO && ks < KO) ? aO + (m * KO + ks) * 32 : aO);
+      for (int m = 0; m < MTC; ++m) {
+        vO[m] = *((m < MC && ks < KC) ? aO + (m * KC + ks) * 32 : aO);
+        vQ[m] = *((m < MC && ks < KC) ? aQ + (m * KC + ks) * 32 : aO);
+        vC[m] = *((m < MC && ks < KC) ? aC + (m * KC + ks) * 32 : aO);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < MTO; ++m) vO[m] = *((m < MO && ks < KO) ? aO + (m * KO + ks) * 32 : aO);
+    }
 #pragma unroll
     for (int m = 0; m < MTB; ++m) vB[m] = *((m < MB && ks < KB) ? aB + (m * KB + ks) * 32 : aO);
-#pragma unroll
-    for (int m = 0; m < MTC; ++m) vC[m] = *((m < MC && ks < KC) ? aC + (m * KC + ks) * 32 : aO);
     const double x1 = (double)r1, x2 = (double)r2;
-    const double fo = __dsub_rn(x1, x2);
-    double fb = __dadd_rn(x1, x2), fc = 0.0;
+    double fb = __dadd_rn(x1, x2);
     if (two) {
       const double a2 = __dadd_rn((double)r3, (double)r4);
-      fc = __dsub_rn(fb, a2);
+      const double fc = __dsub_rn(fb, a2);
       fb = __dadd_rn(fb, a2);
-    }
-    if (ks < KO) {
+      if (ks < KC) {
+        const double fp = __dsub_rn((double)p1, (double)p2), fq = __dsub_rn((double)q1, (double)q2);
+#pragma unroll
+        for (int m = 0; m < MTC; ++m)
+          if (m < MC) {
+            dmma884(accO[m][0], accO[m][1], vO[m], fp);
+            dmma884(accQ[m][0], accQ[m][1], vQ[m], fq);
+            dmma884(accC[m][0], accC[m][1], vC[m], fc);
+          }
+      }
+    } else if (ks < KO) {
+      const double fo = __dsub_rn(x1, x2);
 #pragma unroll
       for (int m = 0; m < MTO; ++m)
         if (m < MO) dmma884(accO[m][0], accO[m][1], vO[m], fo);
@@ -120,15 +146,10 @@ __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const doub
       for (int m = 0; m < MTB; ++m)
         if (m < MB) dmma884(accB[m][0], accB[m][1], vB[m], fb);
     }
-    if (ks < KC) {
-#pragma unroll
-      for (int m = 0; m < MTC; ++m)
-        if (m < MC) dmma884(accC[m][0], accC[m][1], vC[m], fc);
-    }
   };
   if constexpr (CT) {
 #pragma unroll
-    for (int ks = 0; ks < (CKO > CKB ? CKO : CKB); ++ks) step(ks);
+    for (int ks = 0; ks < (CKC > 0 ? CKB : (CKO > CKB ? CKO : CKB)); ++ks) step(ks);
   } else {
 #pragma unroll 2
     for (int ks = 0; ks < KMAX; ++ks) step(ks);
@@ -139,20 +160,29 @@ __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const doub
   for (int h = 0; h < 2; ++h) {
     if (!dlive[h]) continue;
     R* y = x + dl[h];
+    if (two) {
 #pragma unroll
-    for (int m = 0; m < MTO; ++m) {
-      const int k = 2 * (8 * m + q) + 1;
-      if (m < MO && k <= N) y[k * s] = (R)accO[m][h];
+      for (int m = 0; m < MTC; ++m) {
+        const int l = 8 * m + q;
+        if (m < MC && 4 * l < N) {
+          const double P = accO[m][h], Q = accQ[m][h];
+          y[(2 * l + 1) * s] = (R)__dadd_rn(P, Q);
+          y[(N - 2 * l - 1) * s] = (R)__dsub_rn(P, Q);
+        }
+        const int k = 4 * l + 2;
+        if (m < MC && k <= N) y[k * s] = (R)accC[m][h];
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < MTO; ++m) {
+        const int k = 2 * (8 * m + q) + 1;
+        if (m < MO && k <= N) y[k * s] = (R)accO[m][h];
+      }
     }
 #pragma unroll
     for (int m = 0; m < MTB; ++m) {
       const int k = SB * (8 * m + q);
       if (m < MB && k <= N) y[k * s] = (R)accB[m][h];
-    }
-#pragma unroll
-    for (int m = 0; m < MTC; ++m) {
-      const int k = 4 * (8 * m + q) + 2;
-      if (m < MC && k <= N) y[k * s] = (R)accC[m][h];
     }
   }
 }
@@ -162,7 +192,7 @@ __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const doub
 // by element — arrays of an odd number of reals (65 x 65 doubles = 33 800 B) start at every other 8-byte offset.
 // Returns the shifted base.  Every thread commits one group.
 template <typename R>
-__device__ __forceinline__ R* fit_nd_load_async(unsigned char* buf16, const R* g, int reals) {
+__device__ __forceinline__ R* fit_nd_load_async(unsigned char* buf16, const R* g, int reals, int tid, int nthr) {
   const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(g) & 15u);
   R* x = reinterpret_cast<R*>(buf16 + mis);
   int head = (int)(((16u - mis) & 15u) / sizeof(R));
@@ -170,9 +200,9 @@ __device__ __forceinline__ R* fit_nd_load_async(unsigned char* buf16, const R* g
   const int nvec = (int)(((size_t)(reals - head) * sizeof(R)) / 16);
   const int per = 16 / (int)sizeof(R);
   const int tail0 = head + nvec * per;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+  for (int i = tid; i < nvec; i += nthr)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(x + head + i * per)), "l"(g + head + i * per) : "memory");
-  for (int i = threadIdx.x; i < head + (reals - tail0); i += blockDim.x) {
+  for (int i = tid; i < head + (reals - tail0); i += nthr) {
     const int e = i < head ? i : tail0 + (i - head);
     if constexpr (sizeof(R) == 8)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(x + e)), "l"(g + e) : "memory");
@@ -183,43 +213,56 @@ __device__ __forceinline__ R* fit_nd_load_async(unsigned char* buf16, const R* g
   return x;
 }
 
-// MTO/MTB/MTC: accumulator m-tiles of parts O / B / C the instantiation provides (n <= 16 MTO + 1).
+// MTO/MTB/MTC: accumulator m-tiles the instantiation provides for part O (once-folded sizes, n <= 16 MTO + 1), part B and
+// parts P / Q / C (twice-folded sizes).
 // AFG: the matrices are too large for shared memory next to the array (n > 129: 130-200 KB) and are read from global
 // memory instead — they are shared by every CTA and stay in L2.
 // Two array buffers when they fit (prm.nbuf == 2): the next array's copy is in flight while the current one is
 // transformed.
+// TEAMS: a CTA is cut into prm.teams teams of prm.team_warps warps; a team owns one array at a time (its own buffers, its
+// own named barrier), the matrices are shared by the whole CTA.  Small arrays (65 x 65: 10 line groups per pass) keep
+// only 2 warps busy without idle barrier rounds, so an SM runs 6 such teams side by side in ONE CTA with ONE copy of the
+// matrices, instead of 4 CTAs of 4 half-idle warps with a copy each.
 template <typename R, int MTO, int MTB, int MTC, bool AFG>
 __global__ void __launch_bounds__(256) fit_nd_kernel(const __grid_constant__ FitNdParams prm) {
   extern __shared__ __align__(16) unsigned char fastcheb_smem[];
-  // [128-byte header: 8 partial maxima | flag] [matrices unless AFG] [array buffers, 16-byte aligned, 16 bytes of slack]
-  // (no static shared memory: the kernel is launched with the opt-in maximum of dynamic shared memory)
-  double* s_red = reinterpret_cast<double*>(fastcheb_smem);
-  int& s_flag = *reinterpret_cast<int*>(fastcheb_smem + 64);
-  double* af_s = reinterpret_cast<double*>(fastcheb_smem + 128);
-  unsigned char* bufs = fastcheb_smem + 128 + (AFG ? 0 : (((size_t)prm.afragDoubles * 8 + 15) / 16) * 16);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  if constexpr (!AFG)
-    for (int i = tid; i < prm.afragDoubles; i += blockDim.x) af_s[i] = prm.afrag[i];
+  // [1 KB header: per team 8 partial maxima + flag] [matrices unless AFG] [array buffers, 16-byte aligned, 16 bytes of
+  // slack]  (no static shared memory: the kernel is launched with the opt-in maximum of dynamic shared memory)
+  const int team_thr = prm.team_warps * 32;
+  const int team = threadIdx.x / team_thr;
+  const int tid = threadIdx.x - team * team_thr, lane = tid & 31, warp = tid >> 5, nwarps = prm.team_warps;
+  double* s_red = reinterpret_cast<double*>(fastcheb_smem) + team * 8;
+  int& s_flag = *(reinterpret_cast<int*>(fastcheb_smem + 768) + team);
+  double* af_s = reinterpret_cast<double*>(fastcheb_smem + 1024);
   const int reals = prm.reals;
+  const size_t bufBytes = (((size_t)reals * sizeof(R) + 15) / 16) * 16 + 16;
+  unsigned char* bufs = fastcheb_smem + 1024 + (AFG ? 0 : (((size_t)prm.afragDoubles * 8 + 15) / 16) * 16) +
+                        (size_t)team * prm.nbuf * bufBytes;
+  if constexpr (!AFG) {
+    for (int i = threadIdx.x; i < prm.afragDoubles; i += blockDim.x) af_s[i] = prm.afrag[i];
+    __syncthreads();  // the only CTA-wide barrier
+  }
+  // barrier of this team (named barriers 1..15; the team is the whole CTA when prm.teams == 1)
+  auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_thr) : "memory"); };
   const R* src = reinterpret_cast<const R*>(prm.src);
   R* dst = reinterpret_cast<R*>(prm.dst);
-  const size_t bufBytes = (((size_t)reals * sizeof(R) + 15) / 16) * 16 + 16;
   const bool dbl = prm.nbuf == 2;
+  const long long first = (long long)blockIdx.x * prm.teams + team, stride = (long long)gridDim.x * prm.teams;
   R* xnext = nullptr;
-  if ((long long)blockIdx.x < prm.howmany) xnext = fit_nd_load_async<R>(bufs, src + (long long)blockIdx.x * reals, reals);
+  if (first < prm.howmany) xnext = fit_nd_load_async<R>(bufs, src + first * reals, reals, tid, team_thr);
   int it = 0;
-  for (long long f = blockIdx.x; f < prm.howmany; f += gridDim.x, ++it) {
+  for (long long f = first; f < prm.howmany; f += stride, ++it) {
     const R* g = src + f * (long long)reals;
     R* x = xnext;
-    const long long fn = f + gridDim.x;
+    const long long fn = f + stride;
     if (dbl && fn < prm.howmany) {
       // the other buffer was stored in the previous iteration (all threads passed that iteration's last barrier)
-      xnext = fit_nd_load_async<R>(bufs + (size_t)((it + 1) & 1) * bufBytes, src + fn * (long long)reals, reals);
+      xnext = fit_nd_load_async<R>(bufs + (size_t)((it + 1) & 1) * bufBytes, src + fn * (long long)reals, reals, tid, team_thr);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();  // the array (and, first time, the matrices) are in shared memory
+    team_sync();  // the array is in shared memory
     for (int dd = 0; dd < prm.ndim; ++dd) {
       const FitNdDim& d = prm.dim[dd];
       if (d.n <= 1) continue;  // DHT of length 1 = identity (interp.jl:43)
@@ -253,32 +296,32 @@ __global__ void __launch_bounds__(256) fit_nd_kernel(const __grid_constant__ Fit
         else
           afd = af_s + d.afrag;
         // the common sizes run a fully unrolled copy of the pass
-        if (MTO >= 4 && d.KO == 8 && d.KB == 5 && d.KC == 4)        // n = 65
+        if (d.KO == 8 && d.KB == 5 && d.KC == 4)                    // n = 65
           fit_nd_lines<R, 4, 3, 2, 8, 5, 4>(x, d, afd, bl, dl, dlive, lane);
         else if (d.KO == 4 && d.KB == 3 && d.KC == 2)               // n = 33
           fit_nd_lines<R, 2, 2, 1, 4, 3, 2>(x, d, afd, bl, dl, dlive, lane);
         else if (d.KO == 2 && d.KB == 2 && d.KC == 1)               // n = 17
           fit_nd_lines<R, 1, 1, 1, 2, 2, 1>(x, d, afd, bl, dl, dlive, lane);
-        else if (MTO >= 8 && d.KO == 16 && d.KB == 9 && d.KC == 8)  // n = 129
-          fit_nd_lines<R, 8, 5, 4, 16, 9, 8>(x, d, afd, bl, dl, dlive, lane);
+        else if (MTB >= 5 && d.KO == 16 && d.KB == 9 && d.KC == 8)  // n = 129
+          fit_nd_lines<R, 4, 5, 4, 16, 9, 8>(x, d, afd, bl, dl, dlive, lane);
         else
           fit_nd_lines<R, MTO, MTB, MTC, 0, 0, 0>(x, d, afd, bl, dl, dlive, lane);
       }
-      __syncthreads();
+      team_sync();
     }
     // Finite check (interp.jl:40): c_{0..0} carries a non-zero weight of every input, so it is non-finite iff some
     // input is.  Rare path: the CTA scans the (not yet overwritten) input array for the first offending real.
     if (prm.bad) {
       if (tid == 0) s_flag = 0;
-      __syncthreads();
-      for (int i = tid; i < prm.fits * prm.E; i += blockDim.x) {
+      team_sync();
+      for (int i = tid; i < prm.fits * prm.E; i += team_thr) {
         const int fi = i / prm.E, e = i - fi * prm.E;
         if (!(fabs((double)x[(size_t)fi * prm.fit_reals + e]) <= 1.79769313486231570815e308)) s_flag = 1;
       }
-      __syncthreads();
+      team_sync();
       if (s_flag) {
         long long first = 0x7fffffffffffffffLL;
-        for (int i = tid; i < reals; i += blockDim.x)
+        for (int i = tid; i < reals; i += team_thr)
           if (!(fabs((double)g[i]) <= 1.79769313486231570815e308)) {
             first = i;
             break;
@@ -288,30 +331,44 @@ __global__ void __launch_bounds__(256) fit_nd_kernel(const __grid_constant__ Fit
     }
     R* o = dst + f * (long long)reals;
     double mx = 0.0;
-    if (prm.maxabs) {
+    if (prm.maxabs && prm.fits == 1) {
       // infnorm of every element (interp.jl:74-75): complex modulus, max over the K components
       const int E = prm.E;
-      for (int el = tid; el < reals / E; el += blockDim.x) {
+      for (int el = tid; el < reals / E; el += team_thr) {
         const R* ce = x + (size_t)el * E;
         for (int k = 0; k < prm.K; ++k) {
           const double a = prm.cplx ? hypot((double)ce[2 * k], (double)ce[2 * k + 1]) : fabs((double)ce[k]);
           mx = a > mx ? a : mx;
         }
       }
+    } else if (prm.maxabs) {
+      // a block of 1-D lines: one thread scans one fit
+      const int E = prm.E;
+      for (int fi = tid; fi < prm.fits; fi += team_thr) {
+        const R* cf = x + (size_t)fi * prm.fit_reals;
+        double m = 0.0;
+        for (int el = 0; el < prm.fit_reals / E; ++el)
+          for (int k = 0; k < prm.K; ++k) {
+            const R* ce = cf + (size_t)el * E;
+            const double a = prm.cplx ? hypot((double)ce[2 * k], (double)ce[2 * k + 1]) : fabs((double)ce[k]);
+            m = a > m ? a : m;
+          }
+        prm.maxabs[f * prm.fits + fi] = m;
+      }
     }
-    for (int i = tid; i < reals; i += blockDim.x) o[i] = x[i];
-    if (prm.maxabs) {
+    for (int i = tid; i < reals; i += team_thr) o[i] = x[i];
+    if (prm.maxabs && prm.fits == 1) {
       for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
       if (lane == 0) s_red[warp] = mx;
-      __syncthreads();
+      team_sync();
       if (tid == 0) {
         double m = 0.0;
         for (int w = 0; w < nwarps; ++w) m = fmax(m, s_red[w]);
         prm.maxabs[f] = m;
       }
     }
-    __syncthreads();  // every thread has read this buffer: it may be refilled
-    if (!dbl && fn < prm.howmany) xnext = fit_nd_load_async<R>(bufs, src + fn * (long long)reals, reals);
+    team_sync();  // every thread has read this buffer: it may be refilled
+    if (!dbl && fn < prm.howmany) xnext = fit_nd_load_async<R>(bufs, src + fn * (long long)reals, reals, tid, team_thr);
   }
 }
 

@@ -106,9 +106,13 @@ def test_multi_fit(fc, orc, dt):
     vals = rng.uniform(-1, 1, (10_007, 65)).astype(dt)
     got, mx = fc.chebcoefs_multi(vals, return_maxabs=True)
     one = fc.chebcoefs(vals, ndim=1, howmany=len(vals))
-    assert np.array_equal(got, one)
-    want = np.stack([orc.chebcoefs(v.astype(np.float64), 1) for v in vals[:50]])
     tol = 1e-13 if dt == np.float64 else 450 * np.finfo(np.float32).eps
+    # the ragged tail of every device's block takes another kernel than the body (same transform, other rounding), so
+    # the split changes last bits at the block boundaries; with one device the partition is the single-GPU one
+    assert np.abs(got - one).max() <= tol * np.abs(one).max()
+    if _ndev(fc) == 1:
+        assert np.array_equal(got, one)
+    want = np.stack([orc.chebcoefs(v.astype(np.float64), 1) for v in vals[:50]])
     assert np.abs(got[:50] - want).max() <= tol * np.abs(want).max()
     assert np.allclose(mx[:50], np.abs(want).max(axis=1), rtol=1e-5 if dt == np.float32 else 1e-12)
     bad = vals.copy()
