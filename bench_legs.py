@@ -201,8 +201,15 @@ def run_all(device: int = 0, quick: bool = False):
     guard("cfg3_eval4d_complex_val", lambda: eval_leg(torch, fastcheb, _capi, device, (17,) * 4, None, True, f64, 1 << 22, False, reps))
     guard("cfg3_eval4d_complex_jac", lambda: eval_leg(torch, fastcheb, _capi, device, (17,) * 4, None, True, f64, 1 << 21, True, reps))
     guard("eval2d_order32_val", lambda: eval_leg(torch, fastcheb, _capi, device, (33, 33), None, False, f64, 1 << 24, False, reps))
-    guard("cfg4_eval1d_order64_f64_val", lambda: eval_leg(torch, fastcheb, _capi, device, (65,), None, False, f64, 1 << 25, False, reps))
-    guard("cfg4_eval1d_order64_f32_val", lambda: eval_leg(torch, fastcheb, _capi, device, (65,), None, False, f32, 1 << 25, False, reps))
+    # configs[4] evaluates FITTED order-64 polynomials: coefficients of an analytic f_i(x) = sin(a x + b),
+    # which the product-basis path accepts; the dense-random variant (no decay: AUTO keeps the bit-exact Clenshaw
+    # kernel, see eval_pb1d.cuh) is reported next to it
+    x64 = fastcheb.chebpoints(64, -1.0, 1.0)
+    c64 = np.asarray(fastcheb.chebinterp(np.sin(2.3 * x64 + 0.4), -1.0, 1.0, tol=0.0, device=device).coefs)
+    guard("cfg4_eval1d_order64_f64_val", lambda: eval_leg(torch, fastcheb, _capi, device, (65,), None, False, f64, 1 << 25, False, reps, coefs=c64))
+    guard("cfg4_eval1d_order64_f32_val", lambda: eval_leg(torch, fastcheb, _capi, device, (65,), None, False, f32, 1 << 25, False, reps,
+                                                          coefs=c64.astype(np.float32)))
+    guard("cfg4_eval1d_order64_dense_random_f64_val", lambda: eval_leg(torch, fastcheb, _capi, device, (65,), None, False, f64, 1 << 25, False, reps))
     for dt, nm in ((f64, "f64"), (f32, "f32")):
         guard(f"cfg4_eval_many_{nm}_val", lambda: eval_many_leg(torch, _capi, device, dt, False, reps))
         if hasattr(_capi.lib(), "fastcheb_eval_many_shared"):

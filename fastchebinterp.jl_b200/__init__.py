@@ -460,7 +460,9 @@ def eval_many(coefs, lb, ub, pts, deriv: bool = False, device: int = 0):
     (eval.jl:63-70 per point; with deriv=True also chebgradient's derivative, eval.jl:174-177).
 
     coefs: (howmany, n) or (howmany, n, K) real/complex — the layout chebcoefs(..., howmany=) returns;
-    lb, ub: scalars (shared box) or length-howmany arrays; pts: (howmany, M) reals.
+    lb, ub: scalars (shared box) or length-howmany arrays; pts: (howmany, M) reals, or (M,) reals SHARED by all
+    polynomials (with a shared box: the batch is then a matrix product on the FP64 tensor cores,
+    fastcheb_eval_many_shared; n <= 65).
     Returns values (howmany, M[, K]) [and derivatives of the same shape]."""
     coefs = _float_vals(coefs)
     if coefs.ndim not in (2, 3):
@@ -470,11 +472,15 @@ def eval_many(coefs, lb, ub, pts, deriv: bool = False, device: int = 0):
     cplx = np.iscomplexobj(coefs)
     rdt = _real_dtype(coefs.dtype)
     pts = np.ascontiguousarray(np.asarray(pts), dtype=rdt)
-    if pts.ndim != 2 or pts.shape[0] != howmany:
-        raise DimensionMismatch("pts must be (howmany, M)")
-    M = pts.shape[1]
     lbv, ubv = np.atleast_1d(np.asarray(lb, dtype=np.float64)), np.atleast_1d(np.asarray(ub, dtype=np.float64))
     per = int(lbv.size > 1 or ubv.size > 1)
+    if pts.ndim == 1 and not per and n <= 65:
+        return _eval_many_shared(coefs, lbv, ubv, pts, deriv, device, howmany, n, K, cplx, rdt)
+    if pts.ndim == 1:
+        pts = np.ascontiguousarray(np.broadcast_to(pts, (howmany, pts.shape[0])))
+    if pts.ndim != 2 or pts.shape[0] != howmany:
+        raise DimensionMismatch("pts must be (howmany, M) or (M,)")
+    M = pts.shape[1]
     if per:
         lbv, ubv = np.broadcast_to(lbv, (howmany,)).copy(), np.broadcast_to(ubv, (howmany,)).copy()
     flat = np.ascontiguousarray(coefs).reshape(-1)
@@ -492,6 +498,30 @@ def eval_many(coefs, lb, ub, pts, deriv: bool = False, device: int = 0):
         err.index = bad
         raise err
     _check(rc, "fastcheb_eval_many: ")
+
+    def shape(a):
+        a = a.view(np.complex64 if rdt == np.float32 else np.complex128) if cplx else a
+        return a.reshape(howmany, M) if K is None else a.reshape(howmany, M, K)
+
+    return (shape(out), shape(outd)) if deriv else shape(out)
+
+
+def _eval_many_shared(coefs, lbv, ubv, pts, deriv, device, howmany, n, K, cplx, rdt):
+    M = pts.shape[0]
+    flat = np.ascontiguousarray(coefs).reshape(-1)
+    flat = flat.view(rdt) if cplx else flat
+    E = (K or 1) * (2 if cplx else 1)
+    out = np.empty((howmany, M, E), dtype=rdt)
+    outd = np.empty((howmany, M, E), dtype=rdt) if deriv else None
+    rc = _capi.lib().fastcheb_eval_many_shared(howmany, n, _dtype_code(rdt), int(cplx), K or 1, flat.ctypes.data, lbv.ctypes.data,
+                                               ubv.ctypes.data, pts.ctypes.data, M, out.ctypes.data,
+                                               outd.ctypes.data if deriv else None, None, _capi.MEM_HOST, device, None)
+    if rc == _capi.EDOMAIN:
+        bad = _capi.error_index()
+        err = ArgumentError(f"{pts[bad]} not in domain {lbv[0]} to {ubv[0]}")
+        err.index = bad
+        raise err
+    _check(rc, "fastcheb_eval_many_shared: ")
 
     def shape(a):
         a = a.view(np.complex64 if rdt == np.float32 else np.complex128) if cplx else a

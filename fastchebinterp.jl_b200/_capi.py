@@ -24,7 +24,7 @@ SYMBOLS = [
     "fastcheb_create", "fastcheb_destroy", "fastcheb_ndim", "fastcheb_dims", "fastcheb_dtype",
     "fastcheb_is_complex", "fastcheb_ncomp", "fastcheb_device", "fastcheb_get_coefs", "fastcheb_set_algo",
     "fastcheb_get_algo", "fastcheb_product_check", "fastcheb_eval", "fastcheb_eval_jac", "fastcheb_eval_grad", "fastcheb_eval_jac_tuple",
-    "fastcheb_eval_async", "fastcheb_eval_jac_async", "fastcheb_eval_many", "fastcheb_eval_vjp", "fastcheb_eval_jvp", "fastcheb_fit", "fastcheb_fit_async", "fastcheb_droptol_shape", "fastcheb_interp", "fastcheb_reinterp", "fastcheb_vandermonde",
+    "fastcheb_eval_async", "fastcheb_eval_jac_async", "fastcheb_eval_many", "fastcheb_eval_many_shared", "fastcheb_eval_vjp", "fastcheb_eval_jvp", "fastcheb_fit", "fastcheb_fit_async", "fastcheb_droptol_shape", "fastcheb_interp", "fastcheb_reinterp", "fastcheb_vandermonde",
     "fastcheb_multi_create", "fastcheb_multi_destroy", "fastcheb_multi_ngpus", "fastcheb_multi_device", "fastcheb_multi_poly",
     "fastcheb_multi_eval", "fastcheb_multi_eval_jac", "fastcheb_multi_eval_grad", "fastcheb_multi_eval_jac_tuple", "fastcheb_multi_fit",
     "fastcheb_peer_alloc", "fastcheb_peer_free", "fastcheb_peer_open", "fastcheb_peer_close", "fastcheb_peer_read",
@@ -86,6 +86,7 @@ def lib() -> ctypes.CDLL:
         "fastcheb_peer_close": (i32, [vp, i32]),
         "fastcheb_peer_read": (i32, [vp, vp, ctypes.c_size_t, i32]),
         "fastcheb_eval_many": (i32, [i64, i64, i32, i32, i32, vp, vp, vp, i32, vp, i64, vp, vp, vp, i32, i32, vp]),
+        "fastcheb_eval_many_shared": (i32, [i64, i64, i32, i32, i32, vp, vp, vp, vp, i64, vp, vp, vp, i32, i32, vp]),
         "fastcheb_vandermonde": (i32, [i32, i64p, i32, vp, i64, dblp, dblp, vp, i64, i32, i32, vp]),
         "fastcheb_eval_vjp": (i32, [vp, vp, i64, vp, vp, vp, i32, vp]),
         "fastcheb_eval_jvp": (i32, [vp, vp, i64, vp, vp, vp, i32, vp]),

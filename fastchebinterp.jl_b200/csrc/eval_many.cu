@@ -47,6 +47,14 @@ __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ 
     SpanDiv<R> sdiv;
     sdiv.init(lb, ub);
     const R span = sdiv.span;
+    // the points of the next chunk are loaded while the current one is evaluated (the recurrence is ~130 dependent FP64
+    // operations per chunk; an unprefetched load at its head stalls the warp for a global-memory latency every time)
+    R xn[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const long long ip = lane + 32 * p;
+      xn[p] = ip < prm.M ? pts[f * prm.M + ip] : lb;
+    }
     for (long long p0 = lane; p0 < prm.M; p0 += 32 * P) {
       R z[P], z2[P];
       bool live[P];
@@ -54,7 +62,9 @@ __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ 
       for (int p = 0; p < P; ++p) {
         const long long ip = p0 + 32 * p;
         live[p] = ip < prm.M;
-        const R x = live[p] ? pts[f * prm.M + ip] : lb;
+        const R x = xn[p];
+        const long long in = ip + 32 * P;
+        xn[p] = in < prm.M ? pts[f * prm.M + in] : lb;
         const bool ok = (lb <= x) && (x <= ub);                       // eval.jl:64 (closed box, NaN fails)
         z[p] = ok ? rsub(sdiv.div(rmul(rsub(x, lb), R(2))), R(1)) : R(0);  // eval.jl:65 (SpanDiv: the IEEE quotient)
         z2[p] = rmul(R(2), z[p]);

@@ -40,14 +40,7 @@ cudaError_t launch_p(const Pb1dParams& prm, const void* h_D, size_t d_count, int
 template <typename R, int AMAX, int EC, bool JAC>
 cudaError_t launch(const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
   // points per thread: the T_a(w) tables are AMAX (2 AMAX with derivatives) registers per point
-  constexpr int P = JAC ? (AMAX == 8 ? 2 : 1) : (AMAX == 8 ? 4 : 2);
-  if constexpr (P > 1 && EC == 1) {
-    static const int forced = [] {  // experiments: FASTCHEB_PB_P=1 runs one point per thread
-      const char* t = getenv("FASTCHEB_PB_P");
-      return t ? atoi(t) : 0;
-    }();
-    if (forced == 1) return launch_p<R, AMAX, EC, 1, JAC>(prm, h_D, d_count, sms, st);
-  }
+  constexpr int P = JAC ? 1 : 2;
   return launch_p<R, AMAX, EC, P, JAC>(prm, h_D, d_count, sms, st);
 }
 

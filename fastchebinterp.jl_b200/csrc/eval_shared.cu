@@ -1,0 +1,337 @@
+// C ABI: many independent 1-D ChebPolys evaluated at ONE SHARED set of points (include/fastcheb.h,
+// fastcheb_eval_many_shared) — `[c.(xs) for c in cs]` with the same xs for every polynomial, e.g. all 10^5 fitted
+// polynomials of BASELINE.json configs[4] sampled on a common grid.
+//
+// Reference per value: (::ChebPoly{1})(x) /root/reference/src/eval.jl:63-70 (domain check :64, affine map :65, Clenshaw
+// :19-31); derivative: chebgradient eval.jl:174-177 (scale :151).
+//
+// With shared points the batch IS a matrix product,  V[f, m] = sum_k C[f, k] T_k(z_m)  (howmany x n times n x M), so it
+// runs on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA) at the pipe's rate instead of the Clenshaw recurrence's
+// 50 % ceiling:
+//   1. cheb_table_kernel: T_k(z_m) (or T_k'(z_m)) for the M points once, into an L2-resident table; z is formed with
+//      the oracle's operation sequence; the domain check happens here;
+//   2. eval_shared_kernel: a CTA owns 128 rows (polynomial x real component); every warp keeps the A fragments of its
+//      16 rows (all n coefficients) in REGISTERS for the whole launch and sweeps the points in tiles of 64 whose table
+//      rows stream through shared memory (cp.async, double-buffered): per k-step 8 B fragments feed 16 DMMAs.  The
+//      k = 0 term (T_0 = 1) initialises the accumulators.  Results leave as 16-byte stores, 64 contiguous bytes per row
+//      and tile.
+// Float32 data runs the same FP64 kernel (coefficients widened once in the A fragments, results rounded at the end).
+// The summation order differs from Clenshaw's: results agree with the oracle within 16 eps sum|c|, not bit for bit.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include "host_util.h"
+#include "ptx_util.cuh"
+
+namespace fastcheb {
+namespace {
+
+constexpr int kSharedKS = 16;   // k-steps: n - 1 <= 64
+constexpr int kSharedPT = 64;   // points per tile
+
+struct TableParams {
+  const void* pts;
+  double* table;   // [M][RS]: T_1..T_{n-1} (zero padded to 4 KS, row stride RS)
+  long long* bad;
+  long long M;
+  int n, RS, der;
+  double lb, ub;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) cheb_table_kernel(const __grid_constant__ TableParams prm) {
+  const R lb = (R)prm.lb, ub = (R)prm.ub;
+  SpanDiv<R> sdiv;
+  sdiv.init(lb, ub);
+  const R* pts = reinterpret_cast<const R*>(prm.pts);
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < prm.M; m += (long long)gridDim.x * blockDim.x) {
+    const R x = pts[m];
+    const bool ok = (lb <= x) && (x <= ub);                                            // eval.jl:64
+    const double z = ok ? (double)rsub(sdiv.div(rmul(rsub(x, lb), R(2))), R(1)) : 0.0;  // eval.jl:65, oracle's sequence
+    if (!ok && prm.bad) atomicMin(prm.bad, m);
+    double* row = prm.table + m * prm.RS;
+    const double z2 = 2.0 * z;
+    double tkm = 1.0, tk = z, dkm = 0.0, dk = 1.0;  // T_0, T_1, T_0', T_1'
+    for (int k = 1; k < prm.n; ++k) {
+      row[k - 1] = prm.der ? dk : tk;
+      const double tn = fma(z2, tk, -tkm);
+      const double dn = fma(z2, dk, 2.0 * tk) - dkm;
+      tkm = tk;
+      tk = tn;
+      dkm = dk;
+      dk = dn;
+    }
+    for (int k = prm.n; k <= prm.RS; ++k) row[k - 1] = 0.0;
+  }
+}
+
+struct SharedParams {
+  const void* coefs;    // [howmany][n][E]
+  const double* table;  // [M][RS]
+  void* out;            // [howmany][M][E]
+  long long rows;       // howmany * E
+  long long M;
+  int n, E, RS, der, chunks;
+  double lb, ub;
+};
+
+// RT: row tiles (of 8 rows) per warp.  RT = 2 halves the B-fragment loads per DMMA but needs ~250 registers (one CTA per
+// SM, whose 8 warps move in lock-step through the tile barriers); RT = 1 fits two CTAs per SM, which overlap each
+// other's epilogues and barriers.
+template <typename R, int RT>
+__global__ void __launch_bounds__(256, RT == 1 ? 2 : 1) eval_shared_kernel(const __grid_constant__ SharedParams prm) {
+  constexpr int kSharedRows = 8 * 8 * RT;  // rows per CTA
+  extern __shared__ __align__(16) unsigned char fastcheb_smem[];
+  double* tile[2] = {reinterpret_cast<double*>(fastcheb_smem),
+                     reinterpret_cast<double*>(fastcheb_smem) + (size_t)kSharedPT * prm.RS};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = lane & 3, q = lane >> 2;
+  const int n = prm.n, E = prm.E, RS = prm.RS;
+  const R* coefs = reinterpret_cast<const R*>(prm.coefs);
+  R* out = reinterpret_cast<R*>(prm.out);
+  const long long ntiles = (prm.M + kSharedPT - 1) / kSharedPT;
+  const long long nblocks = (prm.rows + kSharedRows - 1) / kSharedRows;
+  const long long nchunks = prm.chunks, tpc = (ntiles + nchunks - 1) / nchunks;  // point-tile chunks: more, smaller work items
+  const int tileDoubles = kSharedPT * RS;
+
+  auto load_tile = [&](int b, long long pt) {
+    // the table has ntiles * PT rows allocated (the last tile is zero-padded by the host), RS is a multiple of 2
+    const double* src = prm.table + pt * (long long)tileDoubles;
+    for (int i = tid; i < tileDoubles / 2; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile[b] + 2 * i)), "l"(src + 2 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  for (long long item = blockIdx.x; item < nblocks * nchunks; item += gridDim.x) {
+    const long long blk = item / nchunks, chunk = item - blk * nchunks;
+    const long long pt0 = chunk * tpc, pt1 = pt0 + tpc < ntiles ? pt0 + tpc : ntiles;
+    if (pt0 >= pt1) continue;
+    // A fragments of this warp's RT x 8 rows: lane (c, q) holds C[row q][k = 1 + 4 ks + c]; the k = 0 column separately
+    double A[RT][kSharedKS], c0[RT][2];
+    long long rowq[RT];
+    bool lived[RT][2];
+#pragma unroll
+    for (int t = 0; t < RT; ++t) {
+      const long long r0 = blk * kSharedRows + warp * (8 * RT) + t * 8;
+      rowq[t] = r0 + q;
+      const bool liveq = rowq[t] < prm.rows;
+      const long long f = liveq ? rowq[t] / E : 0;
+      const int e = liveq ? (int)(rowq[t] - f * E) : 0;
+      const R* cr = coefs + (f * n) * E + e;  // element k at cr[k * E]
+#pragma unroll
+      for (int ks = 0; ks < kSharedKS; ++ks) {
+        const int k = 1 + 4 * ks + c;
+        A[t][ks] = (liveq && k < n) ? (double)cr[(long long)k * E] : 0.0;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // D fragment: lane (c, q) holds out[row q][point 2c + h]: the k = 0 coefficient of row q initialises it
+        lived[t][h] = liveq;
+        c0[t][h] = (liveq && !prm.der) ? (double)cr[0] : 0.0;
+      }
+    }
+    __syncthreads();  // the previous block's last tile has been consumed
+    load_tile(0, pt0);
+    for (long long pt = pt0; pt < pt1; ++pt) {
+      const int b = (int)((pt - pt0) & 1);
+      if (pt + 1 < pt1) {
+        load_tile(b ^ 1, pt + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const double* T = tile[b];
+      double acc[RT][kSharedPT / 8][2];
+#pragma unroll
+      for (int t = 0; t < RT; ++t)
+#pragma unroll
+        for (int j = 0; j < kSharedPT / 8; ++j) {
+          acc[t][j][0] = c0[t][0];
+          acc[t][j][1] = c0[t][1];
+        }
+#pragma unroll
+      for (int ks = 0; ks < kSharedKS; ++ks) {
+        if (4 * ks + 1 >= n) break;  // uniform: shorter polynomials stop early
+#pragma unroll
+        for (int j = 0; j < kSharedPT / 8; ++j) {
+          // B fragment: lane (c, q) holds T[point 8 j + q][k = 1 + 4 ks + c]
+          const double bv = T[(8 * j + q) * RS + 4 * ks + c];
+#pragma unroll
+          for (int t = 0; t < RT; ++t) dmma884(acc[t][j][0], acc[t][j][1], A[t][ks], bv);
+        }
+      }
+      // epilogue: lane (c, q) holds points 8 j + 2c, 8 j + 2c + 1 of row q
+      const long long m0 = pt * kSharedPT;
+      const double span = (double)rsub((R)prm.ub, (R)prm.lb);
+#pragma unroll
+      for (int t = 0; t < RT; ++t) {
+        if (!lived[t][0]) continue;
+        const long long f = rowq[t] / E;
+        const int e = (int)(rowq[t] - f * E);
+        R* orow = out + (f * prm.M) * E + e;  // point m at orow[m * E]
+#pragma unroll
+        for (int j = 0; j < kSharedPT / 8; ++j) {
+          const long long m = m0 + 8 * j + 2 * c;
+          double v0 = acc[t][j][0], v1 = acc[t][j][1];
+          if (prm.der) {  // eval.jl:151: d/dx = (d/dz * 2) / (ub - lb)
+            v0 = __ddiv_rn(__dmul_rn(v0, 2.0), span);
+            v1 = __ddiv_rn(__dmul_rn(v1, 2.0), span);
+          }
+          if (E == 1 && m + 1 < prm.M && ((reinterpret_cast<uintptr_t>(orow + m) & (2 * sizeof(R) - 1)) == 0)) {
+            if constexpr (sizeof(R) == 8)
+              *reinterpret_cast<double2*>(orow + m) = make_double2(v0, v1);
+            else
+              *reinterpret_cast<float2*>(orow + m) = make_float2((float)v0, (float)v1);
+          } else {
+            if (m < prm.M) orow[m * E] = (R)v0;
+            if (m + 1 < prm.M) orow[(m + 1) * E] = (R)v1;
+          }
+        }
+      }
+      __syncthreads();  // tile b may be refilled
+    }
+  }
+}
+
+}  // namespace
+}  // namespace fastcheb
+
+using namespace fastcheb;
+
+extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, int is_complex, int ncomp, const void* coefs,
+                                         const double* lb, const double* ub, const void* pts, int64_t M, void* out_v, void* out_d,
+                                         int64_t* status_dev, int mem, int device, void* stream) {
+  if (howmany < 0 || n < 1 || M < 0 || ncomp < 1) return fail(FASTCHEB_EINVAL, "bad size");
+  if (dtype != FASTCHEB_F32 && dtype != FASTCHEB_F64) return fail(FASTCHEB_EINVAL, "bad dtype %d", dtype);
+  if (mem != FASTCHEB_MEM_HOST && mem != FASTCHEB_MEM_DEVICE) return fail(FASTCHEB_EINVAL, "bad mem %d", mem);
+  if (howmany == 0 || M == 0) return FASTCHEB_OK;
+  if (!coefs || !lb || !ub || !pts || !out_v) return fail(FASTCHEB_EINVAL, "null buffer");
+  if (n - 1 > 4 * kSharedKS)
+    return fail(FASTCHEB_EUNSUPPORTED, "fastcheb_eval_many_shared covers n <= %d, got %lld", 4 * kSharedKS + 1, (long long)n);
+  const int E = ncomp * (is_complex ? 2 : 1);
+  const size_t rs = real_size(dtype);
+  const DeviceInfo* di = device_info(device);
+  if (!di) return FASTCHEB_ECUDA;
+  DeviceGuard dg(device);
+  if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // lb / ub: host doubles in host mode, device doubles in device mode (as in fastcheb_eval_many); the kernels take them
+  // by value, so device-mode bounds are read back once (16 bytes)
+  double hlb, hub;
+  if (mem == FASTCHEB_MEM_DEVICE) {
+    FC_CUDA(cudaMemcpyAsync(&hlb, lb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(cudaMemcpyAsync(&hub, ub, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(cudaStreamSynchronize(st));
+  } else {
+    hlb = lb[0];
+    hub = ub[0];
+  }
+  const int KS = (int)((n - 1 + 3) / 4);
+  int RS = 4 * std::max(KS, 1);
+  while (RS % 16 != 4) RS += 2;  // row stride = 4 (mod 16) doubles: the B-fragment loads of a half warp hit 16 distinct banks
+  const long long ntiles = (M + kSharedPT - 1) / kSharedPT;
+  const size_t tableBytes = (size_t)ntiles * kSharedPT * RS * sizeof(double);
+  const size_t cbytes = (size_t)howmany * n * E * rs, pbytes = (size_t)M * rs, obytes = (size_t)howmany * M * E * rs;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const bool host = mem == FASTCHEB_MEM_HOST;
+  const size_t total = al(tableBytes) + (host ? al(cbytes) + al(pbytes) + al(obytes) : 0);
+  char* scratch = nullptr;
+  FC_CUDA(pool_alloc((void**)&scratch, total, st));
+  struct Free {
+    char* p;
+    cudaStream_t st;
+    ~Free() { cudaFreeAsync(p, st); }
+  } fr{scratch, st};
+  double* d_table = (double*)scratch;
+  const void* d_c = coefs;
+  const void* d_p = pts;
+  char* d_o = nullptr;
+  if (host) {
+    char* q = scratch + al(tableBytes);
+    FC_CUDA(cudaMemcpyAsync(q, coefs, cbytes, cudaMemcpyHostToDevice, st));
+    d_c = q;
+    q += al(cbytes);
+    FC_CUDA(cudaMemcpyAsync(q, pts, pbytes, cudaMemcpyHostToDevice, st));
+    d_p = q;
+    q += al(pbytes);
+    d_o = q;
+  }
+  FlagSlot fs;
+  struct Rel {
+    FlagSlot& f;
+    ~Rel() { flag_release(f); }
+  } rel{fs};
+  long long* flag = (long long*)status_dev;
+  if (host) {
+    FC_TRY(flag_acquire(device, &fs));
+    flag = fs.dev;
+  }
+  if (flag) FC_CUDA(set_flag_async(flag, kNoBad, st));
+  FC_CUDA(cudaMemsetAsync(d_table + (size_t)M * RS, 0, tableBytes - (size_t)M * RS * sizeof(double), st));  // padding rows of the last tile
+  const size_t smem = (size_t)2 * kSharedPT * RS * sizeof(double);
+  const long long rows = (long long)howmany * E;
+  // RT = 1 (64 rows per CTA, two CTAs per SM) measured faster than RT = 2 (profiles/r02_eval_shared.txt);
+  // FASTCHEB_SHARED_RT=2 selects the other (experiments)
+  static const int rt = [] {
+    const char* e = getenv("FASTCHEB_SHARED_RT");
+    return e && atoi(e) == 2 ? 2 : 1;
+  }();
+  const long long nblocks = (rows + 64 * rt - 1) / (64 * rt);
+  for (int der = 0; der < (out_d ? 2 : 1); ++der) {
+    TableParams tp;
+    memset(&tp, 0, sizeof tp);
+    tp.pts = d_p;
+    tp.table = d_table;
+    tp.bad = der == 0 ? flag : nullptr;
+    tp.M = M;
+    tp.n = (int)n;
+    tp.RS = RS;
+    tp.der = der;
+    tp.lb = hlb;
+    tp.ub = hub;
+    const int tgrid = (int)std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)di->sms * 4));
+    if (dtype == FASTCHEB_F64)
+      cheb_table_kernel<double><<<tgrid, 256, 0, st>>>(tp);
+    else
+      cheb_table_kernel<float><<<tgrid, 256, 0, st>>>(tp);
+    FC_CUDA(cudaGetLastError());
+    SharedParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.coefs = d_c;
+    sp.table = d_table;
+    sp.out = host ? (void*)(d_o) : (der ? out_d : out_v);
+    sp.rows = rows;
+    sp.M = M;
+    sp.n = (int)n;
+    sp.E = E;
+    sp.RS = RS;
+    sp.der = der;
+    sp.lb = hlb;
+    sp.ub = hub;
+    const void* kern = dtype == FASTCHEB_F64 ? (rt == 2 ? (const void*)eval_shared_kernel<double, 2> : (const void*)eval_shared_kernel<double, 1>)
+                                             : (rt == 2 ? (const void*)eval_shared_kernel<float, 2> : (const void*)eval_shared_kernel<float, 1>);
+    FC_CUDA(ensure_max_smem(kern));
+    int bps = 1;
+    FC_CUDA(cached_occupancy(&bps, kern, 256, smem));
+    const long long slots = (long long)di->sms * std::max(1, bps);
+    // work items = row blocks x point-tile chunks: enough of them that the last wave is a small fraction of the launch
+    long long chunks = 1;
+    while (chunks < ntiles && nblocks * chunks < 16 * slots && (nblocks * chunks) % slots * 8 < slots * 7 && chunks < 8) ++chunks;
+    sp.chunks = (int)chunks;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(nblocks * chunks, slots));
+    void* args[] = {&sp};
+    FC_CUDA(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, st));
+    FC_CUDA(cudaGetLastError());
+    note_launch(2);
+    if (host) FC_CUDA(cudaMemcpyAsync(der ? out_d : out_v, d_o, obytes, cudaMemcpyDeviceToHost, st));
+  }
+  if (!host) return FASTCHEB_OK;  // asynchronous: the caller reads status_dev after synchronising
+  FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  FC_CUDA(cudaStreamSynchronize(st));
+  if (*fs.host != kNoBad) {
+    err_state().index = *fs.host;
+    return fail(FASTCHEB_EDOMAIN, "point %lld not in domain (eval.jl:64)", *fs.host);
+  }
+  return FASTCHEB_OK;
+}

@@ -158,6 +158,16 @@ int fastcheb_eval_many(int64_t howmany, int64_t n, int dtype, int is_complex, in
                        const double* lb, const double* ub, int bounds_per_poly, const void* pts, int64_t M,
                        void* out_v, void* out_d, int64_t* status_dev, int mem, int device, void* stream);
 
+/* fastcheb_eval_many_shared : the same batch when every polynomial is evaluated at the SAME M points and shares one
+ * box — `[c.(xs) for c in cs]`: V[f, m] = sum_k C[f, k] T_k(z_m) is then a (howmany x n) x (n x M) matrix product and runs
+ * on the FP64 tensor cores (n <= 65).  pts: M reals; lb / ub: one pair (host doubles for mem = HOST, device doubles for
+ * mem = DEVICE); out_v / out_d: howmany x M x E.  Status and errors as fastcheb_eval_many (the index is the point index).
+ * Values agree with the per-polynomial Clenshaw evaluation within 16 eps sum|c| (another summation order), not bit
+ * for bit. */
+int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, int is_complex, int ncomp, const void* coefs,
+                              const double* lb, const double* ub, const void* pts, int64_t M, void* out_v, void* out_d,
+                              int64_t* status_dev, int mem, int device, void* stream);
+
 /* ---- the fit ----------------------------------------------------------------------------------
  * fastcheb_fit : chebcoefs(vals) (interp.jl:39-71) for `howmany` independent arrays stored back to
  * back, each `dims[0] x ... x dims[ndim-1]` elements of E inline reals (so `chebinterp_v1`'s

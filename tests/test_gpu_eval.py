@@ -320,3 +320,44 @@ def test_cfg5_fit_then_eval_many(fc):
     v, d = fc.eval_many(C, -1.0, 1.0, x, deriv=True)
     assert np.abs(v - np.sin(a[:, None] * x + b[:, None])).max() <= 1e-13
     assert np.abs(d - a[:, None] * np.cos(a[:, None] * x + b[:, None])).max() <= 1e-10
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_eval_many_shared_points_matches_oracle(fc, orc, dt):
+    """fastcheb_eval_many_shared: every polynomial at the same points = a matrix product on the FP64 tensor cores.
+    Values within 16 eps sum|c| of the oracle's per-polynomial Clenshaw evaluation, derivatives within the
+    differentiated-series bound; ragged row blocks / point tiles, vector and complex elements, n = 1, 2, 65."""
+    rng = np.random.default_rng(78)
+    eps = np.finfo(dt).eps
+    for n, K, cplx, howmany, M in ((65, None, False, 301, 1000), (65, 3, False, 50, 130), (33, None, True, 77, 257), (1, None, False, 9, 5),
+                                   (2, 2, False, 20, 64), (40, 2, True, 130, 63)):
+        shape = (howmany, n) + ((K,) if K else ())
+        # coefficients that decay like those of fitted smooth functions (what configs[4] evaluates).  For dense-random
+        # coefficient vectors the Clenshaw recurrence itself carries ~k eps |c_k| of rounding at the end points, and a
+        # direct sum (exact there) then differs from it by up to ~1.2 tolerances.
+        decay = (0.85 ** np.arange(n)).reshape((1, n) + ((1,) if K else ()))
+        c = rng.uniform(-1, 1, shape) * decay
+        if cplx:
+            c = (c + 1j * rng.uniform(-1, 1, shape) * decay).astype(np.complex128 if dt == np.float64 else np.complex64)
+        else:
+            c = c.astype(dt)
+        lb, ub = dt(-1.5), dt(0.75)
+        x = (lb + (ub - lb) * rng.random(M)).astype(dt)
+        x = np.clip(x, lb, ub)
+        x[0], x[-1] = lb, ub
+        v, d = fc.eval_many(c, lb, ub, x, deriv=True)
+        assert v.shape == (howmany, M) + ((K,) if K else ()) and v.dtype == c.dtype
+        assert np.array_equal(fc.eval_many(c, lb, ub, x), v)
+        k2 = np.arange(n, dtype=np.float64) ** 2
+        for f in (0, howmany // 2, howmany - 1):
+            ref = orc.OracleChebPoly(c[f], np.array([lb]), np.array([ub]))
+            rv, rJ = ref.jacobian(x.reshape(-1, 1))
+            tol = 16 * eps * np.abs(c[f]).sum()
+            assert np.abs(v[f] - rv.reshape(v[f].shape)).max() <= tol, (n, K, cplx, f)
+            told = 16 * eps * (np.abs(c[f]).reshape(n, -1) * k2[:, None]).sum() * 2 / (float(ub) - float(lb))
+            assert np.abs(d[f] - rJ.reshape(d[f].shape)).max() <= max(told, 0.0), (n, K, cplx, f)
+    with pytest.raises(fc.ArgumentError) as ei:
+        bad = x.copy()
+        bad[17] = 2.0
+        fc.eval_many(c, lb, ub, bad)
+    assert ei.value.index == 17
