@@ -341,6 +341,8 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
 
   if (mem == FASTCHEB_MEM_DEVICE) {
     FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, howmany, vals, coefs, maxabs, fs.dev, st));
+    FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    FC_CUDA(cudaStreamSynchronize(st));
   } else {
     // Host buffers: the fits are independent, so a large batch is cut into chunks that flow through two
     // internal streams — the D2H copy of chunk i overlaps the H2D copy and the transform of chunk i+1 (PCIe is
@@ -350,7 +352,10 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
     if (bytes > (size_t(64) << 20) && howmany >= 4)
       chunk = std::max<int64_t>(1, std::min<int64_t>((howmany + 3) / 4, (int64_t)((size_t(128) << 20) / fit_bytes)));
     const int nbuf = howmany > chunk ? 2 : 1;
-    FC_CUDA(cudaStreamSynchronize(st));  // the flag initialisation above is ordered before the internal streams
+    // two internal streams only for multi-chunk batches: the flag initialisation above is then ordered before them by a
+    // synchronisation; a single chunk (single fits, small batches) runs on the caller's stream with ONE synchronisation
+    // at the end of the call
+    if (nbuf > 1) FC_CUDA(cudaStreamSynchronize(st));
     cudaStream_t ss[2] = {nullptr, nullptr};
     void* dbuf[2] = {nullptr, nullptr};
     const size_t cb = (size_t)chunk * fit_bytes, cb_al = (cb + 255) / 256 * 256;
@@ -394,6 +399,8 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
         ce = cudaMemcpyAsync(maxabs + done, d_mx, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, s2);
       done += m;
     }
+    if (nbuf == 1 && ce == cudaSuccess && rc == FASTCHEB_OK)
+      ce = cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st);  // one synchronisation for all
     for (int i = 0; i < nbuf; ++i) {
       cudaError_t e2 = cudaStreamSynchronize(nbuf == 1 ? st : ss[i]);
       if (ce == cudaSuccess) ce = e2;
@@ -401,9 +408,11 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
     cleanup();
     if (rc != FASTCHEB_OK) return rc;
     if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged fit failed: %s", cudaGetErrorString(ce));
+    if (nbuf > 1) {
+      FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+      FC_CUDA(cudaStreamSynchronize(st));
+    }
   }
-  FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  FC_CUDA(cudaStreamSynchronize(st));
   if (*fs.host != kNoBad) {
     err_state().index = *fs.host;
     return fail(FASTCHEB_ENONFINITE, "non-finite interpolant value at flat index %lld (interp.jl:40)", *fs.host);

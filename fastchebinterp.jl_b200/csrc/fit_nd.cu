@@ -170,7 +170,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     const int gb = dtype == FASTCHEB_F64 ? 2 : 4;
     const size_t bufBytes = (((size_t)arr_reals * rs + 15) / 16) * 16 + 16;
     const size_t fixed = 1024 + af_bytes;
-    const int max_warps = 8;  // launch bounds of the kernel: 256 threads
+    const int max_warps = cls == 0 ? 16 : 8;  // launch bounds of the instantiation: 512 / 256 threads
     if (fixed + bufBytes > budget) return -1;
     auto waste = [&](int w) {
       long long slots = 0, work = 0;
@@ -191,9 +191,11 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     {
       // small arrays: 4 warps (128 threads x 128 registers: four CTAs share an SM; 5 warps would balance 10 line groups
       // exactly but leave room for three CTAs only — measured 34 % against 38 %)
-      const bool small = fixed + bufBytes <= budget / 4;
+      const bool small = fixed + bufBytes <= budget / 4 && narr >= di->sms;  // a single array: latency, not occupancy
       double best = 1e30;
-      for (int w = small ? 4 : 8; w >= 4; --w) {
+      // large arrays (one CTA per SM): up to 16 warps — the n = 33 passes are short dependent chains of 12 DMMAs per line
+      // group and want many groups in flight (33^3 Float32: 10.9 % of HBM with 8 warps, 13.3 % with 16)
+      for (int w = small ? 4 : (fixed + bufBytes > budget / 2 ? max_warps : 8); w >= 4; --w) {
         const double cost = waste(w);
         if (cost < best - 1e-9) {
           best = cost;
@@ -203,7 +205,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     }
     if (const char* t = getenv("FASTCHEB_FITND_WARPS")) {
       const int v = atoi(t);
-      if (v >= 1 && v <= 8) {
+      if (v >= 1 && v <= max_warps) {
         warps = v;
         teams = std::max<int>(1, std::min<int>({(int)((budget - fixed) / bufBytes), max_warps / v, 15}));
       }

@@ -224,7 +224,7 @@ __device__ __forceinline__ R* fit_nd_load_async(unsigned char* buf16, const R* g
 // only 2 warps busy without idle barrier rounds, so an SM runs 6 such teams side by side in ONE CTA with ONE copy of the
 // matrices, instead of 4 CTAs of 4 half-idle warps with a copy each.
 template <typename R, int MTO, int MTB, int MTC, bool AFG>
-__global__ void __launch_bounds__(256) fit_nd_kernel(const __grid_constant__ FitNdParams prm) {
+__global__ void __launch_bounds__(MTB <= 4 ? 512 : 256) fit_nd_kernel(const __grid_constant__ FitNdParams prm) {
   extern __shared__ __align__(16) unsigned char fastcheb_smem[];
   // [1 KB header: per team 8 partial maxima + flag] [matrices unless AFG] [array buffers, 16-byte aligned, 16 bytes of
   // slack]  (no static shared memory: the kernel is launched with the opt-in maximum of dynamic shared memory)

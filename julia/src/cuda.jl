@@ -8,12 +8,14 @@
 # copy or permutation is needed on the Julia side: `Array{SVector{K,T},N}` coefficients,
 # `Vector{SVector{N,T}}` points, `Vector{Tuple{V,SMatrix{K,N}}}` Jacobian results are passed as is.
 #
-# Public API (unchanged names; methods are added for the device-resident type):
+# Public API (unchanged names; METHODS are added to the reference's own functions for the device-resident types):
 #   cu = CuChebPoly(c::ChebPoly)            upload (FastChebInterp.jl:37-41 -> fastcheb_create)
-#   cu(ys::AbstractVector{<:SVector{N}})    == c.(ys)                      (eval.jl:63-70)
+#   cu = CuChebPoly(c; devices=0:7)         replicated on several GPUs, driven from this one process (fastcheb_multi_*)
+#   cu(ys::AbstractVector{<:SVector{N}})    == c.(ys)                      (eval.jl:63-70); mixed precisions promote (eval.jl:25)
 #   cu.(ys)                                 same, through Base.broadcasted
 #   chebjacobian(cu, ys), chebgradient(cu, ys)                             (eval.jl:147-177)
-#   chebinterp(vals, lb, ub; tol, device=0) -> CuChebPoly                  (interp.jl:95-99,140-141)
+#   chebinterp(ondevice(vals), lb, ub; tol) -> CuChebPoly                  (interp.jl:95-99,140-141): a method of chebinterp
+#   chebinterp(cu, order, lb, ub; tol)      re-interpolation on the device (interp.jl:163-170; the loop body of roots)
 #   chebcoefs_batched(vals::Matrix)         10^5 independent 1-D fits      (interp.jl:39-57 per column)
 #   ChebPoly(cu)                            download
 
@@ -63,63 +65,102 @@ function _check(rc::Cint, c=nothing, xs=nothing)
 end
 
 """
-Device-resident `ChebPoly{N,T,Td}`: an opaque handle owned by libfastcheb_cuda (coefficients in the
-kernels' own layouts, `lb`, `ub`, sizes).  Immutable after creation; safe to evaluate from several
-tasks at once.
+Device-resident `ChebPoly{N,T,Td}`: opaque handles owned by libfastcheb_cuda (coefficients in the kernels' own layouts,
+`lb`, `ub`, sizes).  Immutable after creation; safe to evaluate from several tasks at once.  `multi != C_NULL`: the
+polynomial is replicated on several GPUs (`CuChebPoly(c; devices=0:7)`) and every batch is block-partitioned over them
+from this one process.  A `Float32` polynomial evaluated at `Float64` points promotes like the reference
+(`muladd(x, c, c)`, eval.jl:25): the widened `Float64` handle is created on first use and cached in `wide`.
 """
 mutable struct CuChebPoly{N,T,Td<:Real} <: Function
-    handle::Ptr{Cvoid}
+    handle::Ptr{Cvoid}      # fastcheb_poly (single GPU) or C_NULL
+    multi::Ptr{Cvoid}       # fastcheb_multi or C_NULL
     lb::SVector{N,Td}
     ub::SVector{N,Td}
     dims::NTuple{N,Int}
-    device::Int
-    function CuChebPoly{N,T,Td}(h, lb, ub, dims, device) where {N,T,Td}
-        c = new{N,T,Td}(h, lb, ub, dims, device)
-        finalizer(c) do x   # fastcheb_destroy is finalizer-safe: no exceptions, any thread
+    devices::Vector{Int}
+    wide::Any               # nothing, or the CuChebPoly of the Float64-widened coefficients
+    function CuChebPoly{N,T,Td}(h, m, lb, ub, dims, devices) where {N,T,Td}
+        c = new{N,T,Td}(h, m, lb, ub, dims, devices, nothing)
+        finalizer(c) do x   # destroy entry points are finalizer-safe: no exceptions, any thread, NULL is a no-op
             ccall((:fastcheb_destroy, libfastcheb), Cint, (Ptr{Cvoid},), x.handle)
+            ccall((:fastcheb_multi_destroy, libfastcheb), Cint, (Ptr{Cvoid},), x.multi)
         end
         c
     end
 end
 Base.ndims(::CuChebPoly{N}) where {N} = N
 
-function CuChebPoly(c::ChebPoly{N,T,Td}; device::Integer=0) where {N,T,Td}
+function CuChebPoly(c::ChebPoly{N,T,Td}; device::Integer=0, devices=nothing) where {N,T,Td}
     R, cplx, K = _elt(T)
-    h = Ref{Ptr{Cvoid}}(C_NULL)
     dims = collect(Int64, size(c.coefs))
     lb, ub = collect(Float64, c.lb), collect(Float64, c.ub)   # Td may be Int (runtests.jl:170)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    if devices === nothing
+        GC.@preserve c begin
+            rc = ccall((:fastcheb_create, libfastcheb), Cint,
+                       (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Cint),
+                       h, N, dims, _dtype(R), cplx, K, pointer(c.coefs), FASTCHEB_MEM_HOST, lb, ub, device)
+        end
+        _check(rc)
+        return CuChebPoly{N,T,Td}(h[], C_NULL, c.lb, c.ub, size(c.coefs), [Int(device)])
+    end
+    devs = collect(Cint, devices)
     GC.@preserve c begin
-        rc = ccall((:fastcheb_create, libfastcheb), Cint,
-                   (Ref{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Cint),
-                   h, N, dims, _dtype(R), cplx, K, pointer(c.coefs), FASTCHEB_MEM_HOST, lb, ub, device)
+        rc = ccall((:fastcheb_multi_create, libfastcheb), Cint,
+                   (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}, Cint, Ptr{Int64}, Cint, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}),
+                   h, length(devs), devs, N, dims, _dtype(R), cplx, K, pointer(c.coefs), FASTCHEB_MEM_HOST, lb, ub)
     end
     _check(rc)
-    CuChebPoly{N,T,Td}(h[], c.lb, c.ub, size(c.coefs), device)
+    CuChebPoly{N,T,Td}(C_NULL, h[], c.lb, c.ub, size(c.coefs), collect(Int, devices))
 end
 
 function ChebPoly(cu::CuChebPoly{N,T,Td}) where {N,T,Td}
     coefs = Array{T,N}(undef, cu.dims)
-    _check(ccall((:fastcheb_get_coefs, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), cu.handle, coefs, FASTCHEB_MEM_HOST))
+    h = cu.handle != C_NULL ? cu.handle : ccall((:fastcheb_multi_poly, libfastcheb), Ptr{Cvoid}, (Ptr{Cvoid}, Cint), cu.multi, 0)
+    _check(ccall((:fastcheb_get_coefs, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint), h, coefs, FASTCHEB_MEM_HOST))
     ChebPoly{N,T,Td}(coefs, cu.lb, cu.ub)
 end
 
 # result element types — the same promotion as eval.jl:25 (`muladd(x, c, c)`)
 _valtype(::Type{T}, ::Type{Tx}) where {T,Tx} = typeof(zero(T) * zero(Tx))
+_widen(::Type{Float32}) = Float64
+_widen(::Type{Complex{Float32}}) = Complex{Float64}
+_widen(::Type{SVector{K,T}}) where {K,T} = SVector{K,_widen(T)}
+
+# the handle that computes in the precision of the points: Float32 coefficients at Float64 points promote (eval.jl:25)
+function _for_points(cu::CuChebPoly{N,T,Td}, ::Type{R}) where {N,T,Td,R}
+    _elt(T)[1] === R && return cu
+    if _elt(T)[1] === Float32 && R === Float64
+        if cu.wide === nothing
+            c = ChebPoly(cu)
+            cw = ChebPoly{N,_widen(T),Td}(map(x -> _widen(T)(x), c.coefs), c.lb, c.ub)
+            cu.wide = length(cu.devices) > 1 || cu.multi != C_NULL ? CuChebPoly(cw; devices=cu.devices) : CuChebPoly(cw; device=cu.devices[1])
+        end
+        return cu.wide
+    end
+    nothing   # Float64 coefficients at Float32 points: the points are widened by the caller below
+end
 
 # ---- c.(ys): batched evaluation (eval.jl:63-70 per point)
 function (cu::CuChebPoly{N,T})(ys::AbstractVector{SVector{N,R}}) where {N,T,R<:Union{Float32,Float64}}
-    _elt(T)[1] === R || throw(ArgumentError("promote points and coefficients to one precision first"))
+    h = _for_points(cu, R)
+    h === nothing && return cu(map(y -> Float64.(y), ys))        # promote the points instead (eval.jl:65)
+    h === cu || return h(ys)
     ys = ys isa Vector ? ys : collect(ys)
     out = Vector{T}(undef, length(ys))
     GC.@preserve ys out begin
-        rc = ccall((:fastcheb_eval, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
-                   cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
+        rc = cu.multi != C_NULL ?
+            ccall((:fastcheb_multi_eval, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint),
+                  cu.multi, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST) :
+            ccall((:fastcheb_eval, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                  cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
     end
     _check(rc, cu, ys)
     out
 end
 (cu::CuChebPoly{1,T})(xs::AbstractVector{R}) where {T,R<:Union{Float32,Float64}} =
     cu(reinterpret(SVector{1,R}, xs isa Vector ? xs : collect(xs)))
+(cu::CuChebPoly{N})(ys::AbstractVector{<:SVector{N,<:Real}}) where {N} = cu(map(y -> float.(y), ys))   # integer points etc.
 (cu::CuChebPoly{N})(x::SVector{N,<:Real}) where {N} = cu([float.(x)])[1]       # single point: still the device path
 (cu::CuChebPoly{1})(x::Real) = cu(SVector(float(x)))
 # `cu.(ys)` lowers to broadcasted(cu, ys): route whole batches to one library call
@@ -129,24 +170,33 @@ Base.Broadcast.broadcasted(cu::CuChebPoly{1}, xs::AbstractVector{<:Real}) = cu(x
 # ---- chebjacobian / chebgradient over batches (eval.jl:147-177).  The library writes Julia's own
 # Vector{Tuple{V,SMatrix{K,N}}} element layout (fastcheb_eval_jac_tuple), so the result needs no repacking.
 function chebjacobian(cu::CuChebPoly{N,T}, ys::AbstractVector{SVector{N,R}}) where {N,T,R<:Union{Float32,Float64}}
+    h = _for_points(cu, R)
+    h === nothing && return chebjacobian(cu, map(y -> Float64.(y), ys))
+    h === cu || return chebjacobian(h, ys)
     _, _, K = _elt(T)
     S = T <: SVector ? eltype(T) : T
     out = Vector{Tuple{T,SMatrix{K,N,S,K * N}}}(undef, length(ys))
     ys = ys isa Vector ? ys : collect(ys)
     GC.@preserve ys out begin
-        rc = ccall((:fastcheb_eval_jac_tuple, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
-                   cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
+        rc = _jac_tuple(cu, ys, out)
     end
     _check(rc, cu, ys)
     out
 end
+_jac_tuple(cu, ys, out) = cu.multi != C_NULL ?
+    ccall((:fastcheb_multi_eval_jac_tuple, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint),
+          cu.multi, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST) :
+    ccall((:fastcheb_eval_jac_tuple, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+          cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
 function chebgradient(cu::CuChebPoly{N,T}, ys::AbstractVector{SVector{N,R}}) where {N,T,R<:Union{Float32,Float64}}
     T <: SVector && length(T) != 1 && throw(DimensionMismatch())                 # eval.jl:170
+    h = _for_points(cu, R)
+    h === nothing && return chebgradient(cu, map(y -> Float64.(y), ys))
+    h === cu || return chebgradient(h, ys)
     out = Vector{Tuple{T,SVector{N,T}}}(undef, length(ys))                       # same bytes as (v, 1xN SMatrix)
     ys = ys isa Vector ? ys : collect(ys)
     GC.@preserve ys out begin
-        rc = ccall((:fastcheb_eval_jac_tuple, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
-                   cu.handle, pointer(ys), length(ys), pointer(out), FASTCHEB_MEM_HOST, C_NULL)
+        rc = _jac_tuple(cu, ys, out)
     end
     _check(rc, cu, ys)
     out
@@ -155,8 +205,17 @@ chebjacobian(cu::CuChebPoly{N}, x::SVector{N,<:Real}) where {N} = chebjacobian(c
 chebgradient(cu::CuChebPoly{N}, x::SVector{N,<:Real}) where {N} = chebgradient(cu, [float.(x)])[1]
 chebgradient(cu::CuChebPoly{1}, x::Real) = (r = chebgradient(cu, SVector(float(x))); (r[1], r[2][1]))  # eval.jl:174-177
 
-# ---- chebinterp(vals, lb, ub; tol) on the device (interp.jl:95-99, 140-141): fit + droptol + handle
-function cuchebinterp(vals::AbstractArray{T,N}, lb, ub; tol::Real=-1, device::Integer=0) where {T,N}
+# ---- chebinterp(vals, lb, ub; tol) on the device (interp.jl:95-99, 140-141): fit + droptol + handle.
+# The reference's method chebinterp(vals::AbstractArray, lb, ub; tol) stays what it is (CPU / FFTW); the device path is
+# a METHOD OF THE SAME FUNCTION selected by the argument type: wrap the values with `ondevice(vals; device=0)`.
+struct OnDevice{A<:AbstractArray}
+    data::A
+    device::Int
+end
+ondevice(vals::AbstractArray; device::Integer=0) = OnDevice(vals, Int(device))
+
+function chebinterp(v::OnDevice{<:AbstractArray{T,N}}, lb, ub; tol::Real=-1) where {T,N}
+    vals, device = v.data, v.device
     R, cplx, K = _elt(T)
     Td = promote_type(eltype(lb), eltype(ub))
     vals = vals isa Array ? vals : collect(vals)
@@ -171,14 +230,26 @@ function cuchebinterp(vals::AbstractArray{T,N}, lb, ub; tol::Real=-1, device::In
     _check(rc)
     nd = Vector{Int64}(undef, N)
     _check(ccall((:fastcheb_dims, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Int64}), h[], nd))
-    CuChebPoly{N,T,Td}(h[], SVector{N,Td}(lb), SVector{N,Td}(ub), Tuple(nd), device)
+    CuChebPoly{N,T,Td}(h[], C_NULL, SVector{N,Td}(lb), SVector{N,Td}(ub), Tuple(nd), [device])
 end
+chebinterp(v::OnDevice{<:AbstractVector}, lb::Real, ub::Real; kws...) = chebinterp(v, SVector(lb), SVector(ub); kws...)   # interp.jl:140-141
 
 # ---- many independent 1-D fits at once (BASELINE configs[4]): column j of `vals` is one line
-function chebcoefs_batched(vals::Matrix{R}; device::Integer=0) where {R<:Union{Float32,Float64}}
+function chebcoefs_batched(vals::Matrix{R}; device::Integer=0, devices=nothing) where {R<:Union{Float32,Float64}}
     n, howmany = size(vals)
     coefs = similar(vals)
     maxabs = Vector{Float64}(undef, howmany)
+    if devices !== nothing        # the batch split per GPU, one process (SURVEY.md 8e: fits are sharded, a single fit is not)
+        devs = collect(Cint, devices)
+        GC.@preserve vals coefs maxabs begin
+            rc = ccall((:fastcheb_multi_fit, libfastcheb), Cint,
+                       (Cint, Ptr{Cint}, Cint, Ptr{Int64}, Cint, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Cint),
+                       length(devs), devs, 1, Int64[n], _dtype(R), 0, 1, howmany, pointer(vals), pointer(coefs), pointer(maxabs),
+                       FASTCHEB_MEM_HOST)
+        end
+        _check(rc)
+        return coefs, maxabs
+    end
     GC.@preserve vals coefs maxabs begin
         rc = ccall((:fastcheb_fit, libfastcheb), Cint,
                    (Cint, Ptr{Int64}, Cint, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Cvoid}),
@@ -193,14 +264,16 @@ end
 
 # chebinterp(c, order, lb, ub; tol) with a device-resident ChebPoly as the function (interp.jl:163-170; the loop body of
 # roots, roots.jl:105-107): grid -> evaluation -> fit -> droptol never leave the GPU.
-function cuchebinterp(cu::CuChebPoly{N,T,Td}, order::NTuple{N,Int}, lb, ub; tol::Real=-1) where {N,T,Td}
+# A method of the reference's chebinterp(f, order, lb, ub): CuChebPoly <: Function, and this more specific method wins.
+function chebinterp(cu::CuChebPoly{N,T,Td}, order::NTuple{N,Int}, lb, ub; tol::Real=-1) where {N,T,Td}
+    cu.handle == C_NULL && error("re-interpolation runs on one GPU: build the source with CuChebPoly(c; device=d)")
     h = Ref{Ptr{Cvoid}}(C_NULL)
     _check(ccall((:fastcheb_reinterp, libfastcheb), Cint,
                  (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Cvoid}),
                  h, cu.handle, collect(Int64, order), collect(Float64, lb), collect(Float64, ub), tol, C_NULL))
     nd = Vector{Int64}(undef, N)
     _check(ccall((:fastcheb_dims, libfastcheb), Cint, (Ptr{Cvoid}, Ptr{Int64}), h[], nd))
-    CuChebPoly{N,T,Td}(h[], SVector{N,Td}(lb), SVector{N,Td}(ub), Tuple(nd), cu.device)
+    CuChebPoly{N,T,Td}(h[], C_NULL, SVector{N,Td}(lb), SVector{N,Td}(ub), Tuple(nd), cu.devices)
 end
 
 # rrule / frule (chainrules.jl:4-39) over batches: the Jacobian is contracted inside the kernel.
@@ -248,6 +321,22 @@ function cheb_eval_many(coefs::Matrix{R}, lb::Real, ub::Real, xs::Matrix{R}) whe
                    howmany, n, _dtype(R), 0, 1, pointer(coefs), Float64[lb], Float64[ub], 0, pointer(xs), M, pointer(out), C_NULL, C_NULL,
                    FASTCHEB_MEM_HOST, 0, C_NULL)
     end
+    _check(rc)
+    out
+end
+
+# ... and at ONE shared set of points: [c.(xs) for c in cs] is then a matrix product on the FP64 tensor cores
+# (fastcheb_eval_many_shared; n <= 65).  Result: M x howmany.
+function cheb_eval_many(coefs::Matrix{R}, lb::Real, ub::Real, xs::Vector{R}) where {R<:Union{Float32,Float64}}
+    n, howmany = size(coefs); M = length(xs)
+    out = Matrix{R}(undef, M, howmany)
+    GC.@preserve coefs xs out begin
+        rc = ccall((:fastcheb_eval_many_shared, libfastcheb), Cint,
+                   (Int64, Int64, Cint, Cint, Cint, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}),
+                   howmany, n, _dtype(R), 0, 1, pointer(coefs), Float64[lb], Float64[ub], pointer(xs), M, pointer(out), C_NULL, C_NULL,
+                   FASTCHEB_MEM_HOST, 0, C_NULL)
+    end
+    rc == FASTCHEB_EDOMAIN && throw(ArgumentError("$(xs[_error_index() + 1]) not in domain $lb to $ub"))
     _check(rc)
     out
 end
