@@ -56,9 +56,20 @@ int get_matrices(int dev, std::vector<int> ns, const NdMatrices** out) {
   return FASTCHEB_OK;
 }
 
-template <typename R, int MTO, int MTB, int MTC, bool AFG = false>
+template <typename R, int MTO, int MTB, int MTC, bool AFG = false, int SPEC = 0>
 cudaError_t launch(const FitNdParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
-  auto kern = fit_nd_kernel<R, MTO, MTB, MTC, AFG>;
+  auto kern = fit_nd_kernel<R, MTO, MTB, MTC, AFG, SPEC>;
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
+  if (e != cudaSuccess) return e;
+  if (bps) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
+  kern<<<grid, threads, smem, st>>>(prm);
+  note_launch();
+  return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t launch_pipe(const FitNdParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
+  auto kern = fit_nd_pipe_kernel<R, 4, 4, 2>;
   cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
   if (bps) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
@@ -73,6 +84,9 @@ template <typename R>
 cudaError_t dispatch(int cls, const FitNdParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
   switch (cls) {
     case 0: return launch<R, 4, 4, 2>(prm, grid, threads, smem, st, bps);
+    case 17: return launch<R, 4, 4, 2, false, 17>(prm, grid, threads, smem, st, bps);  // matrices in registers
+    case 33: return launch<R, 4, 4, 2, false, 33>(prm, grid, threads, smem, st, bps);
+    case 65: return launch<R, 4, 4, 2, false, 65>(prm, grid, threads, smem, st, bps);
     case 1: return launch<R, 4, 5, 4>(prm, grid, threads, smem, st, bps);
     case 2: return launch<R, 4, 9, 8, true>(prm, grid, threads, smem, st, bps);  // matrices from global memory / L2
   }
@@ -119,7 +133,20 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
   }
   const NdMatrices* mats = nullptr;
   FC_TRY(get_matrices(dev, ns, &mats));
-  const size_t af_bytes = cls == 2 ? 0 : (((size_t)mats->doubles * 8 + 15) / 16) * 16;  // class 2 reads them from L2
+  // all transformed dimensions of size 17 or 33: the matrices live in registers (SPEC instantiations, fit_nd.cuh; 5 / 12
+  // values per lane).  n = 65 (39 values: 166 registers, three CTAs per SM instead of four) measured no faster — 34.9 %
+  // against 36-38 % of HBM on 65 x 65 — and is used only with FASTCHEB_FITND_SPEC=65 (experiments); 33^3 Float32: 14.8 %
+  // against 13.3 %.
+  static const int spec_env = [] {
+    const char* e = getenv("FASTCHEB_FITND_SPEC");
+    return e ? atoi(e) : -1;
+  }();
+  int spec = 0;
+  if (cls == 0 && mats->ns.size() == 1 && spec_env != 0) {
+    const int n0 = mats->ns[0];
+    if (n0 == 17 || n0 == 33 || (n0 == 65 && spec_env == 65)) spec = n0;
+  }
+  const size_t af_bytes = (cls == 2 || spec) ? 0 : (((size_t)mats->doubles * 8 + 15) / 16) * 16;  // class 2 reads them from L2
   const size_t budget = std::min<size_t>(di->smem_optin, kSmemOptinMax) - 3072;
   if (lines) {  // as many lines per block as fit next to the matrices (a multiple of the 16- / 32-line MMA blocks)
     const long long room = ((long long)budget - (long long)af_bytes - 256) / (long long)(reals * rs);
@@ -163,6 +190,46 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
         fd.afrag = mats->off[i];
       }
     }
+    // Small arrays in batches: the warp-specialised pipeline (loader warp, one consumer warp per line group, storer warp;
+    // three buffers) — see fit_nd_pipe_kernel.  FASTCHEB_FITND_PIPE=0 keeps the lock-step kernel (experiments).
+    {
+      static const bool pipe_off = [] {  // measured slower than the lock-step kernel (30 % vs 38 % on 65 x 65): opt-in
+        const char* e = getenv("FASTCHEB_FITND_PIPE");
+        return !(e && atoi(e) == 1);
+      }();
+      const int gb0 = dtype == FASTCHEB_F64 ? 2 : 4;
+      long long gmax = 0;
+      for (int d = 0; d < ndim; ++d)
+        if (dims[d] > 1) {
+          const long long nlines = arr_reals / dims[d];
+          gmax = std::max(gmax, (nlines + 8 * gb0 - 1) / (8 * gb0) * gb0);
+        }
+      const size_t bufB = (((size_t)arr_reals * rs + 15) / 16) * 16 + 16;
+      const size_t af_pipe = (((size_t)mats->doubles * 8 + 15) / 16) * 16;
+      const size_t smem_pipe = 1024 + af_pipe + (size_t)kFitPipeBufs * bufB;
+      const long long rounds = (gmax + 13) / 14;
+      if (!pipe_off && cls == 0 && fits_per_arr == 1 && rounds <= 2 && smem_pipe <= budget && narr >= 2LL * di->sms) {
+        const int NC = (int)((gmax + rounds - 1) / rounds);
+        int NS = 2;  // storer warps
+        if (const char* t = getenv("FASTCHEB_FITND_STORERS")) NS = std::max(1, std::min(4, atoi(t)));
+        if (NC + 1 + NS > 16) NS = 16 - NC - 1;
+        prm.team_warps = NC;
+        prm.teams = NS;
+        prm.nbuf = kFitPipeBufs;
+        const int threads = (NC + 1 + NS) * 32;
+        int bps = 0;
+        cudaError_t e = dtype == FASTCHEB_F64 ? launch_pipe<double>(prm, 0, threads, smem_pipe, st, &bps)
+                                              : launch_pipe<float>(prm, 0, threads, smem_pipe, st, &bps);
+        if (e == cudaSuccess && bps >= 1) {
+          const int grid = (int)std::max<long long>(1, std::min<long long>(narr, (long long)di->sms * bps));
+          e = dtype == FASTCHEB_F64 ? launch_pipe<double>(prm, grid, threads, smem_pipe, st, nullptr)
+                                    : launch_pipe<float>(prm, grid, threads, smem_pipe, st, nullptr);
+          if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "pipelined DCT-I kernel launch failed: %s", cudaGetErrorString(e));
+          return FASTCHEB_OK;
+        }
+        cudaGetLastError();
+      }
+    }
     // Team geometry.  The passes of an array are separated by barriers of the team that owns it, so the line groups
     // of a pass should divide evenly among the team's warps (65 lines = 10 groups: 2 or 5 warps, not 4 or 8), and an
     // SM wants ~12-16 warps in flight: small arrays run several teams per CTA (one copy of the matrices), large ones
@@ -170,7 +237,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     const int gb = dtype == FASTCHEB_F64 ? 2 : 4;
     const size_t bufBytes = (((size_t)arr_reals * rs + 15) / 16) * 16 + 16;
     const size_t fixed = 1024 + af_bytes;
-    const int max_warps = cls == 0 ? 16 : 8;  // launch bounds of the instantiation: 512 / 256 threads
+    const int max_warps = (cls == 0 && spec != 65) ? 16 : 8;  // launch bounds of the instantiation: 512 / 256 threads
     if (fixed + bufBytes > budget) return -1;
     auto waste = [&](int w) {
       long long slots = 0, work = 0;
@@ -227,16 +294,17 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     const int threads = warps * teams * 32;
     const size_t smem = fixed + (size_t)teams * nbuf * bufBytes;
     int bps = 0;
-    cudaError_t e = dtype == FASTCHEB_F64 ? dispatch<double>(cls, prm, 0, threads, smem, st, &bps)
-                                          : dispatch<float>(cls, prm, 0, threads, smem, st, &bps);
+    const int sel = spec ? spec : cls;
+    cudaError_t e = dtype == FASTCHEB_F64 ? dispatch<double>(sel, prm, 0, threads, smem, st, &bps)
+                                          : dispatch<float>(sel, prm, 0, threads, smem, st, &bps);
     if (e != cudaSuccess || bps < 1) {
       cudaGetLastError();
       if (getenv("FASTCHEB_DEBUG")) fprintf(stderr, "fit_nd: not launchable (%s, %d CTAs/SM, %zu B)\n", cudaGetErrorString(e), bps, smem);
       return -1;  // not launchable: the caller falls back
     }
     const int grid = (int)std::max<long long>(1, std::min<long long>((narr + teams - 1) / teams, (long long)di->sms * bps));
-    e = dtype == FASTCHEB_F64 ? dispatch<double>(cls, prm, grid, threads, smem, st, nullptr)
-                              : dispatch<float>(cls, prm, grid, threads, smem, st, nullptr);
+    e = dtype == FASTCHEB_F64 ? dispatch<double>(sel, prm, grid, threads, smem, st, nullptr)
+                              : dispatch<float>(sel, prm, grid, threads, smem, st, nullptr);
     if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "resident DCT-I kernel launch failed: %s", cudaGetErrorString(e));
     return FASTCHEB_OK;
   };

@@ -60,10 +60,15 @@ struct FitNdParams {
 // CKO / CKB / CKC != 0: the k-step counts are compile-time (the common sizes n = 17, 33, 65, 129): the k loop is then one
 // straight-line block, every operand load of a k-step is issued before its DMMAs and the loads of the next k-step
 // overlap them.  0: runtime counts from `d` (any n), with the loads of a k-step hoisted by hand.
-template <typename R, int MTO, int MTB, int MTC, int CKO, int CKB, int CKC>
+// AREG: the A fragments come from REGISTERS (`areg`, loaded once per kernel: all dimensions of the array have this size),
+// not from shared memory — the matrix loads were more than half of the shared-memory wavefronts of a line group, and
+// the shared-memory pipe, not the tensor pipe, bounded the kernel (ncu: 5100 wavefronts per 65 x 65 array against 3100
+// tensor-pipe cycles).
+template <typename R, int MTO, int MTB, int MTC, int CKO, int CKB, int CKC, bool AREG = false>
 __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const double* __restrict__ af, int bl, const int (&dl)[2],
-                                             const bool (&dlive)[2], int lane) {
+                                             const bool (&dlive)[2], int lane, const double* areg = nullptr) {
   constexpr bool CT = CKO != 0;
+  static_assert(!AREG || (CT && CKC > 0), "register-resident matrices: compile-time, twice-folded sizes only");
   const int c = lane & 3, q = lane >> 2;
   const int N = d.n - 1, H = N / 2, s = d.stride;
   const int KO = CT ? CKO : d.KO, KB = CT ? CKB : d.KB, KC = CT ? CKC : d.KC;
@@ -106,7 +111,18 @@ __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const doub
     // the A fragments of this k-step, all loaded before the first DMMA (the first entry of the matrices where the part
     // has no such tile; those values are never used)
     double vO[MTP], vQ[MTC], vB[MTB], vC[MTC];
-    if (two) {
+    if constexpr (AREG) {
+      // register layout = the matrices' order: P | Q | B | C, each [m][ks]
+      constexpr int oQ = ((CKC + 1) / 2) * CKC, oB = 2 * oQ, oC = oB + ((CKB + 1) / 2) * CKB;
+#pragma unroll
+      for (int m = 0; m < MTC; ++m) {
+        vO[m] = (m < MC && ks < KC) ? areg[m * CKC + ks] : 0.0;
+        vQ[m] = (m < MC && ks < KC) ? areg[oQ + m * CKC + ks] : 0.0;
+        vC[m] = (m < MC && ks < KC) ? areg[oC + m * CKC + ks] : 0.0;
+      }
+#pragma unroll
+      for (int m = 0; m < MTB; ++m) vB[m] = (m < MB && ks < KB) ? areg[oB + m * CKB + ks] : 0.0;
+    } else if (two) {
 #pragma unroll
       for (int m = 0; m < MTC; ++m) {
         vO[m] = *((m < MC && ks < KC) ? aO + (m * KC + ks) * 32 : aO);
@@ -117,8 +133,10 @@ __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const doub
 #pragma unroll
       for (int m = 0; m < MTO; ++m) vO[m] = *((m < MO && ks < KO) ? aO + (m * KO + ks) * 32 : aO);
     }
+    if constexpr (!AREG) {
 #pragma unroll
-    for (int m = 0; m < MTB; ++m) vB[m] = *((m < MB && ks < KB) ? aB + (m * KB + ks) * 32 : aO);
+      for (int m = 0; m < MTB; ++m) vB[m] = *((m < MB && ks < KB) ? aB + (m * KB + ks) * 32 : aO);
+    }
     const double x1 = (double)r1, x2 = (double)r2;
     double fb = __dadd_rn(x1, x2);
     if (two) {
@@ -187,6 +205,61 @@ __device__ __forceinline__ void fit_nd_lines(R* x, const FitNdDim& d, const doub
   }
 }
 
+// One pass along a dimension: the team's warps take line groups round-robin.
+// number of A-fragment values per lane of the register-resident form (parts P | Q | B | C)
+__host__ __device__ constexpr int fit_nd_areg_count(int spec) { return spec == 65 ? 39 : (spec == 33 ? 12 : (spec == 17 ? 5 : 1)); }
+
+// SPEC != 0: every transformed dimension has size SPEC (17, 33 or 65) and its matrices are in `areg`
+template <typename R, int MTO, int MTB, int MTC, int SPEC = 0>
+__device__ __forceinline__ void fit_nd_pass(R* x, const FitNdDim& d, const double* afd, int reals, int warp, int nwarps, int lane,
+                                            const double* areg = nullptr) {
+  const int s = d.stride;
+  const int nlines = reals / d.n;
+  constexpr int GB = sizeof(R) == 8 ? 2 : 4;  // groups per block of 8 GB lines
+  const int ngroups = (nlines + 8 * GB - 1) / (8 * GB) * GB;
+  for (int gi = warp; gi < ngroups; gi += nwarps) {
+    // line L -> (outer o, inner i): base = o * n * s + i
+    auto base_of = [&](int L) {
+      const int o = L / s, i = L - o * s;
+      return o * d.n * s + i;
+    };
+    const int c = lane & 3, q = lane >> 2;
+    const int blk = (gi / GB) * 8 * GB, t = gi % GB;
+    auto line_of = [&](int col) { return blk + (GB == 2 ? 4 * (col & 3) + (col >> 2) + 2 * t : 4 * col + t); };
+    const int Lb = line_of(q);
+    const int bl = base_of(Lb < nlines ? Lb : 0);
+    int dl[2];
+    bool dlive[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int Ld = line_of(2 * c + h);
+      dlive[h] = Ld < nlines;
+      dl[h] = base_of(dlive[h] ? Ld : 0);
+    }
+    if constexpr (SPEC == 65) {
+      fit_nd_lines<R, 4, 3, 2, 8, 5, 4, true>(x, d, afd, bl, dl, dlive, lane, areg);
+      continue;
+    } else if constexpr (SPEC == 33) {
+      fit_nd_lines<R, 2, 2, 1, 4, 3, 2, true>(x, d, afd, bl, dl, dlive, lane, areg);
+      continue;
+    } else if constexpr (SPEC == 17) {
+      fit_nd_lines<R, 1, 1, 1, 2, 2, 1, true>(x, d, afd, bl, dl, dlive, lane, areg);
+      continue;
+    }
+    // the common sizes run a fully unrolled copy of the pass
+    if (d.KO == 8 && d.KB == 5 && d.KC == 4)                    // n = 65
+      fit_nd_lines<R, 4, 3, 2, 8, 5, 4>(x, d, afd, bl, dl, dlive, lane);
+    else if (d.KO == 4 && d.KB == 3 && d.KC == 2)               // n = 33
+      fit_nd_lines<R, 2, 2, 1, 4, 3, 2>(x, d, afd, bl, dl, dlive, lane);
+    else if (d.KO == 2 && d.KB == 2 && d.KC == 1)               // n = 17
+      fit_nd_lines<R, 1, 1, 1, 2, 2, 1>(x, d, afd, bl, dl, dlive, lane);
+    else if (MTB >= 5 && d.KO == 16 && d.KB == 9 && d.KC == 8)  // n = 129
+      fit_nd_lines<R, 4, 5, 4, 16, 9, 8>(x, d, afd, bl, dl, dlive, lane);
+    else
+      fit_nd_lines<R, MTO, MTB, MTC, 0, 0, 0>(x, d, afd, bl, dl, dlive, lane);
+  }
+}
+
 // Asynchronous copy of one array into shared memory (cp.async, SASS LDGSTS): the destination is shifted so that it has
 // the source's alignment modulo 16 bytes, the body then moves in 16-byte pieces and only the ragged head / tail element
 // by element — arrays of an odd number of reals (65 x 65 doubles = 33 800 B) start at every other 8-byte offset.
@@ -223,8 +296,9 @@ __device__ __forceinline__ R* fit_nd_load_async(unsigned char* buf16, const R* g
 // own named barrier), the matrices are shared by the whole CTA.  Small arrays (65 x 65: 10 line groups per pass) keep
 // only 2 warps busy without idle barrier rounds, so an SM runs 6 such teams side by side in ONE CTA with ONE copy of the
 // matrices, instead of 4 CTAs of 4 half-idle warps with a copy each.
-template <typename R, int MTO, int MTB, int MTC, bool AFG>
-__global__ void __launch_bounds__(MTB <= 4 ? 512 : 256) fit_nd_kernel(const __grid_constant__ FitNdParams prm) {
+// SPEC (17 / 33 / 65): all transformed dimensions have this size: the matrices live in registers (no shared-memory copy).
+template <typename R, int MTO, int MTB, int MTC, bool AFG, int SPEC = 0>
+__global__ void __launch_bounds__((MTB <= 4 && SPEC != 65) ? 512 : 256) fit_nd_kernel(const __grid_constant__ FitNdParams prm) {
   extern __shared__ __align__(16) unsigned char fastcheb_smem[];
   // [1 KB header: per team 8 partial maxima + flag] [matrices unless AFG] [array buffers, 16-byte aligned, 16 bytes of
   // slack]  (no static shared memory: the kernel is launched with the opt-in maximum of dynamic shared memory)
@@ -236,11 +310,17 @@ __global__ void __launch_bounds__(MTB <= 4 ? 512 : 256) fit_nd_kernel(const __gr
   double* af_s = reinterpret_cast<double*>(fastcheb_smem + 1024);
   const int reals = prm.reals;
   const size_t bufBytes = (((size_t)reals * sizeof(R) + 15) / 16) * 16 + 16;
-  unsigned char* bufs = fastcheb_smem + 1024 + (AFG ? 0 : (((size_t)prm.afragDoubles * 8 + 15) / 16) * 16) +
+  unsigned char* bufs = fastcheb_smem + 1024 + ((AFG || SPEC != 0) ? 0 : (((size_t)prm.afragDoubles * 8 + 15) / 16) * 16) +
                         (size_t)team * prm.nbuf * bufBytes;
-  if constexpr (!AFG) {
+  if constexpr (!AFG && SPEC == 0) {
     for (int i = threadIdx.x; i < prm.afragDoubles; i += blockDim.x) af_s[i] = prm.afrag[i];
     __syncthreads();  // the only CTA-wide barrier
+  }
+  // SPEC: this lane's A-fragment values of the one matrix set, in registers for the whole kernel
+  [[maybe_unused]] double areg[fit_nd_areg_count(SPEC)];
+  if constexpr (SPEC != 0) {
+#pragma unroll
+    for (int i = 0; i < fit_nd_areg_count(SPEC); ++i) areg[i] = prm.afrag[i * 32 + (threadIdx.x & 31)];
   }
   // barrier of this team (named barriers 1..15; the team is the whole CTA when prm.teams == 1)
   auto team_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_thr) : "memory"); };
@@ -266,47 +346,15 @@ __global__ void __launch_bounds__(MTB <= 4 ? 512 : 256) fit_nd_kernel(const __gr
     for (int dd = 0; dd < prm.ndim; ++dd) {
       const FitNdDim& d = prm.dim[dd];
       if (d.n <= 1) continue;  // DHT of length 1 = identity (interp.jl:43)
-      const int s = d.stride;
-      const int nlines = reals / d.n;
-      constexpr int GB = sizeof(R) == 8 ? 2 : 4;  // groups per block of 8 GB lines
-      const int ngroups = (nlines + 8 * GB - 1) / (8 * GB) * GB;
-      for (int gi = warp; gi < ngroups; gi += nwarps) {
-        // line L -> (outer o, inner i): base = o * n * s + i
-        auto base_of = [&](int L) {
-          const int o = L / s, i = L - o * s;
-          return o * d.n * s + i;
-        };
-        const int c = lane & 3, q = lane >> 2;
-        const int blk = (gi / GB) * 8 * GB, t = gi % GB;
-        auto line_of = [&](int col) { return blk + (GB == 2 ? 4 * (col & 3) + (col >> 2) + 2 * t : 4 * col + t); };
-        const int Lb = line_of(q);
-        const int bl = base_of(Lb < nlines ? Lb : 0);
-        int dl[2];
-        bool dlive[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int Ld = line_of(2 * c + h);
-          dlive[h] = Ld < nlines;
-          dl[h] = base_of(dlive[h] ? Ld : 0);
-        }
-        // matrices: shared memory (the address space stays visible to the compiler) or, AFG, global memory / L2
-        const double* afd;
-        if constexpr (AFG)
-          afd = prm.afrag + d.afrag;
-        else
-          afd = af_s + d.afrag;
-        // the common sizes run a fully unrolled copy of the pass
-        if (d.KO == 8 && d.KB == 5 && d.KC == 4)                    // n = 65
-          fit_nd_lines<R, 4, 3, 2, 8, 5, 4>(x, d, afd, bl, dl, dlive, lane);
-        else if (d.KO == 4 && d.KB == 3 && d.KC == 2)               // n = 33
-          fit_nd_lines<R, 2, 2, 1, 4, 3, 2>(x, d, afd, bl, dl, dlive, lane);
-        else if (d.KO == 2 && d.KB == 2 && d.KC == 1)               // n = 17
-          fit_nd_lines<R, 1, 1, 1, 2, 2, 1>(x, d, afd, bl, dl, dlive, lane);
-        else if (MTB >= 5 && d.KO == 16 && d.KB == 9 && d.KC == 8)  // n = 129
-          fit_nd_lines<R, 4, 5, 4, 16, 9, 8>(x, d, afd, bl, dl, dlive, lane);
-        else
-          fit_nd_lines<R, MTO, MTB, MTC, 0, 0, 0>(x, d, afd, bl, dl, dlive, lane);
-      }
+      const double* afd;  // matrices: shared memory (address space visible to the compiler) or, AFG, global memory / L2
+      if constexpr (AFG)
+        afd = prm.afrag + d.afrag;
+      else
+        afd = af_s + d.afrag;
+      if constexpr (SPEC != 0)
+        fit_nd_pass<R, MTO, MTB, MTC, SPEC>(x, d, nullptr, reals, warp, nwarps, lane, areg);
+      else
+        fit_nd_pass<R, MTO, MTB, MTC>(x, d, afd, reals, warp, nwarps, lane);
       team_sync();
     }
     // Finite check (interp.jl:40): c_{0..0} carries a non-zero weight of every input, so it is non-finite iff some
@@ -369,6 +417,168 @@ __global__ void __launch_bounds__(MTB <= 4 ? 512 : 256) fit_nd_kernel(const __gr
     }
     team_sync();  // every thread has read this buffer: it may be refilled
     if (!dbl && fn < prm.howmany) xnext = fit_nd_load_async<R>(bufs, src + fn * (long long)reals, reals, tid, team_thr);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same transform as a PIPELINE for small arrays (three buffers + the matrices fit shared memory, <= 14 line groups
+// per pass: 65 x 65, 33 x 33, 17^3 ...).  In fit_nd_kernel a CTA's warps load, transform and store in lock-step, and
+// its few line groups leave warps idle at every barrier (65 lines = 10 groups: 4 warps run 3 rounds, the last
+// half-empty): the tensor pipe was 45 % busy.  Here the warps are specialised:
+//   * one LOADER warp keeps cp.async copies of the next arrays in flight (3 buffers; completion on an mbarrier per
+//     buffer via cp.async.mbarrier.arrive),
+//   * NC CONSUMER warps — as many as a pass has line groups, so a pass is ONE round — transform the array in place; the
+//     barrier between dimensions is a named barrier of the consumers only,
+//   * one STORER warp writes the coefficients back (fusing the finite check and max|c|) while the consumers are already
+//     on the next array.
+// The consumers never wait for memory unless HBM itself is the limit.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kFitPipeBufs = 3;
+
+template <typename R, int MTO, int MTB, int MTC>
+__global__ void __launch_bounds__(512) fit_nd_pipe_kernel(const __grid_constant__ FitNdParams prm) {
+  extern __shared__ __align__(16) unsigned char fastcheb_smem[];
+  // [1 KB header: mbarriers full[3] | done[3] | empty[3]] [matrices] [3 array buffers]
+  uint64_t* full = reinterpret_cast<uint64_t*>(fastcheb_smem);
+  uint64_t* done = full + kFitPipeBufs;
+  uint64_t* empty = done + kFitPipeBufs;
+  double* af_s = reinterpret_cast<double*>(fastcheb_smem + 1024);
+  const int reals = prm.reals;
+  const size_t bufBytes = (((size_t)reals * sizeof(R) + 15) / 16) * 16 + 16;
+  unsigned char* bufs = fastcheb_smem + 1024 + (((size_t)prm.afragDoubles * 8 + 15) / 16) * 16;
+  const int NC = prm.team_warps;  // consumer warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < kFitPipeBufs; ++b) {
+      mbar_init(&full[b], 32);   // the loader's 32 lanes, each after its own copies
+      mbar_init(&done[b], NC);   // one arrival per consumer warp
+      mbar_init(&empty[b], prm.teams);   // the storer warps (prm.teams of them)
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < prm.afragDoubles; i += blockDim.x) af_s[i] = prm.afrag[i];
+  __syncthreads();  // the only CTA-wide barrier
+  const R* src = reinterpret_cast<const R*>(prm.src);
+  R* dst = reinterpret_cast<R*>(prm.dst);
+  const long long first = blockIdx.x, stride = gridDim.x;
+  auto xbase = [&](int b, const R* g) {
+    return reinterpret_cast<R*>(bufs + (size_t)b * bufBytes + (reinterpret_cast<uintptr_t>(g) & 15u));
+  };
+
+  if (warp == NC) {
+    // ---- loader
+    long long i = 0;
+    for (long long f = first; f < prm.howmany; f += stride, ++i) {
+      const int b = (int)(i % kFitPipeBufs);
+      const long long use = i / kFitPipeBufs;
+      if (use > 0) mbar_wait(&empty[b], (uint32_t)((use - 1) & 1));  // the storer has drained the previous array
+      const R* g = src + f * (long long)reals;
+      R* x = xbase(b, g);
+      const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(g) & 15u);
+      int head = (int)(((16u - mis) & 15u) / sizeof(R));
+      if (head > reals) head = reals;
+      const int nvec = (int)(((size_t)(reals - head) * sizeof(R)) / 16);
+      constexpr int per = 16 / (int)sizeof(R);
+      const int tail0 = head + nvec * per;
+      for (int k = lane; k < nvec; k += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(x + head + k * per)), "l"(g + head + k * per) : "memory");
+      for (int k = lane; k < head + (reals - tail0); k += 32) {
+        const int e = k < head ? k : tail0 + (k - head);
+        if constexpr (sizeof(R) == 8)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(x + e)), "l"(g + e) : "memory");
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(x + e)), "l"(g + e) : "memory");
+      }
+      cp_async_mbar_arrive(&full[b]);  // arrives when this lane's copies have landed
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp > NC && warp <= NC + prm.teams) {
+    // ---- storers (NS warps share an array): coefficients out, finite check (interp.jl:40) and max|c| (interp.jl:74-78) on
+    // the way.  One warp alone needs ~5000 cycles per 65 x 65 array (132 dependent LDS -> STG round trips per lane) and
+    // was the bottleneck of the first version; the loop is batched 4 deep and split over the storer warps.
+    const int NS = prm.teams, sw = warp - NC - 1;
+    const int slane = sw * 32 + lane, sthr = NS * 32;
+    long long i = 0;
+    for (long long f = first; f < prm.howmany; f += stride, ++i) {
+      const int b = (int)(i % kFitPipeBufs);
+      const long long use = i / kFitPipeBufs;
+      mbar_wait(&done[b], (uint32_t)(use & 1));
+      const R* g = src + f * (long long)reals;
+      const R* x = xbase(b, g);
+      R* o = dst + f * (long long)reals;
+      const int E = prm.E;
+      // finite check first: the rare path scans the INPUT array, which (vals == coefs allowed) the copy below overwrites
+      if (prm.bad) {
+        bool bad = false;
+        for (int e = 0; e < E; ++e) bad = bad || !(fabs((double)x[e]) <= 1.79769313486231570815e308);
+        if (bad) {
+          long long firstbad = 0x7fffffffffffffffLL;
+          for (int k = slane; k < reals; k += sthr)
+            if (!(fabs((double)g[k]) <= 1.79769313486231570815e308)) {
+              firstbad = k;
+              break;
+            }
+          if (firstbad != 0x7fffffffffffffffLL) atomicMin(prm.bad, prm.idx_base + f * (long long)reals + firstbad);
+        }
+      }
+      double mx = 0.0;
+      if (E == 1) {
+        int k = slane;
+        for (; k + 3 * sthr < reals; k += 4 * sthr) {
+          const R v0 = x[k], v1 = x[k + sthr], v2 = x[k + 2 * sthr], v3 = x[k + 3 * sthr];
+          mx = fmax(fmax(mx, fabs((double)v0)), fmax(fabs((double)v1), fmax(fabs((double)v2), fabs((double)v3))));
+          o[k] = v0;
+          o[k + sthr] = v1;
+          o[k + 2 * sthr] = v2;
+          o[k + 3 * sthr] = v3;
+        }
+        for (; k < reals; k += sthr) {
+          const R v = x[k];
+          mx = fmax(mx, fabs((double)v));
+          o[k] = v;
+        }
+      } else {
+        for (int el = slane; el < reals / E; el += sthr) {
+          const R* ce = x + (size_t)el * E;
+          for (int k = 0; k < prm.K; ++k) {
+            const double a = prm.cplx ? hypot((double)ce[2 * k], (double)ce[2 * k + 1]) : fabs((double)ce[k]);
+            mx = a > mx ? a : mx;
+          }
+          for (int e = 0; e < E; ++e) o[(size_t)el * E + e] = ce[e];
+        }
+      }
+      if (prm.maxabs) {  // maxabs is zero-initialised by the host (fit_device_t): the storer warps combine with an atomic max
+        for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(prm.maxabs + f), (unsigned long long)__double_as_longlong(mx));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[b]);
+    }
+  } else if (warp < NC) {
+    // ---- consumers
+    const int cthr = NC * 32;
+    long long i = 0;
+    for (long long f = first; f < prm.howmany; f += stride, ++i) {
+      const int b = (int)(i % kFitPipeBufs);
+      const long long use = i / kFitPipeBufs;
+      mbar_wait(&full[b], (uint32_t)(use & 1));
+      R* x = xbase(b, src + f * (long long)reals);
+      for (int dd = 0; dd < prm.ndim; ++dd) {
+        const FitNdDim& d = prm.dim[dd];
+        if (d.n <= 1) continue;
+        fit_nd_pass<R, MTO, MTB, MTC>(x, d, af_s + d.afrag, reals, warp, NC, lane);
+        asm volatile("bar.sync 1, %0;" ::"r"(cthr) : "memory");  // consumers only
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[b]);
+    }
   }
 }
 

@@ -112,3 +112,40 @@ def test_nd_fit_properties_at_size(fc):
     want = np.zeros((M, 33, 33))
     want[np.arange(M), k1, k2] = 1.0
     assert np.abs(c - want).max() <= 1e-13
+
+
+@pytest.mark.parametrize("env", [{"FASTCHEB_FITND_PIPE": "1"}, {"FASTCHEB_FITND_SPEC": "65"}, {"FASTCHEB_FITND_SPEC": "0"}],
+                         ids=["pipeline", "spec65", "nospec"])
+def test_experimental_fit_nd_variants_agree(env):
+    """The opt-in variants of the resident fit kernel (warp-specialised pipeline; register-resident matrices for n = 65;
+    no register-resident matrices at all) compute the same transform: run in a subprocess (the switches are read once),
+    a batch large enough for the pipeline (>= 2 arrays per SM), against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, os
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "oracle"))
+import numpy as np, fastcheb, cheb_oracle as orc
+rng = np.random.default_rng(5)
+for dims, hm in (((65, 65), 400), ((33, 33), 700), ((17, 17, 17), 320)):
+    for dt, tol in ((np.float64, 1e-13), (np.float32, 450 * np.finfo(np.float32).eps)):
+        v = rng.uniform(-1, 1, (hm,) + dims).astype(dt)
+        got, mx = fastcheb.chebcoefs(v, ndim=len(dims), howmany=hm, return_maxabs=True)
+        for i in (0, hm // 2, hm - 1):
+            want = orc.chebcoefs(v[i].astype(np.float64), len(dims))
+            assert np.abs(got[i] - want).max() <= tol * np.abs(want).max(), (dims, dt, i)
+        assert np.allclose(mx, np.abs(got.astype(np.float64)).reshape(hm, -1).max(axis=1), rtol=1e-6)
+    bad = rng.uniform(-1, 1, (hm,) + dims)
+    bad[hm - 3].flat[7] = np.nan
+    try:
+        fastcheb.chebcoefs(bad, ndim=len(dims), howmany=hm)
+        raise SystemExit("no DomainError")
+    except fastcheb.DomainError:
+        pass
+print("ok")
+""" % (root, root)
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
