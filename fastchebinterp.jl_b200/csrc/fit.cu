@@ -159,10 +159,18 @@ int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, i
   R* rcoefs = coefs + off;
   // N-d arrays and longer lines: the resident tensor-core kernel (whole array in shared memory, one HBM round trip;
   // finite check and per-array maximum fused)
-  bool nd_done = false;
+  bool nd_done = false, nd_max = false;
   FC_TRY(fit_nd(di, dev, ndim, dims, K, cplx, rest, dt, rvals, rcoefs, bad_dev, idx_base + off, maxabs_dev ? maxabs_dev + done : nullptr,
-                st, &nd_done));
-  if (nd_done) return FASTCHEB_OK;
+                st, &nd_done, &nd_max));
+  if (nd_done) {
+    if (nd_max && maxabs_dev) {
+      const long long nchunks = ((elems + 1023) / 1024) * rest;
+      coef_max_kernel<R><<<grid_for(nchunks * 32, 256, di->sms), 256, 0, st>>>(rcoefs, elems, rest, K, cplx, maxabs_dev + done);
+      FC_CUDA(cudaGetLastError());
+      note_launch();
+    }
+    return FASTCHEB_OK;
+  }
   if (bad_dev) {
     nonfinite_kernel<R><<<grid_for(rest * elems * E, 256, di->sms), 256, 0, st>>>(rvals, rest * elems * E, idx_base + off, bad_dev);  // interp.jl:40
     FC_CUDA(cudaGetLastError());

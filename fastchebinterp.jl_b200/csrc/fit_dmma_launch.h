@@ -22,5 +22,5 @@ void fit_afrag_host(int n, int map, bool split, std::vector<double>& h, int* ko,
 // caller then uses the generic per-dimension kernels.
 int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, int cplx, long long howmany, int dtype,
            const void* vals, void* coefs, long long* bad_dev, long long idx_base, double* maxabs_dev, cudaStream_t st,
-           bool* handled);
+           bool* handled, bool* need_max = nullptr);  // *need_max: the caller still has to reduce max|c| per array
 }  // namespace fastcheb

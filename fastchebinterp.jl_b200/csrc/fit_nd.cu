@@ -95,10 +95,111 @@ cudaError_t dispatch(int cls, const FitNdParams& prm, int grid, int threads, siz
 
 }  // namespace
 
+namespace {
+template <typename R, int MTO, int MTB, int MTC, bool AFG>
+cudaError_t launch_tile(const FitTileParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
+  auto kern = fit_nd_tile_kernel<R, MTO, MTB, MTC, AFG>;
+  cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
+  if (e != cudaSuccess) return e;
+  if (bps) return cached_occupancy(bps, reinterpret_cast<const void*>(kern), threads, smem);
+  kern<<<grid, threads, smem, st>>>(prm);
+  note_launch();
+  return cudaGetLastError();
+}
+template <typename R>
+cudaError_t dispatch_tile(int cls, const FitTileParams& prm, int grid, int threads, size_t smem, cudaStream_t st, int* bps) {
+  switch (cls) {
+    case 0: return launch_tile<R, 4, 4, 2, false>(prm, grid, threads, smem, st, bps);
+    case 1: return launch_tile<R, 4, 5, 4, false>(prm, grid, threads, smem, st, bps);
+    case 2: return launch_tile<R, 4, 9, 8, true>(prm, grid, threads, smem, st, bps);
+  }
+  return cudaErrorInvalidValue;
+}
+
+int size_class(int n) {
+  if (n <= 65) return 0;
+  if ((n - 1) % 4 != 0) return -1;  // the larger classes are sized for the twice-folded form
+  return n <= 129 ? 1 : (n <= 257 ? 2 : -1);
+}
+}  // namespace
+
+// An array too large for shared memory: dims 1..N-1 slab by slab (recursively), then the last dimension on strided
+// tiles.  *handled = false (nothing launched) when some dimension is not covered.
+static int fit_nd_split(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, int cplx, long long howmany, int dtype,
+                        const void* vals, void* coefs, long long* bad_dev, long long idx_base, double* maxabs_dev, cudaStream_t st,
+                        bool* handled, bool* need_max) {
+  *handled = false;
+  if (ndim < 2) return FASTCHEB_OK;
+  const int E = K * (cplx ? 2 : 1);
+  const size_t rs = real_size(dtype);
+  for (int d = 0; d < ndim; ++d)
+    if (dims[d] > 1 && size_class((int)dims[d]) < 0) return FASTCHEB_OK;
+  const int nl = (int)dims[ndim - 1];
+  long long inner = E;
+  for (int d = 0; d + 1 < ndim; ++d) inner *= dims[d];
+  if (inner * nl > (1LL << 31) || inner > (1LL << 30)) return FASTCHEB_OK;
+  const size_t budget = std::min<size_t>(di->smem_optin, kSmemOptinMax) - 3072;
+  const int cls = nl > 1 ? size_class(nl) : 0;
+  const NdMatrices* mats = nullptr;
+  size_t af_bytes = 0;
+  int tile_cols = 0;
+  if (nl > 1) {
+    FC_TRY(get_matrices(dev, std::vector<int>{nl}, &mats));
+    af_bytes = cls == 2 ? 0 : (((size_t)mats->doubles * 8 + 15) / 16) * 16;
+    // a tile of nl rows x tile_cols columns (+1 pad column), two CTAs per SM when possible
+    const long long room = ((long long)(budget / 2) - (long long)af_bytes) / (long long)(nl * rs) - 1;
+    tile_cols = (int)std::min<long long>((inner + 15) / 16 * 16, room / 16 * 16);
+    if (tile_cols < 16) return FASTCHEB_OK;
+  }
+  // leading dimensions: howmany * nl contiguous slabs (recursion: a slab that is itself too large splits again)
+  bool lead = false, lead_max = false;
+  FC_TRY(fit_nd(di, dev, ndim - 1, dims, K, cplx, howmany * nl, dtype, vals, coefs, bad_dev, idx_base, nullptr, st, &lead));
+  (void)lead_max;
+  if (!lead) return FASTCHEB_OK;  // nothing was launched
+  *handled = true;
+  if (nl > 1) {
+    FitTileParams prm;
+    memset(&prm, 0, sizeof prm);
+    prm.data = coefs;
+    prm.afrag = mats->d;
+    prm.afragDoubles = mats->doubles;
+    prm.narrays = howmany;
+    prm.array_stride = inner * nl;
+    prm.inner = inner;
+    prm.row_stride = (int)inner;
+    prm.tile_cols = tile_cols;
+    prm.tiles_per_array = (int)((inner + tile_cols - 1) / tile_cols);
+    prm.maxabs = (maxabs_dev && E == 1) ? maxabs_dev : nullptr;
+    prm.dim.n = nl;
+    prm.dim.stride = tile_cols + 1;
+    prm.dim.KO = mats->ko[0];
+    prm.dim.KB = mats->kb[0];
+    prm.dim.KC = mats->kc[0];
+    prm.dim.two = prm.dim.KC > 0;
+    prm.dim.afrag = 0;
+    const size_t smem = af_bytes + (size_t)nl * (tile_cols + 1) * rs + 16;
+    int bps = 0;
+    cudaError_t e = dtype == FASTCHEB_F64 ? dispatch_tile<double>(cls, prm, 0, 256, smem, st, &bps)
+                                          : dispatch_tile<float>(cls, prm, 0, 256, smem, st, &bps);
+    if (e != cudaSuccess || bps < 1)
+      return fail(FASTCHEB_ECUDA, "tile DCT-I kernel not launchable: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaErrorInvalidConfiguration));
+    const long long ntiles = howmany * prm.tiles_per_array;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)di->sms * bps));
+    e = dtype == FASTCHEB_F64 ? dispatch_tile<double>(cls, prm, grid, 256, smem, st, nullptr)
+                              : dispatch_tile<float>(cls, prm, grid, 256, smem, st, nullptr);
+    if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "tile DCT-I kernel launch failed: %s", cudaGetErrorString(e));
+  }
+  // vector / complex elements: the per-array maximum needs the element-wise infnorm: the caller's reduction kernel
+  if (maxabs_dev && (E != 1 || nl == 1)) *need_max = true;
+  return FASTCHEB_OK;
+}
+
 int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, int cplx, long long howmany, int dtype,
            const void* vals, void* coefs, long long* bad_dev, long long idx_base, double* maxabs_dev, cudaStream_t st,
-           bool* handled) {
+           bool* handled, bool* need_max) {
   *handled = false;
+  bool nm_local = false;
+  if (!need_max) need_max = &nm_local;
   static const bool off = [] {  // experiments: FASTCHEB_FIT_ND=0 keeps the generic per-dimension kernels
     const char* e = getenv("FASTCHEB_FIT_ND");
     return e && atoi(e) == 0;
@@ -155,7 +256,18 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     arrays = howmany / LB;
     per_array = reals * LB;
   }
-  if (af_bytes + (size_t)per_array * rs + 256 > budget) return FASTCHEB_OK;
+  // arrays too large for shared memory go slab by slab + strided tiles (33^3 Float64: 19 % of HBM).  Arrays that fit stay
+  // resident even when only one CTA per SM holds them (33^3 Float32, 144 KB: 14.8 % resident, 7.6 % split);
+  // FASTCHEB_FITND_SPLIT=bytes lowers the threshold (experiments)
+  static const long long split_above = [] {
+    const char* e = getenv("FASTCHEB_FITND_SPLIT");
+    return (e && *e) ? atoll(e) : -1LL;
+  }();
+  const size_t resident_max = split_above >= 0 ? (size_t)split_above : budget;
+  if (af_bytes + (size_t)per_array * rs + 1024 + 256 > std::min(budget, resident_max) && !(lines && af_bytes + (size_t)per_array * rs + 1280 <= budget)) {
+    if (lines) return FASTCHEB_OK;
+    return fit_nd_split(di, dev, ndim, dims, K, cplx, howmany, dtype, vals, coefs, bad_dev, idx_base, maxabs_dev, st, handled, need_max);
+  }
 
   auto run = [&](const void* src, void* dst, long long narr, long long arr_reals, long long first_fit, long long fits_per_arr) -> int {
     FitNdParams prm;

@@ -212,9 +212,9 @@ __host__ __device__ constexpr int fit_nd_areg_count(int spec) { return spec == 6
 // SPEC != 0: every transformed dimension has size SPEC (17, 33 or 65) and its matrices are in `areg`
 template <typename R, int MTO, int MTB, int MTC, int SPEC = 0>
 __device__ __forceinline__ void fit_nd_pass(R* x, const FitNdDim& d, const double* afd, int reals, int warp, int nwarps, int lane,
-                                            const double* areg = nullptr) {
+                                            const double* areg = nullptr, int nlines_live = -1) {
   const int s = d.stride;
-  const int nlines = reals / d.n;
+  const int nlines = nlines_live >= 0 ? nlines_live : reals / d.n;
   constexpr int GB = sizeof(R) == 8 ? 2 : 4;  // groups per block of 8 GB lines
   const int ngroups = (nlines + 8 * GB - 1) / (8 * GB) * GB;
   for (int gi = warp; gi < ngroups; gi += nwarps) {
@@ -578,6 +578,73 @@ __global__ void __launch_bounds__(512) fit_nd_pipe_kernel(const __grid_constant_
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&done[b]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Arrays that do NOT fit shared memory (33^3 Float64 = 287 KB, 17^4 = 668 KB, 65^3 ...): the leading dimensions are
+// transformed slab by slab with the resident kernel (a slab of dims 1..N-1 is contiguous), and the LAST dimension by
+// this kernel on strided tiles: `rows` = n_N rows of `ncols` consecutive reals, `row_stride` apart in global memory,
+// dense in shared memory with a row stride of tile_cols + 1 (= 1 mod 16: the bank model of fit_nd_lines holds with the
+// columns as lines).  Two HBM round trips in total instead of one per dimension with O(n^2) scalar sums.
+struct FitTileParams {
+  void* data;           // in place
+  const double* afrag;
+  int afragDoubles;
+  long long narrays, array_stride;  // reals between consecutive arrays
+  long long inner;      // columns per array = reals per row of the last dimension
+  int row_stride;       // = inner (reals)
+  int tile_cols, tiles_per_array;
+  double* maxabs;       // optional (real scalar elements only): atomic max per array, zero-initialised by the caller
+  FitNdDim dim;         // the last dimension: n = rows, stride = tile_cols + 1
+};
+
+template <typename R, int MTO, int MTB, int MTC, bool AFG>
+__global__ void __launch_bounds__(256) fit_nd_tile_kernel(const __grid_constant__ FitTileParams prm) {
+  extern __shared__ __align__(16) unsigned char fastcheb_smem[];
+  double* af_s = reinterpret_cast<double*>(fastcheb_smem);
+  R* x = reinterpret_cast<R*>(fastcheb_smem + (AFG ? 0 : (((size_t)prm.afragDoubles * 8 + 15) / 16) * 16));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if constexpr (!AFG)
+    for (int i = tid; i < prm.afragDoubles; i += blockDim.x) af_s[i] = prm.afrag[i];
+  const int rows = prm.dim.n, TS = prm.dim.stride;
+  R* data = reinterpret_cast<R*>(prm.data);
+  const long long ntiles = prm.narrays * prm.tiles_per_array;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const long long a = t / prm.tiles_per_array;
+    const int cb = (int)(t - a * prm.tiles_per_array);
+    const long long c0 = (long long)cb * prm.tile_cols;
+    const int ncols = (int)((prm.inner - c0) < prm.tile_cols ? (prm.inner - c0) : prm.tile_cols);
+    R* g = data + a * prm.array_stride + c0;
+    __syncthreads();  // the previous tile has been stored (and, first time, the matrices are in place)
+    for (int i = tid; i < rows * ncols; i += blockDim.x) {
+      const int r = i / ncols, c = i - r * ncols;
+      if constexpr (sizeof(R) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(x + r * TS + c)), "l"(g + (long long)r * prm.row_stride + c) : "memory");
+      else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(x + r * TS + c)), "l"(g + (long long)r * prm.row_stride + c) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const double* afd;
+    if constexpr (AFG)
+      afd = prm.afrag;
+    else
+      afd = af_s;
+    fit_nd_pass<R, MTO, MTB, MTC>(x, prm.dim, afd, rows * TS, warp, nwarps, lane, nullptr, ncols);
+    __syncthreads();
+    double mx = 0.0;
+    for (int i = tid; i < rows * ncols; i += blockDim.x) {
+      const int r = i / ncols, c = i - r * ncols;
+      const R v = x[r * TS + c];
+      mx = fmax(mx, fabs((double)v));
+      g[(long long)r * prm.row_stride + c] = v;
+    }
+    if (prm.maxabs) {
+      for (int off = 16; off; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(prm.maxabs + a), (unsigned long long)__double_as_longlong(mx));
     }
   }
 }
