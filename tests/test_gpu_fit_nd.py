@@ -26,6 +26,9 @@ ND_CASES = [  # dims, K, complex, howmany
     ((33, 9), None, True, 40),
     ((5, 65, 3), None, False, 7),
     ((129, 17), None, False, 6),          # class 1 (n <= 129) inside an N-d array
+    ((33, 33, 33), 2, False, 3),          # too large for shared memory in both precisions: slabs + strided tiles, vector elements
+    ((17, 17, 17, 9), None, True, 3),     # ... complex, unequal last dimension
+    ((65, 65, 20), None, False, 2),       # ... once-folded last dimension (n - 1 = 19)
 ]
 
 
@@ -94,6 +97,16 @@ def test_nd_fit_nonfinite_index_and_in_place(fc):
                                      fc._capi.MEM_HOST, 0, None)
     assert rc == 0
     assert np.array_equal(flat.reshape(40, 33, 33).transpose(0, 2, 1), ref)
+
+
+def test_large_array_nonfinite_index(fc):
+    """An array that goes through the slab + tile path reports the first non-finite input like any other."""
+    vals = np.ones((2, 33, 33, 33))
+    vals[1, 5, 7, 30] = np.nan
+    vals[1, 9, 9, 31] = np.inf
+    with pytest.raises(fc.DomainError):
+        fc.chebcoefs(vals, ndim=3, howmany=2)
+    assert fc._capi.error_index() == 33 ** 3 + 5 + 33 * 7 + 33 * 33 * 30
 
 
 def test_nd_fit_properties_at_size(fc):
