@@ -40,7 +40,14 @@ cudaError_t launch_p(const Pb1dParams& prm, const void* h_D, size_t d_count, int
 template <typename R, int AMAX, int EC, bool JAC>
 cudaError_t launch(const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
   // points per thread: the T_a(w) tables are AMAX (2 AMAX with derivatives) registers per point
-  constexpr int P = JAC ? 1 : 2;
+  // (Float32: half the registers per point, and the FP32 pipe is fast enough for the kernel to be issue-bound — twice
+  // the points per thread halve the non-FMA instructions per point)
+  constexpr int P0 = JAC ? 1 : 2;
+  constexpr int P = P0 * ((sizeof(R) == 4 && EC <= 2) ? 2 : 1);
+  if constexpr (P != P0) {
+    static const bool small = getenv("FASTCHEB_PB_SMALLP") != nullptr;  // experiments
+    if (small) return launch_p<R, AMAX, EC, P0, JAC>(prm, h_D, d_count, sms, st);
+  }
   return launch_p<R, AMAX, EC, P, JAC>(prm, h_D, d_count, sms, st);
 }
 
@@ -88,6 +95,7 @@ int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
   prm.e0 = 0;
   prm.Etot = p->E;
   prm.M = pb.M;
+  prm.last_len = (int)p->dims[0] - pb.AMAX * (pb.M - 1);
   prm.lb = p->lb[0];
   prm.ub = p->ub[0];
   prm.tan = tan;
@@ -131,36 +139,37 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
       return p->dtype == FASTCHEB_F64 ? (long double)((const double*)raw.data())[(size_t)k * E + e]
                                       : (long double)((const float*)raw.data())[(size_t)k * E + e];
     };
-    std::vector<long double> D((size_t)(A + 1) * M);
-    // kernel layout (eval_pb1d.cuh): full groups of G rows interleaved [group][a][j][e] from offset 0, the M % G
-    // remaining rows [t][a][e] from the fixed offset pb_tail_base
+    // D[hi][lo], hi < M rows (the runtime extent), lo < A (the compile-time modulus L of the kernel)
+    std::vector<long double> D((size_t)(M + 1) * A);
+    // kernel layout (eval_pb1d.cuh): full groups of G rows interleaved [group][lo][j][e] from offset 0, the M % G
+    // remaining rows [t][lo][e] from the fixed offset pb_tail_base
     const int G = pb_group(E), ngroups = M / G;
     const size_t count = ngroups * G == M ? (size_t)M * A * E : (size_t)pb_tail_base(A, E) + (size_t)(M - ngroups * G) * A * E;
     std::vector<unsigned char> out(count * rs, 0);
     long double sum_abs = 0, sum_k2 = 0;
     for (int e = 0; e < E; ++e) {
       std::fill(D.begin(), D.end(), 0.0L);
-      for (int a = A - 1; a >= 0; --a)
-        for (int b = 0; b < M; ++b) {
-          const long double c = coef(M * a + b, e);
+      for (int hi = M - 1; hi >= 0; --hi)
+        for (int lo = 0; lo < A; ++lo) {
+          const long double c = coef(A * hi + lo, e);
           long double v;
-          if (b == 0)
+          if (lo == 0)
             v = c;
-          else if (a == 0)
-            v = c - 0.5L * D[(size_t)1 * M + (M - b)];
+          else if (hi == 0)
+            v = c - 0.5L * D[(size_t)1 * A + (A - lo)];
           else
-            v = 2.0L * c - D[(size_t)(a + 1) * M + (M - b)];
-          D[(size_t)a * M + b] = v;
+            v = 2.0L * c - D[(size_t)(hi + 1) * A + (A - lo)];
+          D[(size_t)hi * A + lo] = v;
         }
-      for (int b = 0; b < M; ++b)
-        for (int a = 0; a < A; ++a) {
-          const size_t o = b < ngroups * G
-                               ? (((size_t)(b / G) * A + a) * G + (size_t)(b % G)) * E + e
-                               : (size_t)pb_tail_base(A, E) + ((size_t)(b - ngroups * G) * A + a) * E + e;
+      for (int hi = 0; hi < M; ++hi)
+        for (int lo = 0; lo < A; ++lo) {
+          const size_t o = hi < ngroups * G
+                               ? (((size_t)(hi / G) * A + lo) * G + (size_t)(hi % G)) * E + e
+                               : (size_t)pb_tail_base(A, E) + ((size_t)(hi - ngroups * G) * A + lo) * E + e;
           if (p->dtype == FASTCHEB_F64)
-            ((double*)out.data())[o] = (double)D[(size_t)a * M + b];
+            ((double*)out.data())[o] = (double)D[(size_t)hi * A + lo];
           else
-            ((float*)out.data())[o] = (float)D[(size_t)a * M + b];
+            ((float*)out.data())[o] = (float)D[(size_t)hi * A + lo];
         }
       for (int k = 0; k < n; ++k) {
         sum_abs += fabsl(coef(k, e));

@@ -5,16 +5,20 @@
 //   (c::ChebPoly{1})(x)            /root/reference/src/eval.jl:63-70 -> evaluate, eval.jl:19-31
 //   chebgradient(c, x)             eval.jl:168-177 -> Jevaluate, eval.jl:82-101 (scale :151)
 //
-// Mathematics.  With k = M a + b (0 <= b < M, 0 <= a < A, A M >= n) and w = T_M(z):
-//     T_{Ma}(z) = T_a(w),      T_{Ma}(z) T_b(z) = (T_{Ma+b}(z) + T_{|Ma-b|}(z)) / 2,
-// so the functions T_a(w) T_b(z) have the distinct degrees Ma + b: a basis of the polynomials of degree < A M.  The
-// plan (eval_pb1d.cu, long double on the host) rewrites the Chebyshev coefficients once,
-//     sum_k c_k T_k(z) = sum_b T_b(z) * ( sum_a D[a][b] T_a(w) ),
-// by the triangular recursion  D[a][0] = c_{Ma},  D[a][b] = 2 c_{Ma+b} - D[a+1][M-b]  (a >= 1),
-// D[0][b] = c_b - D[1][M-b] / 2.  A thread keeps T_0..T_{A-1}(w) of its points in registers; the inner sums are one
-// DFMA per coefficient with the coefficient broadcast from shared memory, the outer sum one DFMA per b:
-//     n + A + 3 M  FP64 operations per point instead of 2 n   (order 200, A = 16, M = 13: 263 instead of 402).
-// The gradient needs T_a'(w), T_b'(z) and w' = T_M'(z):  dv/dz = sum_b T_b' g_b + w' sum_b T_b g'_b.
+// Mathematics.  With k = L hi + lo (0 <= lo < L, 0 <= hi < H, L H >= n) and w = T_L(z):
+//     T_{L hi}(z) = T_hi(w),      T_{L hi}(z) T_lo(z) = (T_{L hi + lo}(z) + T_{|L hi - lo|}(z)) / 2,
+// so the functions T_hi(w) T_lo(z) have the distinct degrees L hi + lo: a basis of the polynomials of degree < L H.
+// The plan (eval_pb1d.cu, long double on the host) rewrites the Chebyshev coefficients once,
+//     sum_k c_k T_k(z) = sum_hi T_hi(w) * ( sum_lo D[hi][lo] T_lo(z) ),
+// by the triangular recursion  D[hi][0] = c_{L hi},  D[hi][lo] = 2 c_{L hi + lo} - D[hi+1][L-lo]  (hi >= 1),
+// D[0][lo] = c_lo - D[1][L-lo] / 2.  L = AMAX is a compile-time constant (8 or 16): a thread keeps T_0..T_{L-1}(z) of
+// its points in registers, and the next step of the same recurrence IS w; the inner sums are one DFMA per
+// coefficient with the coefficient a constant-bank operand, the outer factor T_hi(w) advances by its own recurrence
+// one row ahead, the outer sum is one DFMA per row:
+//     n + L + 2 H  FP64 operations per point instead of 2 n   (order 200, L = 16, H = 13: 236 instead of 402).
+// (The first version kept the HIGH factor T_a(w) in registers and ran the low one on the fly; it needed a separate
+// recurrence for w = T_M(z) ahead of everything else: n + A + 3 M operations and a dependent prologue twice as long.)
+// The gradient needs T_lo'(z), T_hi'(w) and w' = T_L'(z):  dv/dz = w' sum_hi T_hi'(w) g_hi + sum_hi T_hi(w) g'_hi.
 //
 // Numerics.  z is the oracle's z (same IEEE sequence, eval.jl:65); the summation order differs from Clenshaw's, so
 // results agree with the oracle within rounding, not bit for bit.  Both algorithms lose accuracy like k^2 eps next
@@ -27,7 +31,7 @@
 
 namespace fastcheb {
 
-// rows b of D processed together (their coefficients are interleaved, see the kernel): 8 independent accumulation
+// rows hi of D processed together (their coefficients are interleaved, see the kernel): 8 independent accumulation
 // chains per thread whatever the number of components
 __host__ __device__ constexpr int pb_group(int ec) { return ec == 1 ? 4 : (ec == 2 ? 2 : 1); }
 
@@ -37,12 +41,14 @@ struct Pb1dParams {
   void* out_J;      // derivatives: out_J[p * J_stride + e0 + e]   (mode 0)
   long long* bad;   // first out-of-domain point index (atomicMin), may be null
   long long npts, idx_base, v_stride, J_stride;
-  int e0, Etot, M;
+  int e0, Etot, M;  // M = H, the number of rows hi
   double lb, ub;
   // Jacobian contraction (AD rules, chainrules.jl:4-39), as in the other evaluation kernels: 0 = store J;
   // 1 = pullback out_J[p] = sum_e J[e] tan[p*Etot + e]; 2 = pushforward out_J[p*Etot + e] = J[e] tan[p]
   const void* tan;
   int mode;
+  int spin;      // always 0 (see the kernel)
+  int last_len;  // number of non-zero entries of the last row of D: n - L (H - 1)
 };
 
 // The coefficients travel IN THE KERNEL PARAMETERS (constant bank 0; up to 18 KB of the 32 KB parameter space): every
@@ -50,9 +56,9 @@ struct Pb1dParams {
 // register-file write, whereas a broadcast LDS writes the value into all 32 lanes' registers — measured
 // (profiles/r01_micro_fp64.jsonl, lds128_dfma_p2) that return path caps DFMAs fed two per loaded double at 69 % of the
 // FP64 peak, which is where the first version of this kernel sat (63 % pipe utilisation, profiles/r02_pb1d_*).
-// Layout of D: floor(M / pb_group(EC)) groups [group][a][j][e] (b = pb_group(EC) * group + j) from offset 0, the
-// M % pb_group(EC) remaining rows [t][a][e] from pb_tail_base (a fixed offset: all offsets are compile-time).
-// M <= pb_mmax(AMAX) rows; the groups sit at compile-time offsets, the M % BU single rows after the LAST POSSIBLE group
+// Layout of D: floor(H / pb_group(EC)) groups [group][lo][j][e] (hi = pb_group(EC) * group + j) from offset 0, the
+// H % pb_group(EC) remaining rows [t][lo][e] from pb_tail_base (a fixed offset: all offsets are compile-time).
+// H <= pb_mmax(AMAX) rows; the groups sit at compile-time offsets, the H % BU single rows after the LAST POSSIBLE group
 __host__ __device__ constexpr int pb_mmax(int amax) { return amax == 8 ? 16 : 32; }
 __host__ __device__ constexpr int pb_tail_base(int amax, int ec) { return pb_mmax(amax) * amax * ec; }
 __host__ __device__ constexpr int pb_cap(int amax, int ec) { return (pb_mmax(amax) + pb_group(ec) - 1) * amax * ec; }
@@ -63,8 +69,16 @@ struct Pb1dArgs {
   R D[CAP];
 };
 
+// resident CTAs of 256 threads the register allocation aims at: the short-table (AMAX = 8) scalar Float64 value kernel
+// needs 82 registers, which the allocation granularity turns into 2 CTAs per SM — capped at 80 it runs 3 (24 warps:
+// the order-64 shapes are latency-bound, profiles/r02_pb1d_order64_ncu_summary.txt)
+template <typename R, int AMAX, int EC, bool JAC>
+__host__ __device__ constexpr int pb_min_ctas() {
+  return (sizeof(R) == 8 && AMAX == 8 && EC == 1 && !JAC) ? 3 : 2;
+}
+
 template <typename R, int AMAX, int EC, int P, bool JAC>
-__global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant__ Pb1dArgs<R, pb_cap(AMAX, EC)> args) {
+__global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1d_kernel(const __grid_constant__ Pb1dArgs<R, pb_cap(AMAX, EC)> args) {
   const Pb1dParams& prm = args.p;
   const R* Ds = args.D;
   const int M = prm.M;
@@ -111,51 +125,19 @@ __global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant
     }
     if (first_bad != 0x7fffffffffffffffLL && prm.bad) atomicMin(prm.bad, first_bad + prm.idx_base);
 
-    // w = T_M(z), w' = T_M'(z): the points' recurrences advance together (independent chains interleave).  (Doubling
-    // formulas T_{2m} = 2 T_m^2 - 1 would cut the dependency depth to log2 M but measured less accurate — they failed
-    // the 16 eps sum|c| check on the order-200 README polynomial — and no faster.)
-    {
-      R z2[P], tkm[P], tk[P];
-      [[maybe_unused]] R dkm[P], dk[P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        z2[p] = rmul(R(2), z[p]);
-        tkm[p] = R(1);
-        tk[p] = z[p];
-        if constexpr (JAC) {
-          dkm[p] = R(0);
-          dk[p] = R(1);
-        }
-      }
-      for (int k = 1; k < M; ++k) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const R tn = rfma(z2[p], tk[p], -tkm[p]);
-          if constexpr (JAC) {
-            const R dn = rsub(rfma(z2[p], dk[p], rmul(R(2), tk[p])), dkm[p]);
-            dkm[p] = dk[p];
-            dk[p] = dn;
-          }
-          tkm[p] = tk[p];
-          tk[p] = tn;
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        w[p] = tk[p];
-        if constexpr (JAC) dw[p] = dk[p];
-      }
-    }
-    // T_a(w) (and T_a'(w)) of every point, in registers
+    // T_lo(z) (and T_lo'(z)) for lo < L = AMAX of every point, in registers; one more step of the same recurrence is
+    // w = T_L(z) (and w' = T_L'(z)), the argument of the outer factor: T_{L hi}(z) = T_hi(w).  (Doubling formulas
+    // T_{2m} = 2 T_m^2 - 1 would cut the dependency depth to log2 L but measured less accurate — they failed the
+    // 16 eps sum|c| check on the order-200 README polynomial — and no faster.)
     R Ta[P][AMAX];
     [[maybe_unused]] R dTa[JAC ? P : 1][JAC ? AMAX : 1];
     {
-      R w2[P];
+      R z2[P];
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        w2[p] = rmul(R(2), w[p]);
+        z2[p] = rmul(R(2), z[p]);
         Ta[p][0] = R(1);
-        Ta[p][1] = w[p];
+        Ta[p][1] = z[p];
         if constexpr (JAC) {
           dTa[p][0] = R(0);
           dTa[p][1] = R(1);
@@ -165,15 +147,25 @@ __global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant
       for (int a = 2; a < AMAX; ++a)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-          Ta[p][a] = rfma(w2[p], Ta[p][a - 1], -Ta[p][a - 2]);
-          if constexpr (JAC) dTa[p][a] = rsub(rfma(w2[p], dTa[p][a - 1], rmul(R(2), Ta[p][a - 1])), dTa[p][a - 2]);
+          Ta[p][a] = rfma(z2[p], Ta[p][a - 1], -Ta[p][a - 2]);
+          if constexpr (JAC) dTa[p][a] = rsub(rfma(z2[p], dTa[p][a - 1], rmul(R(2), Ta[p][a - 1])), dTa[p][a - 2]);
         }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        w[p] = rfma(z2[p], Ta[p][AMAX - 1], -Ta[p][AMAX - 2]);
+        if constexpr (JAC) dw[p] = rsub(rfma(z2[p], dTa[p][AMAX - 1], rmul(R(2), Ta[p][AMAX - 1])), dTa[p][AMAX - 2]);
+      }
     }
 
-    // sums over b, two interleaved accumulators each (even / odd rows) so that consecutive rows do not chain
+    // A loop that never runs (spin = 0).  Without it the tile loop is an INNERMOST loop, and ptxas hoists the ~250
+    // loop-invariant constant-bank loads of the coefficients out of it: the uniform registers overflow into vector
+    // registers and from there into local memory (128 registers + 184 bytes of spills instead of 114 registers).
+#pragma unroll 1
+    for (int r = 0; r < prm.spin; ++r) __nanosleep(1);
+    // sums over the rows hi, two interleaved accumulators each (even / odd rows) so that consecutive rows do not chain
     R v[2][P][EC];
-    [[maybe_unused]] R dv1[2][JAC ? P : 1][EC], dv2[2][JAC ? P : 1][EC];  // sum_b T_b' g_b and sum_b T_b g'_b
-    R tbm[P], tb[P], z2[P];                                                // T_{b-1}(z), T_b(z)
+    [[maybe_unused]] R dv1[2][JAC ? P : 1][EC], dv2[2][JAC ? P : 1][EC];  // sum_hi T_hi'(w) g_hi and sum_hi T_hi(w) g'_hi
+    R tbm[P], tb[P], z2[P];                                                // T_{hi-1}(w), T_hi(w); z2 = 2 w
     [[maybe_unused]] R dbm[JAC ? P : 1], db[JAC ? P : 1];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
@@ -182,15 +174,15 @@ __global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant
         v[0][p][e] = v[1][p][e] = R(0);
         if constexpr (JAC) dv1[0][p][e] = dv1[1][p][e] = dv2[0][p][e] = dv2[1][p][e] = R(0);
       }
-      z2[p] = rmul(R(2), z[p]);
-      tbm[p] = z[p];  // T_{-1} = T_1: the recurrence T_{b+1} = 2 z T_b - T_{b-1} then also yields T_1 from T_0
+      z2[p] = rmul(R(2), w[p]);
+      tbm[p] = w[p];  // T_{-1} = T_1: the recurrence T_{b+1} = 2 w T_b - T_{b-1} then also yields T_1 from T_0
       tb[p] = R(1);
       if constexpr (JAC) {
-        dbm[p] = R(1);  // T_{-1}' = T_1' = 1: the derivative recurrence T_{b+1}' = 2 T_b + 2 z T_b' - T_{b-1}' then gives
+        dbm[p] = R(1);  // T_{-1}' = T_1' = 1: the derivative recurrence T_{b+1}' = 2 T_b + 2 w T_b' - T_{b-1}' then gives
         db[p] = R(0);   // T_1' = 2 - 1 = 1 from T_0' = 0
       }
     }
-    // T_b(z), T_b'(z) of the next row: taken BEFORE the row's contraction, so the recurrence step overlaps it
+    // T_hi(w), T_hi'(w) of the next row: taken BEFORE the row's contraction, so the recurrence step overlaps it
     auto next_tb = [&](R (&t)[P], [[maybe_unused]] R (&d)[JAC ? P : 1]) {
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -240,7 +232,7 @@ __global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant
         for (int p = 0; p < P; ++p)
 #pragma unroll
           for (int e = 0; e < EC; ++e) {
-            g[j][p][e] = Dg[j * EC + e];  // a = 0: T_0(w) = 1, T_0'(w) = 0
+            g[j][p][e] = Dg[j * EC + e];  // lo = 0: T_0(z) = 1, T_0'(z) = 0
             if constexpr (JAC) gd[j][p][e] = R(0);
           }
 #pragma unroll
@@ -279,8 +271,11 @@ __global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant
             g[p][e] = Dt[e];
             if constexpr (JAC) gd[p][e] = R(0);
           }
+        // the LAST row of D is short (its entries lo >= n - L (H - 1) are zero): stop at the next multiple of 4
+        const int alim = t == ntail - 1 ? prm.last_len : AMAX;
 #pragma unroll
         for (int a = 1; a < AMAX; ++a) {
+          if ((a & 3) == 1 && a >= alim) break;  // uniform
 #pragma unroll
           for (int e = 0; e < EC; ++e) {
             const R d = Dt[a * EC + e];
@@ -305,7 +300,7 @@ __global__ void __launch_bounds__(256, 2) eval_pb1d_kernel(const __grid_constant
         R Js[EC];
 #pragma unroll
         for (int e = 0; e < EC; ++e)
-          Js[e] = rdiv(rmul(rfma(dw[p], dv2[0][p][e] + dv2[1][p][e], dv1[0][p][e] + dv1[1][p][e]), R(2)), span);  // eval.jl:151
+          Js[e] = rdiv(rmul(rfma(dw[p], dv1[0][p][e] + dv1[1][p][e], dv2[0][p][e] + dv2[1][p][e]), R(2)), span);  // eval.jl:151
         if (prm.mode == 0) {
 #pragma unroll
           for (int e = 0; e < EC; ++e) out_J[idx[p] * prm.J_stride + prm.e0 + e] = Js[e];

@@ -71,7 +71,7 @@ struct SharedParams {
   void* out;            // [howmany][M][E]
   long long rows;       // howmany * E
   long long M;
-  int n, E, RS, der, chunks;
+  int n, E, RS, der;
   double lb, ub;
 };
 
@@ -79,7 +79,7 @@ struct SharedParams {
 // SM, whose 8 warps move in lock-step through the tile barriers); RT = 1 fits two CTAs per SM, which overlap each
 // other's epilogues and barriers.
 template <typename R, int RT>
-__global__ void __launch_bounds__(256, RT == 1 ? 2 : 1) eval_shared_kernel(const __grid_constant__ SharedParams prm) {
+__global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_constant__ SharedParams prm) {
   constexpr int kSharedRows = 8 * 8 * RT;  // rows per CTA
   extern __shared__ __align__(16) unsigned char fastcheb_smem[];
   double* tile[2] = {reinterpret_cast<double*>(fastcheb_smem),
@@ -91,7 +91,6 @@ __global__ void __launch_bounds__(256, RT == 1 ? 2 : 1) eval_shared_kernel(const
   R* out = reinterpret_cast<R*>(prm.out);
   const long long ntiles = (prm.M + kSharedPT - 1) / kSharedPT;
   const long long nblocks = (prm.rows + kSharedRows - 1) / kSharedRows;
-  const long long nchunks = prm.chunks, tpc = (ntiles + nchunks - 1) / nchunks;  // point-tile chunks: more, smaller work items
   const int tileDoubles = kSharedPT * RS;
 
   auto load_tile = [&](int b, long long pt) {
@@ -102,91 +101,126 @@ __global__ void __launch_bounds__(256, RT == 1 ? 2 : 1) eval_shared_kernel(const
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  for (long long item = blockIdx.x; item < nblocks * nchunks; item += gridDim.x) {
-    const long long blk = item / nchunks, chunk = item - blk * nchunks;
-    const long long pt0 = chunk * tpc, pt1 = pt0 + tpc < ntiles ? pt0 + tpc : ntiles;
-    if (pt0 >= pt1) continue;
-    // A fragments of this warp's RT x 8 rows: lane (c, q) holds C[row q][k = 1 + 4 ks + c]; the k = 0 column separately
-    double A[RT][kSharedKS], c0[RT][2];
-    long long rowq[RT];
-    bool lived[RT][2];
-#pragma unroll
-    for (int t = 0; t < RT; ++t) {
-      const long long r0 = blk * kSharedRows + warp * (8 * RT) + t * 8;
-      rowq[t] = r0 + q;
-      const bool liveq = rowq[t] < prm.rows;
-      const long long f = liveq ? rowq[t] / E : 0;
-      const int e = liveq ? (int)(rowq[t] - f * E) : 0;
-      const R* cr = coefs + (f * n) * E + e;  // element k at cr[k * E]
-#pragma unroll
-      for (int ks = 0; ks < kSharedKS; ++ks) {
-        const int k = 1 + 4 * ks + c;
-        A[t][ks] = (liveq && k < n) ? (double)cr[(long long)k * E] : 0.0;
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        // D fragment: lane (c, q) holds out[row q][point 2c + h]: the k = 0 coefficient of row q initialises it
-        lived[t][h] = liveq;
-        c0[t][h] = (liveq && !prm.der) ? (double)cr[0] : 0.0;
-      }
-    }
-    __syncthreads();  // the previous block's last tile has been consumed
-    load_tile(0, pt0);
-    for (long long pt = pt0; pt < pt1; ++pt) {
-      const int b = (int)((pt - pt0) & 1);
-      if (pt + 1 < pt1) {
-        load_tile(b ^ 1, pt + 1);
+  // Work = the (row block, point tile) pairs in row-block-major order; a CTA owns one CONTIGUOUS range of them (balanced
+  // to within one tile), so the table tiles stream through the two buffers without a restart at a row-block boundary and
+  // the A fragments are reloaded only when the row block changes.
+  const long long total = nblocks * ntiles;
+  const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
+  if (g0 >= g1) return;
+  // A fragments of this warp's RT x 8 rows: lane (c, q) holds C[row q][k = 1 + 4 ks + c]; the k = 0 column separately
+  double A[RT][kSharedKS], c0[RT][2];
+  long long rowq[RT];
+  bool lived[RT][2];
+  long long cur = -1;
+  load_tile(0, g0 % ntiles);
+  {
+    for (long long g = g0; g < g1; ++g) {
+      const int b = (int)((g - g0) & 1);
+      const long long blk = g / ntiles, pt = g - blk * ntiles;
+      if (g + 1 < g1) {
+        load_tile(b ^ 1, (g + 1) % ntiles);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
       } else {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
-      __syncthreads();
-      const double* T = tile[b];
-      double acc[RT][kSharedPT / 8][2];
+      if (blk != cur) {
+        cur = blk;
 #pragma unroll
-      for (int t = 0; t < RT; ++t)
+        for (int t = 0; t < RT; ++t) {
+          const long long r0 = blk * kSharedRows + warp * (8 * RT) + t * 8;
+          rowq[t] = r0 + q;
+          const bool liveq = rowq[t] < prm.rows;
+          const long long f = liveq ? rowq[t] / E : 0;
+          const int e = liveq ? (int)(rowq[t] - f * E) : 0;
+          const R* cr = coefs + (f * n) * E + e;  // element k at cr[k * E]
 #pragma unroll
-        for (int j = 0; j < kSharedPT / 8; ++j) {
-          acc[t][j][0] = c0[t][0];
-          acc[t][j][1] = c0[t][1];
-        }
+          for (int ks = 0; ks < kSharedKS; ++ks) {
+            const int k = 1 + 4 * ks + c;
+            A[t][ks] = (liveq && k < n) ? (double)cr[(long long)k * E] : 0.0;
+          }
 #pragma unroll
-      for (int ks = 0; ks < kSharedKS; ++ks) {
-        if (4 * ks + 1 >= n) break;  // uniform: shorter polynomials stop early
-#pragma unroll
-        for (int j = 0; j < kSharedPT / 8; ++j) {
-          // B fragment: lane (c, q) holds T[point 8 j + q][k = 1 + 4 ks + c]
-          const double bv = T[(8 * j + q) * RS + 4 * ks + c];
-#pragma unroll
-          for (int t = 0; t < RT; ++t) dmma884(acc[t][j][0], acc[t][j][1], A[t][ks], bv);
+          for (int h = 0; h < 2; ++h) {
+            // D fragment: lane (c, q) holds out[row q][point 2c + h]: the k = 0 coefficient of row q initialises it
+            lived[t][h] = liveq;
+            c0[t][h] = (liveq && !prm.der) ? (double)cr[0] : 0.0;
+          }
         }
       }
-      // epilogue: lane (c, q) holds points 8 j + 2c, 8 j + 2c + 1 of row q
+      __syncthreads();
+      const double* T = tile[b];
       const long long m0 = pt * kSharedPT;
       const double span = (double)rsub((R)prm.ub, (R)prm.lb);
-#pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        if (!lived[t][0]) continue;
+      // epilogue of one column tile: lane (c, q) holds points 8 j + 2c, 8 j + 2c + 1 of row q
+      auto store = [&](int t, int j, double v0, double v1) {
+        if (!lived[t][0]) return;
         const long long f = rowq[t] / E;
         const int e = (int)(rowq[t] - f * E);
         R* orow = out + (f * prm.M) * E + e;  // point m at orow[m * E]
+        const long long m = m0 + 8 * j + 2 * c;
+        if (prm.der) {  // eval.jl:151: d/dx = (d/dz * 2) / (ub - lb)
+          v0 = __ddiv_rn(__dmul_rn(v0, 2.0), span);
+          v1 = __ddiv_rn(__dmul_rn(v1, 2.0), span);
+        }
+        if (E == 1 && m + 1 < prm.M && ((reinterpret_cast<uintptr_t>(orow + m) & (2 * sizeof(R) - 1)) == 0)) {
+          if constexpr (sizeof(R) == 8)
+            *reinterpret_cast<double2*>(orow + m) = make_double2(v0, v1);
+          else
+            *reinterpret_cast<float2*>(orow + m) = make_float2((float)v0, (float)v1);
+        } else {
+          if (m < prm.M) orow[m * E] = (R)v0;
+          if (m + 1 < prm.M) orow[(m + 1) * E] = (R)v1;
+        }
+      };
+      if constexpr (RT == 1) {
+        // one row tile per warp: all 8 column tiles of the point tile accumulate together (k outermost)
+        double acc[kSharedPT / 8][2];
 #pragma unroll
         for (int j = 0; j < kSharedPT / 8; ++j) {
-          const long long m = m0 + 8 * j + 2 * c;
-          double v0 = acc[t][j][0], v1 = acc[t][j][1];
-          if (prm.der) {  // eval.jl:151: d/dx = (d/dz * 2) / (ub - lb)
-            v0 = __ddiv_rn(__dmul_rn(v0, 2.0), span);
-            v1 = __ddiv_rn(__dmul_rn(v1, 2.0), span);
+          acc[j][0] = c0[0][0];
+          acc[j][1] = c0[0][1];
+        }
+#pragma unroll
+        for (int ks = 0; ks < kSharedKS; ++ks) {
+          if (4 * ks + 1 >= n) break;  // uniform: shorter polynomials stop early
+#pragma unroll
+          for (int j = 0; j < kSharedPT / 8; ++j) {
+            // B fragment: lane (c, q) holds T[point 8 j + q][k = 1 + 4 ks + c]
+            const double bv = T[(8 * j + q) * RS + 4 * ks + c];
+            dmma884(acc[j][0], acc[j][1], A[0][ks], bv);
           }
-          if (E == 1 && m + 1 < prm.M && ((reinterpret_cast<uintptr_t>(orow + m) & (2 * sizeof(R) - 1)) == 0)) {
-            if constexpr (sizeof(R) == 8)
-              *reinterpret_cast<double2*>(orow + m) = make_double2(v0, v1);
-            else
-              *reinterpret_cast<float2*>(orow + m) = make_float2((float)v0, (float)v1);
-          } else {
-            if (m < prm.M) orow[m * E] = (R)v0;
-            if (m + 1 < prm.M) orow[(m + 1) * E] = (R)v1;
+        }
+#pragma unroll
+        for (int j = 0; j < kSharedPT / 8; ++j) store(0, j, acc[j][0], acc[j][1]);
+      } else {
+        // RT row tiles per warp, column tiles two at a time (k innermost): every B fragment feeds RT DMMAs, 2 RT
+        // independent accumulator chains per warp, and only those 2 RT accumulators are live next to the A fragments —
+        // 128 registers, two CTAs per SM (all 8 column tiles at once need ~250)
+#pragma unroll
+        for (int j = 0; j < kSharedPT / 8; j += 2) {
+          double acc[RT][2][2];
+#pragma unroll
+          for (int t = 0; t < RT; ++t)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              acc[t][jj][0] = c0[t][0];
+              acc[t][jj][1] = c0[t][1];
+            }
+          const double* T0 = T + (8 * j + q) * RS + c;
+          const double* T1 = T0 + 8 * RS;
+#pragma unroll
+          for (int ks = 0; ks < kSharedKS; ++ks) {
+            if (4 * ks + 1 >= n) break;  // uniform
+            const double b0 = T0[4 * ks], b1 = T1[4 * ks];
+#pragma unroll
+            for (int t = 0; t < RT; ++t) {
+              dmma884(acc[t][0][0], acc[t][0][1], A[t][ks], b0);
+              dmma884(acc[t][1][0], acc[t][1][1], A[t][ks], b1);
+            }
           }
+#pragma unroll
+          for (int t = 0; t < RT; ++t)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) store(t, j + jj, acc[t][jj][0], acc[t][jj][1]);
         }
       }
       __syncthreads();  // tile b may be refilled
@@ -315,11 +349,8 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
     int bps = 1;
     FC_CUDA(cached_occupancy(&bps, kern, 256, smem));
     const long long slots = (long long)di->sms * std::max(1, bps);
-    // work items = row blocks x point-tile chunks: enough of them that the last wave is a small fraction of the launch
-    long long chunks = 1;
-    while (chunks < ntiles && nblocks * chunks < 16 * slots && (nblocks * chunks) % slots * 8 < slots * 7 && chunks < 8) ++chunks;
-    sp.chunks = (int)chunks;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(nblocks * chunks, slots));
+    // one contiguous range of (row block, point tile) pairs per resident CTA
+    const int grid = (int)std::max<long long>(1, std::min<long long>(nblocks * ntiles, slots));
     void* args[] = {&sp};
     FC_CUDA(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(256), args, smem, st));
     FC_CUDA(cudaGetLastError());

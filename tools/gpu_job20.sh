@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_product.py tests/test_gpu_eval.py -x -q 2>&1 | tail -2
+python tools/probe_pb1d.py 2>&1 | grep "cfg\|check"
+echo RT1; python tools/probe_shared.py
+echo RT2; FASTCHEB_SHARED_RT=2 python tools/probe_shared.py
+FASTCHEB_SHARED_RT=2 python -m pytest tests/test_gpu_eval.py -x -q -k "shared" 2>&1 | tail -2
