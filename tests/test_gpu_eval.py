@@ -308,6 +308,45 @@ def test_eval_many_bit_identical_to_oracle(fc, orc, dt):
     assert ei.value.index == 3 * 11 + 4
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+def test_eval_many_large_batches_bit_identical(fc, orc, dt):
+    """Batches of hundreds to thousands of scalar polynomials (more polynomials than resident warps, ragged point counts,
+    per-polynomial and shared bounds): bit-identical to the oracle, and a sub-batch evaluated alone gives the same bits."""
+    rng = np.random.default_rng(79)
+    for n, howmany, M, per_poly in ((65, 301, 1000, True), (64, 1200, 130, False), (33, 700, 500, True), (17, 5000, 17, True),
+                                    (40, 333, 999, False), (5, 2000, 33, True), (1, 400, 400, True), (2, 400, 400, False)):
+        c = rng.uniform(-1, 1, (howmany, n)).astype(dt)
+        if per_poly:
+            lb = rng.uniform(-2, 0, howmany).astype(dt)
+            ub = (lb + rng.uniform(0.5, 3, howmany)).astype(dt)
+            lbm, ubm = lb[:, None], ub[:, None]
+        else:
+            lb, ub = dt(-1.25), dt(2.5)
+            lbm, ubm = lb, ub
+        pts = np.clip((lbm + (ubm - lbm) * rng.random((howmany, M))).astype(dt), lbm, ubm)
+        pts[:, 0], pts[:, -1] = lb, ub                                    # closed box
+        v, d = fc.eval_many(c, lb, ub, pts, deriv=True)
+        assert np.array_equal(fc.eval_many(c, lb, ub, pts), v)
+        # the first 40 polynomials alone: same bits
+        sl = slice(0, 40)
+        v40, d40 = fc.eval_many(c[sl], lb[sl] if per_poly else lb, ub[sl] if per_poly else ub, pts[sl], deriv=True)
+        assert np.array_equal(v[sl], v40) and np.array_equal(d[sl], d40), (n, howmany, M)
+        for f in (0, 31, 32, howmany // 2, howmany - 1):
+            lf, uf = (lb[f], ub[f]) if per_poly else (lb, ub)
+            ref = orc.OracleChebPoly(c[f], np.array([lf]), np.array([uf]))
+            rv, rJ = ref.jacobian(pts[f].reshape(-1, 1))
+            assert np.array_equal(v[f], rv.reshape(v[f].shape)), (n, howmany, M, f)
+            assert np.array_equal(d[f], rJ.reshape(d[f].shape)), (n, howmany, M, f)
+    # domain error: the flat index of the first offending point
+    c = rng.uniform(-1, 1, (600, 20)).astype(dt)
+    pts = rng.random((600, 100)).astype(dt)
+    pts[417, 63] = 1.5
+    pts[599, 99] = np.nan
+    with pytest.raises(fc.ArgumentError) as ei:
+        fc.eval_many(c, 0.0, 1.0, pts)
+    assert ei.value.index == 417 * 100 + 63
+
+
 def test_cfg5_fit_then_eval_many(fc):
     """configs[4] end to end at full size: 10^5 order-64 fits (tensor-core DCT-I), then every polynomial evaluated at
     10^3 of its own points (10^8 evaluations) against the analytic functions f_i(x) = sin(a_i x + b_i)."""
