@@ -28,12 +28,16 @@ struct ManyParams {
   int n, bounds_per_poly;
 };
 
+template <typename R> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
 template <typename R, int E, int P, bool DER>
 __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ ManyParams prm) {
   extern __shared__ __align__(16) unsigned char fastcheb_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int n = prm.n, nE = n * E;
-  R* cs = reinterpret_cast<R*>(fastcheb_smem) + (size_t)warp * nE;
+  R* cs = reinterpret_cast<R*>(fastcheb_smem) + (size_t)warp * ((nE + 1) & ~1);  // even stride: 16-byte aligned pairs
   const R* coefs = reinterpret_cast<const R*>(prm.coefs);
   const R* pts = reinterpret_cast<const R*>(prm.pts);
   R* out_v = reinterpret_cast<R*>(prm.out_v);
@@ -81,21 +85,36 @@ __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ 
           b1[p][e] = b2[p][e] = R(0);
           if constexpr (DER) d1[p][e] = d2[p][e] = R(0);
         }
-      for (int j = n - 1; j >= 1; --j) {
+      auto step = [&](int e, R cj) {
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const R cj = cs[j * E + e];
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const R nb = rsub(rfma(z2[p], b1[p][e], cj), b2[p][e]);                    // eval.jl:28 / :96
-            if constexpr (DER) {
-              const R nd = rsub(rfma(z2[p], d1[p][e], rmul(R(2), b1[p][e])), d2[p][e]);  // eval.jl:97
-              d2[p][e] = d1[p][e];
-              d1[p][e] = nd;
-            }
-            b2[p][e] = b1[p][e];
-            b1[p][e] = nb;
+        for (int p = 0; p < P; ++p) {
+          const R nb = rsub(rfma(z2[p], b1[p][e], cj), b2[p][e]);                    // eval.jl:28 / :96
+          if constexpr (DER) {
+            const R nd = rsub(rfma(z2[p], d1[p][e], rmul(R(2), b1[p][e])), d2[p][e]);  // eval.jl:97
+            d2[p][e] = d1[p][e];
+            d1[p][e] = nd;
           }
+          b2[p][e] = b1[p][e];
+          b1[p][e] = nb;
+        }
+      };
+      if constexpr (E == 1) {
+        // scalar coefficients: two per shared-memory load (the warp's region is 16-byte aligned, pairs (c_{j-1}, c_j), j odd)
+        int j = n - 1;
+        if (j >= 1 && (j & 1) == 0) {
+          step(0, cs[j]);
+          --j;
+        }
+        for (; j >= 3; j -= 2) {
+          const auto c2 = *reinterpret_cast<const typename Vec2<R>::type*>(cs + j - 1);
+          step(0, c2.y);
+          step(0, c2.x);
+        }
+        if (j == 1) step(0, cs[1]);
+      } else {
+        for (int j = n - 1; j >= 1; --j) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) step(e, cs[j * E + e]);
         }
       }
 #pragma unroll
@@ -117,7 +136,7 @@ template <typename R, int E, bool DER>
 cudaError_t launch(const ManyParams& prm, int sms, cudaStream_t st) {
   constexpr int P = sizeof(R) == 8 ? (E >= 3 ? 2 : 4) : (E >= 3 ? 2 : 4);
   const int warps = 8;
-  const size_t smem = (size_t)warps * prm.n * E * sizeof(R);
+  const size_t smem = (size_t)warps * (((size_t)prm.n * E + 1) & ~(size_t)1) * sizeof(R);
   auto kern = eval_many_kernel<R, E, P, DER>;
   cudaError_t e = ensure_max_smem(reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) return e;
