@@ -134,7 +134,8 @@ int fit_passes(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int
 
 template <typename R>
 int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int cplx, int K, int64_t howmany,
-                 const R* vals, R* coefs, double* maxabs_dev, long long* bad_dev, long long idx_base, cudaStream_t st) {
+                 const R* vals, R* coefs, double* maxabs_dev, long long* bad_dev, long long idx_base, cudaStream_t st,
+                 double* stats_dev = nullptr, const int* stats_hoff = nullptr, double stats_tol = 0.0, bool* stats_done = nullptr) {
   const int E = K * (cplx ? 2 : 1);
   long long elems = 1;
   for (int d = 0; d < ndim; ++d) elems *= dims[d];
@@ -161,7 +162,7 @@ int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, i
   // finite check and per-array maximum fused)
   bool nd_done = false, nd_max = false;
   FC_TRY(fit_nd(di, dev, ndim, dims, K, cplx, rest, dt, rvals, rcoefs, bad_dev, idx_base + off, maxabs_dev ? maxabs_dev + done : nullptr,
-                st, &nd_done, &nd_max));
+                st, &nd_done, &nd_max, stats_dev, stats_hoff, stats_tol, stats_done));
   if (nd_done) {
     if (nd_max && maxabs_dev) {
       const long long nchunks = ((elems + 1023) / 1024) * rest;
@@ -188,12 +189,14 @@ int fit_device_t(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, i
 
 int fit_device(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int dtype, int cplx, int K, int64_t howmany,
                const void* vals, void* coefs, double* maxabs_dev, long long* bad_dev, cudaStream_t st,
-               long long idx_base = 0) {
+               long long idx_base = 0, double* stats_dev = nullptr, const int* stats_hoff = nullptr, double stats_tol = 0.0,
+               bool* stats_done = nullptr) {
+  if (stats_done) *stats_done = false;
   if (dtype == FASTCHEB_F64)
     return fit_device_t<double>(di, dev, ndim, dims, cplx, K, howmany, (const double*)vals, (double*)coefs, maxabs_dev,
-                                bad_dev, idx_base, st);
+                                bad_dev, idx_base, st, stats_dev, stats_hoff, stats_tol, stats_done);
   return fit_device_t<float>(di, dev, ndim, dims, cplx, K, howmany, (const float*)vals, (float*)coefs, maxabs_dev,
-                             bad_dev, idx_base, st);
+                             bad_dev, idx_base, st, stats_dev, stats_hoff, stats_tol, stats_done);
 }
 
 int check_args(int ndim, const int64_t* dims, int dtype, int ncomp, int mem) {
@@ -218,7 +221,9 @@ struct DroptolJob {
   NormParams np;
   size_t nd = 0;
   double* d_stats = nullptr;  // stream-ordered pool allocation
-  std::vector<double> h;
+  double* h = nullptr;        // PINNED host mirror (cached): a pageable target would make the read-back a blocking staged copy
+  std::vector<double> h_fallback;
+  ~DroptolJob() { pin_release(h); }
 };
 
 int droptol_enqueue(DroptolJob& job, const DeviceInfo* di, int ndim, const int64_t* dims, int dtype, int cplx, int K,
@@ -234,12 +239,15 @@ int droptol_enqueue(DroptolJob& job, const DeviceInfo* di, int ndim, const int64
     hsum += (int)dims[d];
   }
   job.nd = 2 + (size_t)hsum;
-  job.h.resize(job.nd);
-  if (pool_alloc((void**)&job.d_stats, job.nd * sizeof(double), st) != cudaSuccess) {
+  if (!job.h && !(job.h = (double*)pin_acquire(job.nd * sizeof(double)))) {
+    job.h_fallback.resize(job.nd);
+  }
+  if (!job.d_stats && pool_alloc((void**)&job.d_stats, job.nd * sizeof(double), st) != cudaSuccess) {
     cudaGetLastError();
     job.d_stats = nullptr;
     return fail(FASTCHEB_ENOMEM, "droptol scratch");
   }
+  if (!d_coefs) return FASTCHEB_OK;  // layout + scratch only: the fit kernel itself produces the statistics
   norm_init_kernel<<<(int)std::min<size_t>((job.nd + 255) / 256, 64), 256, 0, st>>>(job.d_stats, (int)job.nd);
   const int grid = grid_for(elems, 256, di->sms);
   if (dtype == FASTCHEB_F64)
@@ -258,19 +266,20 @@ int droptol_enqueue(DroptolJob& job, const DeviceInfo* di, int ndim, const int64
 // blocks until the statistics are on the host (the one synchronisation of droptol), then decides the shape
 int droptol_finish(DroptolJob& job, int ndim, const int64_t* dims, double tol, int64_t* newdims, double* maxabs_out,
                    cudaStream_t st) {
-  cudaError_t e = cudaMemcpyAsync(job.h.data(), job.d_stats, job.nd * sizeof(double), cudaMemcpyDeviceToHost, st);
+  double* h = job.h ? job.h : job.h_fallback.data();
+  cudaError_t e = cudaMemcpyAsync(h, job.d_stats, job.nd * sizeof(double), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFreeAsync(job.d_stats, st);
   job.d_stats = nullptr;
   if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "droptol reduction failed: %s", cudaGetErrorString(e));
   for (int d = 0; d < ndim; ++d) newdims[d] = dims[d];
-  const double mx = job.h[0], mn = job.h[1];
+  const double mx = h[0], mn = h[1];
   if (maxabs_out) *maxabs_out = mx;
   const double abstol = mx * tol;        // interp.jl:78
   if (mn >= abstol) return FASTCHEB_OK;  // interp.jl:79: nothing to drop
   for (int d = 0; d < ndim; ++d) {       // interp.jl:83-91
     int64_t n = dims[d];
-    while (n > 1 && !(job.h[2 + job.np.hoff[d] + (n - 1)] >= abstol)) --n;
+    while (n > 1 && !(h[2 + job.np.hoff[d] + (n - 1)] >= abstol)) --n;
     newdims[d] = n;
   }
   return FASTCHEB_OK;
@@ -345,7 +354,7 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
     FlagSlot& f;
     ~Rel() { flag_release(f); }
   } rel{fs};
-  FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+  FC_CUDA(flag_prepare(fs, st));
 
   if (mem == FASTCHEB_MEM_DEVICE) {
     FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, howmany, vals, coefs, maxabs, fs.dev, st));
@@ -363,7 +372,7 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
     // two internal streams only for multi-chunk batches: the flag initialisation above is then ordered before them by a
     // synchronisation; a single chunk (single fits, small batches) runs on the caller's stream with ONE synchronisation
     // at the end of the call
-    if (nbuf > 1) FC_CUDA(cudaStreamSynchronize(st));
+    if (nbuf > 1 && fs.dirty) FC_CUDA(cudaStreamSynchronize(st));
     cudaStream_t ss[2] = {nullptr, nullptr};
     void* dbuf[2] = {nullptr, nullptr};
     const size_t cb = (size_t)chunk * fit_bytes, cb_al = (cb + 255) / 256 * 256;
@@ -421,6 +430,7 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
       FC_CUDA(cudaStreamSynchronize(st));
     }
   }
+  flag_observe(fs);
   if (*fs.host != kNoBad) {
     err_state().index = *fs.host;
     return fail(FASTCHEB_ENONFINITE, "non-finite interpolant value at flat index %lld (interp.jl:40)", *fs.host);
@@ -491,7 +501,7 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
     FlagSlot& f;
     ~Rel() { flag_release(f); }
   } rel{fs};
-  FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+  FC_CUDA(flag_prepare(fs, st));
   HostStage in(device, st), co(device, st), blk(device, st);
   const void* d_vals = vals;
   if (mem == FASTCHEB_MEM_HOST) {
@@ -502,11 +512,21 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
   }
   co.d = ws_acquire(device, bytes);
   if (!co.d) return fail(FASTCHEB_ENOMEM, "device scratch of %zu bytes", bytes);
-  FC_TRY(fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, 1, d_vals, co.d, nullptr, fs.dev, st));
-  // one host synchronisation for both the finite flag (interp.jl:40) and droptol's statistics (interp.jl:77-91)
+  // one host synchronisation for both the finite flag (interp.jl:40) and droptol's statistics (interp.jl:77-91); arrays
+  // that the resident fit kernel handles get the statistics from that kernel (no reduction launches)
   DroptolJob job;
   const bool trim = tol > 0;  // tol == 0: abstol = 0 and nothing is ever dropped (interp.jl:78-79)
-  if (trim) FC_TRY(droptol_enqueue(job, di, ndim, dims, dtype, is_complex, ncomp, co.d, st));
+  bool stats_done = false;
+  if (trim) FC_TRY(droptol_enqueue(job, di, ndim, dims, dtype, is_complex, ncomp, nullptr, st));  // scratch + layout
+  {
+    const int rc = fit_device(di, device, ndim, dims, dtype, is_complex, ncomp, 1, d_vals, co.d, nullptr, fs.dev, st, 0,
+                              trim ? job.d_stats : nullptr, trim ? job.np.hoff : nullptr, tol, &stats_done);
+    if (rc != FASTCHEB_OK) {
+      if (job.d_stats) cudaFreeAsync(job.d_stats, st);
+      return rc;
+    }
+  }
+  if (trim && !stats_done) FC_TRY(droptol_enqueue(job, di, ndim, dims, dtype, is_complex, ncomp, co.d, st));
   if (cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st) != cudaSuccess) {
     if (job.d_stats) cudaFreeAsync(job.d_stats, st);
     return fail(FASTCHEB_ECUDA, "status read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -518,6 +538,7 @@ int fastcheb_interp(fastcheb_poly** out, int ndim, const int64_t* dims, int dtyp
     FC_CUDA(cudaStreamSynchronize(st));
     for (int d = 0; d < ndim; ++d) newdims[d] = dims[d];
   }
+  flag_observe(fs);
   if (*fs.host != kNoBad) {
     err_state().index = *fs.host;
     return fail(FASTCHEB_ENONFINITE, "non-finite interpolant value at flat index %lld (interp.jl:40)", *fs.host);

@@ -22,5 +22,9 @@ void fit_afrag_host(int n, int map, bool split, std::vector<double>& h, int* ko,
 // caller then uses the generic per-dimension kernels.
 int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, int cplx, long long howmany, int dtype,
            const void* vals, void* coefs, long long* bad_dev, long long idx_base, double* maxabs_dev, cudaStream_t st,
-           bool* handled, bool* need_max = nullptr);  // *need_max: the caller still has to reduce max|c| per array
+           bool* handled, bool* need_max = nullptr,  // *need_max: the caller still has to reduce max|c| per array
+           double* stats_dev = nullptr, const int* stats_hoff = nullptr, double stats_tol = 0.0, bool* stats_done = nullptr);
+// stats_dev (howmany == 1 only): droptol's statistics computed by the same kernel, layout as coef_norm_kernel
+// (fit_direct.cuh): [0] max, [1] min, [2 + hoff[d] + k] >= stats_tol * max iff the hyperplane k_d = k keeps an element that
+// large (what droptol asks of the hyperplane maxima); *stats_done = true when they were produced.
 }  // namespace fastcheb

@@ -196,8 +196,9 @@ static int fit_nd_split(const DeviceInfo* di, int dev, int ndim, const int64_t* 
 
 int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, int cplx, long long howmany, int dtype,
            const void* vals, void* coefs, long long* bad_dev, long long idx_base, double* maxabs_dev, cudaStream_t st,
-           bool* handled, bool* need_max) {
+           bool* handled, bool* need_max, double* stats_dev, const int* stats_hoff, double stats_tol, bool* stats_done) {
   *handled = false;
+  if (stats_done) *stats_done = false;
   bool nm_local = false;
   if (!need_max) need_max = &nm_local;
   static const bool off = [] {  // experiments: FASTCHEB_FIT_ND=0 keeps the generic per-dimension kernels
@@ -287,6 +288,15 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     prm.reals = (int)arr_reals;
     prm.fits = (int)fits_per_arr;
     prm.fit_reals = (int)reals;
+    const bool want_stats = stats_dev && stats_hoff && howmany == 1 && narr == 1 && fits_per_arr == 1;
+    if (want_stats) {
+      prm.stats = stats_dev;
+      prm.stats_tol = stats_tol;
+      for (int d = 0; d < ndim; ++d) {
+        prm.hoff[d] = stats_hoff[d];
+        prm.hsum += (int)dims[d];
+      }
+    }
     int stride = E;
     for (int d = 0; d < ndim; ++d) {
       FitNdDim& fd = prm.dim[d];
@@ -403,6 +413,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     prm.nbuf = nbuf;
     prm.teams = teams;
     prm.team_warps = warps;
+    if (teams != 1 || warps > 16) prm.stats = nullptr;  // the statistics use the CTA's header scratch
     const int threads = warps * teams * 32;
     const size_t smem = fixed + (size_t)teams * nbuf * bufBytes;
     int bps = 0;
@@ -418,6 +429,7 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
     e = dtype == FASTCHEB_F64 ? dispatch<double>(sel, prm, grid, threads, smem, st, nullptr)
                               : dispatch<float>(sel, prm, grid, threads, smem, st, nullptr);
     if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "resident DCT-I kernel launch failed: %s", cudaGetErrorString(e));
+    if (prm.stats && stats_done) *stats_done = true;
     return FASTCHEB_OK;
   };
 

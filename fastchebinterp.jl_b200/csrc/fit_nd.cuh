@@ -52,6 +52,10 @@ struct FitNdParams {
   int fits, fit_reals;  // independent fits in one array (1-D line blocks: > 1) and reals per fit
   int nbuf;             // array buffers in shared memory (2: the next array loads while this one is transformed)
   int teams, team_warps;  // a CTA = teams x team_warps warps; a team owns one array at a time
+  double* stats;          // optional, ONE array only: droptol's statistics (interp.jl:77-91) — [0] max, [1] min of the
+  int hoff[kFitNdMaxDims];  // element norms, [2 + hoff[d] + k] != 0 iff the hyperplane k_d = k has an element >= tol * max
+  int hsum;               // sum of the dimensions
+  double stats_tol;
   FitNdDim dim[kFitNdMaxDims];
 };
 
@@ -376,6 +380,62 @@ __global__ void __launch_bounds__((MTB <= 4 && SPEC != 65) ? 512 : 256) fit_nd_k
           }
         if (first != 0x7fffffffffffffffLL) atomicMin(prm.bad, prm.idx_base + f * (long long)reals + first);
       }
+    }
+    if (prm.stats) {
+      // droptol's statistics of a single array, while it is still in shared memory (saves the two reduction launches of
+      // a chebinterp call, whose three global atomics per element cost ~30 us on a 65 x 65 array):
+      //   phase 1: max / min of the element norms (interp.jl:78-79);
+      //   phase 2, only when something can be dropped (min < tol * max): a hyperplane k_d = k survives iff one of its
+      //   elements is >= tol * max (interp.jl:83-91) — every such element marks its N hyperplanes with a plain store.
+      // stats[2 + hoff[d] + k] = max (marked) or 0 (not marked): the host compares them with tol * max as before.
+      const int E = prm.E, nel = reals / E;
+      double* s_w = reinterpret_cast<double*>(fastcheb_smem);  // header scratch (teams == 1): [0,16) maxima, [16,32) minima
+      auto infnorm = [&](const R* ce) {
+        double m = 0.0;
+        for (int k = 0; k < prm.K; ++k) {
+          const double a = prm.cplx ? hypot((double)ce[2 * k], (double)ce[2 * k + 1]) : fabs((double)ce[k]);
+          m = a > m ? a : m;
+        }
+        return m;
+      };
+      double tm = 0.0, tn = 1.79769313486231570815e308;
+      for (int el = tid; el < nel; el += team_thr) {
+        const double a = infnorm(x + (size_t)el * E);
+        tm = fmax(tm, a);
+        tn = fmin(tn, a);
+      }
+      for (int off = 16; off; off >>= 1) {
+        tm = fmax(tm, __shfl_xor_sync(0xffffffffu, tm, off));
+        tn = fmin(tn, __shfl_xor_sync(0xffffffffu, tn, off));
+      }
+      if (lane == 0) {
+        s_w[warp] = tm;
+        s_w[16 + warp] = tn;
+      }
+      for (int i = tid; i < prm.hsum; i += team_thr) prm.stats[2 + i] = 0.0;
+      team_sync();
+      double gm = 0.0, gn = 1.79769313486231570815e308;
+      for (int w = 0; w < nwarps; ++w) {
+        gm = fmax(gm, s_w[w]);
+        gn = fmin(gn, s_w[16 + w]);
+      }
+      if (tid == 0) {
+        prm.stats[0] = gm;
+        prm.stats[1] = gn;
+      }
+      const double abstol = gm * prm.stats_tol;  // interp.jl:78 (the host forms the same product)
+      if (!(gn >= abstol)) {                     // interp.jl:79
+        for (int el = tid; el < nel; el += team_thr) {
+          if (!(infnorm(x + (size_t)el * E) >= abstol)) continue;
+          int rem = el;
+          for (int dd = 0; dd < prm.ndim; ++dd) {
+            const int nd = prm.dim[dd].n, k = rem % nd;
+            rem /= nd;
+            prm.stats[2 + prm.hoff[dd] + k] = gm;
+          }
+        }
+      }
+      team_sync();  // the header scratch is free again (the max|c| reduction below uses it)
     }
     R* o = dst + f * (long long)reals;
     double mx = 0.0;

@@ -40,6 +40,7 @@ struct FlagPool {
   long long* dev = nullptr;
   long long* host = nullptr;
   uint64_t used = 0;
+  uint64_t dirty = ~uint64_t(0);  // slots whose device flag is not known to be kNoBad
 };
 std::map<int, FlagPool> g_flags;
 
@@ -250,7 +251,9 @@ void* pin_acquire(size_t bytes) {
     std::lock_guard<std::mutex> lk(g_mu);
     int best = -1;
     for (int i = 0; i < (int)g_pin.size(); ++i)
-      if (!g_pin[i].busy && g_pin[i].bytes >= bytes && (best < 0 || g_pin[i].bytes < g_pin[best].bytes)) best = i;
+      if (!g_pin[i].busy && g_pin[i].bytes >= bytes && g_pin[i].bytes <= std::max<size_t>(bytes * 64, size_t(1) << 16) &&
+          (best < 0 || g_pin[i].bytes < g_pin[best].bytes))
+        best = i;  // (a small request does not take a staging buffer thousands of times its size)
     if (best >= 0) {
       g_pin[best].busy = true;
       return g_pin[best].p;
@@ -347,6 +350,9 @@ int flag_acquire(int dev, FlagSlot* out) {
       out->host = fp.host + i;
       out->dev_id = dev;
       out->slot = i;
+      out->dirty = (fp.dirty >> i & 1) != 0;
+      out->clean = false;
+      fp.dirty |= uint64_t(1) << i;  // until released clean
       return FASTCHEB_OK;
     }
   return fail(FASTCHEB_ENOMEM, "more than %d concurrent calls on device %d", kFlagSlots, dev);
@@ -355,7 +361,14 @@ int flag_acquire(int dev, FlagSlot* out) {
 void flag_release(const FlagSlot& s) {
   if (s.slot < 0) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  g_flags[s.dev_id].used &= ~(uint64_t(1) << s.slot);
+  FlagPool& fp = g_flags[s.dev_id];
+  fp.used &= ~(uint64_t(1) << s.slot);
+  if (s.clean) fp.dirty &= ~(uint64_t(1) << s.slot);
+}
+
+cudaError_t flag_prepare(FlagSlot& s, cudaStream_t st) {
+  if (!s.dirty) return cudaSuccess;
+  return set_flag_async(s.dev, kNoBad, st);
 }
 
 

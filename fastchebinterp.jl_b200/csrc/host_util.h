@@ -91,9 +91,15 @@ struct FlagSlot {
   long long* host = nullptr;  // pinned
   int dev_id = -1;
   int slot = -1;
+  bool dirty = true;   // at acquire: the device flag may hold something other than kNoBad
+  bool clean = false;  // at release: the caller has seen kNoBad after its last kernel (flag_observe)
 };
 int flag_acquire(int dev, FlagSlot* out);
 void flag_release(const FlagSlot& s);
+// Slots go back to the pool CLEAN when the call that used them read kNoBad back after synchronising (the common case), so
+// the next call skips the reset kernel: one launch less on every small synchronous call.
+cudaError_t flag_prepare(FlagSlot& s, cudaStream_t st);  // reset the device flag to kNoBad unless the slot is clean
+inline void flag_observe(FlagSlot& s) { s.clean = s.host && *s.host == 0x7fffffffffffffffLL; }  // after the final sync
 
 constexpr long long kNoBad = 0x7fffffffffffffffLL;
 cudaError_t set_flag_async(long long* dev_flag, long long value, cudaStream_t st);

@@ -429,11 +429,11 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
   const size_t rs = real_size(p->dtype);
 
   if (mem == FASTCHEB_MEM_DEVICE) {
-    FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+    FC_CUDA(flag_prepare(fs, st));
     FC_TRY(eval_device(p, pts, npts, o.v, o.v_stride, o.J, o.J_stride, jac, fs.dev, 0, st));
     FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
     FC_CUDA(cudaStreamSynchronize(st));
-    return check_flag(*fs.host, p);
+    return (flag_observe(fs), check_flag(*fs.host, p));
   }
 
   // host buffers: chunked H2D -> kernel -> D2H pipeline on two cached internal streams
@@ -462,7 +462,7 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
     char* d_v = d_in + in_al;
     char* d_J = d_v + v_al;
     int rc = FASTCHEB_OK;
-    cudaError_t ce = set_flag_async(fs.dev, kNoBad, st);
+    cudaError_t ce = flag_prepare(fs, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_in, pts, (size_t)npts * in_pp, cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) {
       if (o.interleaved)
@@ -479,7 +479,7 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
     ws_release(p->device, dbuf);
     if (rc != FASTCHEB_OK) return rc;
     if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged evaluation failed: %s", cudaGetErrorString(ce));
-    return check_flag(*fs.host, p);
+    return (flag_observe(fs), check_flag(*fs.host, p));
   }
 
   // Large batches.  PAGEABLE caller memory (a Julia Vector, a numpy array) would make every cudaMemcpyAsync block the
@@ -512,8 +512,11 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
     }
   }
   int rc = FASTCHEB_OK;
-  cudaError_t ce = set_flag_async(fs.dev, kNoBad, sp.s[0]);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(sp.s[0]);  // ordered before the second stream's work
+  cudaError_t ce = cudaSuccess;
+  if (fs.dirty) {
+    ce = set_flag_async(fs.dev, kNoBad, sp.s[0]);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(sp.s[0]);  // ordered before the second stream's work
+  }
   struct Pending {
     int64_t first = 0, m = 0;
     bool live = false;
@@ -568,7 +571,7 @@ int eval_sync(const fastcheb_poly* p, const void* pts, int64_t npts, const OutSp
   cleanup();
   if (rc != FASTCHEB_OK) return rc;
   if (ce != cudaSuccess) return fail(FASTCHEB_ECUDA, "host-staged evaluation failed: %s", cudaGetErrorString(ce));
-  return check_flag(*fs.host, p);
+  return (flag_observe(fs), check_flag(*fs.host, p));
 }
 
 }  // namespace
@@ -651,7 +654,7 @@ int eval_tangent(const fastcheb_poly* p, const void* pts, int64_t npts, const vo
     FlagSlot& f;
     ~Rel() { flag_release(f); }
   } rel{fs};
-  FC_CUDA(set_flag_async(fs.dev, kNoBad, st));
+  FC_CUDA(flag_prepare(fs, st));
   if (mem == FASTCHEB_MEM_DEVICE) {
     FC_TRY(eval_device(p, pts, npts, out_v, E, out_t, 0, true, fs.dev, 0, st, mode, tan));
   } else {
@@ -683,7 +686,7 @@ int eval_tangent(const fastcheb_poly* p, const void* pts, int64_t npts, const vo
   }
   FC_CUDA(cudaMemcpyAsync(fs.host, fs.dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
   FC_CUDA(cudaStreamSynchronize(st));
-  return check_flag(*fs.host, p);
+  return (flag_observe(fs), check_flag(*fs.host, p));
 }
 }  // namespace
 
