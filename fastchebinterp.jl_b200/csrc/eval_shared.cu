@@ -28,6 +28,7 @@ namespace {
 
 constexpr int kSharedKS = 16;   // k-steps: n - 1 <= 64
 constexpr int kSharedPT = 64;   // points per tile
+constexpr int kSharedHeader = 256;  // mbarriers + release counters
 
 struct TableParams {
   const void* pts;
@@ -35,12 +36,13 @@ struct TableParams {
   long long* bad;
   long long M;
   int n, RS, der;
-  double lb, ub;
+  double lb, ub;              // the bounds by value (host mode) ...
+  const double *lbp, *ubp;    // ... or in device memory (device mode: no read-back, the call stays asynchronous)
 };
 
 template <typename R>
 __global__ void __launch_bounds__(256) cheb_table_kernel(const __grid_constant__ TableParams prm) {
-  const R lb = (R)prm.lb, ub = (R)prm.ub;
+  const R lb = (R)(prm.lbp ? *prm.lbp : prm.lb), ub = (R)(prm.ubp ? *prm.ubp : prm.ub);
   SpanDiv<R> sdiv;
   sdiv.init(lb, ub);
   const R* pts = reinterpret_cast<const R*>(prm.pts);
@@ -71,58 +73,76 @@ struct SharedParams {
   void* out;            // [howmany][M][E]
   long long rows;       // howmany * E
   long long M;
-  int n, E, RS, der;
+  int n, E, RS, der, nstage;
   double lb, ub;
+  const double *lbp, *ubp;  // as in TableParams
 };
 
-// RT: row tiles (of 8 rows) per warp.  RT = 2 halves the B-fragment loads per DMMA but needs ~250 registers (one CTA per
-// SM, whose 8 warps move in lock-step through the tile barriers); RT = 1 fits two CTAs per SM, which overlap each
-// other's epilogues and barriers.
-template <typename R, int RT>
+// RT: row tiles (of 8 rows) per warp.  With RT = 2 every B fragment feeds two DMMAs (two accumulator chains interleave by
+// construction); the column tiles are then taken two at a time with k innermost so that only four accumulators are live
+// next to the 2 x 16 A fragments (128 registers, two CTAs per SM — all eight column tiles at once would need ~250).
+// KSU: k-steps executed, a compile-time constant (4, 8, 12 or 16 >= ceil((n - 1) / 4); coefficients and table rows are
+// zero-padded): the tile loop is then one straight-line block whose B-fragment loads ptxas schedules across k-steps.
+// (With a run-time count and a uniform exit per k-step every k-step was a basic block of its own: the loads' latency was
+// exposed 16 times per tile, and branch / NOP slots were a quarter of the stall samples.)
+template <typename R, int RT, int KSU>
 __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_constant__ SharedParams prm) {
   constexpr int kSharedRows = 8 * 8 * RT;  // rows per CTA
-  extern __shared__ __align__(16) unsigned char fastcheb_smem[];
-  double* tile[2] = {reinterpret_cast<double*>(fastcheb_smem),
-                     reinterpret_cast<double*>(fastcheb_smem) + (size_t)kSharedPT * prm.RS};
+  extern __shared__ __align__(128) unsigned char fastcheb_smem[];
+  // [256 B header: full[NST] mbarriers | released[NST] counters] [NST tile buffers]
+  uint64_t* full = reinterpret_cast<uint64_t*>(fastcheb_smem);
+  unsigned int* released = reinterpret_cast<unsigned int*>(fastcheb_smem + 64);
+  double* tiles = reinterpret_cast<double*>(fastcheb_smem + kSharedHeader);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = lane & 3, q = lane >> 2;
-  const int n = prm.n, E = prm.E, RS = prm.RS;
+  const int n = prm.n, E = prm.E, RS = prm.RS, NST = prm.nstage;
   const R* coefs = reinterpret_cast<const R*>(prm.coefs);
   R* out = reinterpret_cast<R*>(prm.out);
   const long long ntiles = (prm.M + kSharedPT - 1) / kSharedPT;
   const long long nblocks = (prm.rows + kSharedRows - 1) / kSharedRows;
   const int tileDoubles = kSharedPT * RS;
 
-  auto load_tile = [&](int b, long long pt) {
-    // the table has ntiles * PT rows allocated (the last tile is zero-padded by the host), RS is a multiple of 2
-    const double* src = prm.table + pt * (long long)tileDoubles;
-    for (int i = tid; i < tileDoubles / 2; i += blockDim.x)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile[b] + 2 * i)), "l"(src + 2 * i) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
   // Work = the (row block, point tile) pairs in row-block-major order; a CTA owns one CONTIGUOUS range of them (balanced
-  // to within one tile), so the table tiles stream through the two buffers without a restart at a row-block boundary and
-  // the A fragments are reloaded only when the row block changes.
+  // to within one tile), so the table tiles stream through the ring without a restart at a row-block boundary and the A
+  // fragments are reloaded only when the row block changes.
   const long long total = nblocks * ntiles;
   const long long g0 = total * blockIdx.x / gridDim.x, g1 = total * (blockIdx.x + 1) / gridDim.x;
   if (g0 >= g1) return;
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      released[s] = 0;
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier
+  // A tile is one contiguous, 16-byte aligned piece of the table (the last tile is zero-padded by the host): ONE bulk
+  // copy (TMA engine) signalled on the stage's mbarrier.  No producer warp and no barrier in the loop: the LAST warp to
+  // release a stage (shared-memory counter) refills it with the tile NST visits ahead, so the warps of a CTA drift up to
+  // NST - 1 tiles apart instead of meeting twice per tile.
+  auto issue = [&](long long g) {  // one thread
+    const int s = (int)((g - g0) % NST);
+    const uint32_t bytes = (uint32_t)tileDoubles * 8u;
+    const char* src = reinterpret_cast<const char*>(prm.table + (g % ntiles) * (long long)tileDoubles);
+    char* dst = reinterpret_cast<char*>(tiles + (size_t)s * tileDoubles);
+    mbar_arrive_expect_tx(&full[s], bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768u) {
+      const uint32_t len = bytes - o < 32768u ? bytes - o : 32768u;
+      bulk_g2s(dst + o, src + o, len, &full[s]);
+    }
+  };
+  if (tid == 0)
+    for (long long g = g0; g < g0 + NST && g < g1; ++g) issue(g);
   // A fragments of this warp's RT x 8 rows: lane (c, q) holds C[row q][k = 1 + 4 ks + c]; the k = 0 column separately
-  double A[RT][kSharedKS], c0[RT][2];
+  double A[RT][KSU], c0[RT][2];
   long long rowq[RT];
   bool lived[RT][2];
   long long cur = -1;
-  load_tile(0, g0 % ntiles);
   {
     for (long long g = g0; g < g1; ++g) {
-      const int b = (int)((g - g0) & 1);
+      const int b = (int)((g - g0) % NST);
+      const uint32_t parity = (uint32_t)(((g - g0) / NST) & 1);
       const long long blk = g / ntiles, pt = g - blk * ntiles;
-      if (g + 1 < g1) {
-        load_tile(b ^ 1, (g + 1) % ntiles);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
       if (blk != cur) {
         cur = blk;
 #pragma unroll
@@ -134,7 +154,7 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
           const int e = liveq ? (int)(rowq[t] - f * E) : 0;
           const R* cr = coefs + (f * n) * E + e;  // element k at cr[k * E]
 #pragma unroll
-          for (int ks = 0; ks < kSharedKS; ++ks) {
+          for (int ks = 0; ks < KSU; ++ks) {
             const int k = 1 + 4 * ks + c;
             A[t][ks] = (liveq && k < n) ? (double)cr[(long long)k * E] : 0.0;
           }
@@ -146,10 +166,10 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
           }
         }
       }
-      __syncthreads();
-      const double* T = tile[b];
+      mbar_wait(&full[b], parity);
+      const double* T = tiles + (size_t)b * tileDoubles;
       const long long m0 = pt * kSharedPT;
-      const double span = (double)rsub((R)prm.ub, (R)prm.lb);
+      const double span = (double)rsub((R)(prm.ubp ? *prm.ubp : prm.ub), (R)(prm.lbp ? *prm.lbp : prm.lb));
       // epilogue of one column tile: lane (c, q) holds points 8 j + 2c, 8 j + 2c + 1 of row q
       auto store = [&](int t, int j, double v0, double v1) {
         if (!lived[t][0]) return;
@@ -180,8 +200,7 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
           acc[j][1] = c0[0][1];
         }
 #pragma unroll
-        for (int ks = 0; ks < kSharedKS; ++ks) {
-          if (4 * ks + 1 >= n) break;  // uniform: shorter polynomials stop early
+        for (int ks = 0; ks < KSU; ++ks) {
 #pragma unroll
           for (int j = 0; j < kSharedPT / 8; ++j) {
             // B fragment: lane (c, q) holds T[point 8 j + q][k = 1 + 4 ks + c]
@@ -195,6 +214,8 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
         // RT row tiles per warp, column tiles two at a time (k innermost): every B fragment feeds RT DMMAs, 2 RT
         // independent accumulator chains per warp, and only those 2 RT accumulators are live next to the A fragments —
         // 128 registers, two CTAs per SM (all 8 column tiles at once need ~250)
+        // (unrolled although `no_instruction` is 15 % of the stall samples: as a run-time loop of four iterations the kernel
+        // drops from 68 % to 62 %)
 #pragma unroll
         for (int j = 0; j < kSharedPT / 8; j += 2) {
           double acc[RT][2][2];
@@ -208,8 +229,7 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
           const double* T0 = T + (8 * j + q) * RS + c;
           const double* T1 = T0 + 8 * RS;
 #pragma unroll
-          for (int ks = 0; ks < kSharedKS; ++ks) {
-            if (4 * ks + 1 >= n) break;  // uniform
+          for (int ks = 0; ks < KSU; ++ks) {
             const double b0 = T0[4 * ks], b1 = T1[4 * ks];
 #pragma unroll
             for (int t = 0; t < RT; ++t) {
@@ -223,7 +243,18 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
             for (int jj = 0; jj < 2; ++jj) store(t, j + jj, acc[t][jj][0], acc[t][jj][1]);
         }
       }
-      __syncthreads();  // tile b may be refilled
+      // release the stage; the last warp out refills it
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&released[b], 1u) == (unsigned)(blockDim.x >> 5) - 1u) {
+          released[b] = 0;
+          if (g + NST < g1) {
+            fence_proxy_async();
+            issue(g + NST);
+          }
+        }
+      }
     }
   }
 }
@@ -250,13 +281,13 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
   DeviceGuard dg(device);
   if (!dg.ok()) return fail(FASTCHEB_ECUDA, "cudaSetDevice(%d) failed", device);
   cudaStream_t st = (cudaStream_t)stream;
-  // lb / ub: host doubles in host mode, device doubles in device mode (as in fastcheb_eval_many); the kernels take them
-  // by value, so device-mode bounds are read back once (16 bytes)
-  double hlb, hub;
+  // lb / ub: host doubles in host mode (passed to the kernels by value), device doubles in device mode (as in
+  // fastcheb_eval_many; the kernels read them through the pointers: no read-back, the device-mode call never synchronises)
+  double hlb = 0.0, hub = 0.0;
+  const double *lbp = nullptr, *ubp = nullptr;
   if (mem == FASTCHEB_MEM_DEVICE) {
-    FC_CUDA(cudaMemcpyAsync(&hlb, lb, sizeof(double), cudaMemcpyDeviceToHost, st));
-    FC_CUDA(cudaMemcpyAsync(&hub, ub, sizeof(double), cudaMemcpyDeviceToHost, st));
-    FC_CUDA(cudaStreamSynchronize(st));
+    lbp = lb;
+    ubp = ub;
   } else {
     hlb = lb[0];
     hub = ub[0];
@@ -303,15 +334,23 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
   }
   if (flag) FC_CUDA(set_flag_async(flag, kNoBad, st));
   FC_CUDA(cudaMemsetAsync(d_table + (size_t)M * RS, 0, tableBytes - (size_t)M * RS * sizeof(double), st));  // padding rows of the last tile
-  const size_t smem = (size_t)2 * kSharedPT * RS * sizeof(double);
   const long long rows = (long long)howmany * E;
-  // RT = 1 (64 rows per CTA, two CTAs per SM) measured faster than RT = 2 (profiles/r02_eval_shared.txt);
-  // FASTCHEB_SHARED_RT=2 selects the other (experiments)
-  static const int rt = [] {
+  // row tiles per warp: 2 for Float64 order > 48 (every B fragment feeds two DMMAs: 67.8 % vs 66.2 % of peak at 10^3
+  // points, 71 % vs 69 % at 4096), 1 otherwise (Float32 data: 66 % vs 62 %); FASTCHEB_SHARED_RT=1|2 forces one (experiments)
+  static const int rt_env = [] {
     const char* e = getenv("FASTCHEB_SHARED_RT");
-    return e && atoi(e) == 2 ? 2 : 1;
+    return e ? atoi(e) : 0;
   }();
-  const long long nblocks = (rows + 64 * rt - 1) / (64 * rt);
+  const int rt = rt_env == 1 || rt_env == 2 ? rt_env : (dtype == FASTCHEB_F64 ? 2 : 1);
+  const int ksu = KS <= 4 ? 4 : (KS <= 8 ? 8 : (KS <= 12 ? 12 : 16));  // k-steps the instantiation executes
+  const int rte = (rt == 2 && ksu == 16) ? 2 : 1;
+  const long long nblocks = (rows + 64 * rte - 1) / (64 * rte);
+  // as many tile stages as two resident CTAs per SM leave room for (3 at n = 65), at least 2
+  const size_t tileBytes = (size_t)kSharedPT * RS * sizeof(double);
+  int nstage = 4;
+  const size_t ctas = 2;  // resident CTAs per SM the kernel is built for (128 registers; three CTAs of 80 registers: 62 % vs 65 %)
+  while (nstage > 2 && ctas * (kSharedHeader + nstage * tileBytes + 1024) > di->smem_optin) --nstage;
+  const size_t smem = kSharedHeader + (size_t)nstage * tileBytes;
   for (int der = 0; der < (out_d ? 2 : 1); ++der) {
     TableParams tp;
     memset(&tp, 0, sizeof tp);
@@ -324,11 +363,16 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
     tp.der = der;
     tp.lb = hlb;
     tp.ub = hub;
-    const int tgrid = (int)std::max<long long>(1, std::min<long long>((M + 255) / 256, (long long)di->sms * 4));
+    tp.lbp = lbp;
+    tp.ubp = ubp;
+    // one warp per CTA: every lane writes its own table row (32 sectors per store instruction), so the kernel is bound by
+    // the store path of the SMs it runs on — 1000 points on 4 SMs took 13.8 us, a warp per SM takes ~2
+    const int tthreads = 32;
+    const int tgrid = (int)std::max<long long>(1, std::min<long long>((M + tthreads - 1) / tthreads, (long long)di->sms * 32));
     if (dtype == FASTCHEB_F64)
-      cheb_table_kernel<double><<<tgrid, 256, 0, st>>>(tp);
+      cheb_table_kernel<double><<<tgrid, tthreads, 0, st>>>(tp);
     else
-      cheb_table_kernel<float><<<tgrid, 256, 0, st>>>(tp);
+      cheb_table_kernel<float><<<tgrid, tthreads, 0, st>>>(tp);
     FC_CUDA(cudaGetLastError());
     SharedParams sp;
     memset(&sp, 0, sizeof sp);
@@ -341,10 +385,23 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
     sp.E = E;
     sp.RS = RS;
     sp.der = der;
+    sp.nstage = nstage;
     sp.lb = hlb;
     sp.ub = hub;
-    const void* kern = dtype == FASTCHEB_F64 ? (rt == 2 ? (const void*)eval_shared_kernel<double, 2> : (const void*)eval_shared_kernel<double, 1>)
-                                             : (rt == 2 ? (const void*)eval_shared_kernel<float, 2> : (const void*)eval_shared_kernel<float, 1>);
+    sp.lbp = lbp;
+    sp.ubp = ubp;
+    const void* kern;
+#define FC_SH(RR)                                                                                                      \
+  (rte == 2 ? (const void*)eval_shared_kernel<RR, 2, 16>                                                           \
+   : ksu == 4           ? (const void*)eval_shared_kernel<RR, 1, 4>                                                    \
+   : ksu == 8           ? (const void*)eval_shared_kernel<RR, 1, 8>                                                    \
+   : ksu == 12          ? (const void*)eval_shared_kernel<RR, 1, 12>                                                   \
+                        : (const void*)eval_shared_kernel<RR, 1, 16>)
+    if (dtype == FASTCHEB_F64)
+      kern = FC_SH(double);
+    else
+      kern = FC_SH(float);
+#undef FC_SH
     FC_CUDA(ensure_max_smem(kern));
     int bps = 1;
     FC_CUDA(cached_occupancy(&bps, kern, 256, smem));
