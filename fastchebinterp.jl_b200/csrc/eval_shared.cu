@@ -78,6 +78,13 @@ struct SharedParams {
   const double *lbp, *ubp;  // as in TableParams
 };
 
+// the general (ragged / vector-element / unaligned) form of the epilogue store, kept out of line
+template <typename R>
+__device__ __noinline__ void store_slow(R* orow, long long m, long long M, int E, double v0, double v1) {
+  if (m < M) orow[m * E] = (R)v0;
+  if (m + 1 < M) orow[(m + 1) * E] = (R)v1;
+}
+
 // RT: row tiles (of 8 rows) per warp.  With RT = 2 every B fragment feeds two DMMAs (two accumulator chains interleave by
 // construction); the column tiles are then taken two at a time with k innermost so that only four accumulators are live
 // next to the 2 x 16 A fragments (128 registers, two CTAs per SM — all eight column tiles at once would need ~250).
@@ -85,7 +92,7 @@ struct SharedParams {
 // zero-padded): the tile loop is then one straight-line block whose B-fragment loads ptxas schedules across k-steps.
 // (With a run-time count and a uniform exit per k-step every k-step was a basic block of its own: the loads' latency was
 // exposed 16 times per tile, and branch / NOP slots were a quarter of the stall samples.)
-template <typename R, int RT, int KSU>
+template <typename R, int RT, int KSU, bool DER>
 __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_constant__ SharedParams prm) {
   constexpr int kSharedRows = 8 * 8 * RT;  // rows per CTA
   extern __shared__ __align__(128) unsigned char fastcheb_smem[];
@@ -137,7 +144,11 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
   double A[RT][KSU], c0[RT][2];
   long long rowq[RT];
   bool lived[RT][2];
+  R* orow[RT];  // this lane's output row of each row tile: point m at orow[m * E]
   long long cur = -1;
+  // derivative pass: eval.jl:151's factor 2 / (ub - lb) is folded into the coefficients as they are loaded (one rounding
+  // more than the reference's (d * 2) / span — this path is held to the tolerance, not to bit-identity)
+  const double dscale = DER ? 2.0 / (double)rsub((R)(prm.ubp ? *prm.ubp : prm.ub), (R)(prm.lbp ? *prm.lbp : prm.lb)) : 1.0;
   {
     for (long long g = g0; g < g1; ++g) {
       const int b = (int)((g - g0) % NST);
@@ -153,42 +164,41 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
           const long long f = liveq ? rowq[t] / E : 0;
           const int e = liveq ? (int)(rowq[t] - f * E) : 0;
           const R* cr = coefs + (f * n) * E + e;  // element k at cr[k * E]
+          orow[t] = out + (f * prm.M) * E + e;
 #pragma unroll
           for (int ks = 0; ks < KSU; ++ks) {
             const int k = 1 + 4 * ks + c;
-            A[t][ks] = (liveq && k < n) ? (double)cr[(long long)k * E] : 0.0;
+            A[t][ks] = (liveq && k < n) ? (double)cr[(long long)k * E] * dscale : 0.0;
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             // D fragment: lane (c, q) holds out[row q][point 2c + h]: the k = 0 coefficient of row q initialises it
             lived[t][h] = liveq;
-            c0[t][h] = (liveq && !prm.der) ? (double)cr[0] : 0.0;
+            c0[t][h] = (liveq && !DER) ? (double)cr[0] : 0.0;
           }
         }
       }
       mbar_wait(&full[b], parity);
       const double* T = tiles + (size_t)b * tileDoubles;
       const long long m0 = pt * kSharedPT;
-      const double span = (double)rsub((R)(prm.ubp ? *prm.ubp : prm.ub), (R)(prm.lbp ? *prm.lbp : prm.lb));
       // epilogue of one column tile: lane (c, q) holds points 8 j + 2c, 8 j + 2c + 1 of row q
+      // Fast path, decided once per tile and row: scalar elements, the whole tile inside M and the lane's pairs of points
+      // 2-element aligned — one vector store and nothing else in the unrolled body (the body's size matters: the
+      // instruction cache, not the tensor pipe, limited the first versions).  Everything else goes through store_slow.
+      bool fastst[RT];
+#pragma unroll
+      for (int t = 0; t < RT; ++t)
+        fastst[t] = lived[t][0] && E == 1 && m0 + kSharedPT <= prm.M &&
+                    ((reinterpret_cast<uintptr_t>(orow[t] + m0 + 2 * c) & (2 * sizeof(R) - 1)) == 0);
       auto store = [&](int t, int j, double v0, double v1) {
-        if (!lived[t][0]) return;
-        const long long f = rowq[t] / E;
-        const int e = (int)(rowq[t] - f * E);
-        R* orow = out + (f * prm.M) * E + e;  // point m at orow[m * E]
-        const long long m = m0 + 8 * j + 2 * c;
-        if (prm.der) {  // eval.jl:151: d/dx = (d/dz * 2) / (ub - lb)
-          v0 = __ddiv_rn(__dmul_rn(v0, 2.0), span);
-          v1 = __ddiv_rn(__dmul_rn(v1, 2.0), span);
-        }
-        if (E == 1 && m + 1 < prm.M && ((reinterpret_cast<uintptr_t>(orow + m) & (2 * sizeof(R) - 1)) == 0)) {
+        if (fastst[t]) {
+          R* o = orow[t] + m0 + 8 * j + 2 * c;
           if constexpr (sizeof(R) == 8)
-            *reinterpret_cast<double2*>(orow + m) = make_double2(v0, v1);
+            *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
           else
-            *reinterpret_cast<float2*>(orow + m) = make_float2((float)v0, (float)v1);
-        } else {
-          if (m < prm.M) orow[m * E] = (R)v0;
-          if (m + 1 < prm.M) orow[(m + 1) * E] = (R)v1;
+            *reinterpret_cast<float2*>(o) = make_float2((float)v0, (float)v1);
+        } else if (lived[t][0]) {
+          store_slow<R>(orow[t], m0 + 8 * j + 2 * c, prm.M, E, v0, v1);
         }
       };
       if constexpr (RT == 1) {
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) eval_shared_kernel(const __grid_consta
         // 128 registers, two CTAs per SM (all 8 column tiles at once need ~250)
         // (unrolled although `no_instruction` is 15 % of the stall samples: as a run-time loop of four iterations the kernel
         // drops from 68 % to 62 %)
-#pragma unroll
+#pragma unroll 2
         for (int j = 0; j < kSharedPT / 8; j += 2) {
           double acc[RT][2][2];
 #pragma unroll
@@ -335,13 +345,13 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
   if (flag) FC_CUDA(set_flag_async(flag, kNoBad, st));
   FC_CUDA(cudaMemsetAsync(d_table + (size_t)M * RS, 0, tableBytes - (size_t)M * RS * sizeof(double), st));  // padding rows of the last tile
   const long long rows = (long long)howmany * E;
-  // row tiles per warp: 2 for Float64 order > 48 (every B fragment feeds two DMMAs: 67.8 % vs 66.2 % of peak at 10^3
-  // points, 71 % vs 69 % at 4096), 1 otherwise (Float32 data: 66 % vs 62 %); FASTCHEB_SHARED_RT=1|2 forces one (experiments)
+  // row tiles per warp: 2 (every B fragment feeds two DMMAs: Float64 73 % vs 66 % of peak at 10^3 points, Float32 data
+  // 70 % vs 66 %); FASTCHEB_SHARED_RT=1 keeps one (experiments).  Orders below 49 use the one-tile instantiations.
   static const int rt_env = [] {
     const char* e = getenv("FASTCHEB_SHARED_RT");
     return e ? atoi(e) : 0;
   }();
-  const int rt = rt_env == 1 || rt_env == 2 ? rt_env : (dtype == FASTCHEB_F64 ? 2 : 1);
+  const int rt = rt_env == 1 ? 1 : 2;
   const int ksu = KS <= 4 ? 4 : (KS <= 8 ? 8 : (KS <= 12 ? 12 : 16));  // k-steps the instantiation executes
   const int rte = (rt == 2 && ksu == 16) ? 2 : 1;
   const long long nblocks = (rows + 64 * rte - 1) / (64 * rte);
@@ -391,16 +401,18 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
     sp.lbp = lbp;
     sp.ubp = ubp;
     const void* kern;
-#define FC_SH(RR)                                                                                                      \
-  (rte == 2 ? (const void*)eval_shared_kernel<RR, 2, 16>                                                           \
-   : ksu == 4           ? (const void*)eval_shared_kernel<RR, 1, 4>                                                    \
-   : ksu == 8           ? (const void*)eval_shared_kernel<RR, 1, 8>                                                    \
-   : ksu == 12          ? (const void*)eval_shared_kernel<RR, 1, 12>                                                   \
-                        : (const void*)eval_shared_kernel<RR, 1, 16>)
+#define FC_SH2(RR, DD)                                                                                                 \
+  (rte == 2    ? (const void*)eval_shared_kernel<RR, 2, 16, DD>                                                        \
+   : ksu == 4  ? (const void*)eval_shared_kernel<RR, 1, 4, DD>                                                         \
+   : ksu == 8  ? (const void*)eval_shared_kernel<RR, 1, 8, DD>                                                         \
+   : ksu == 12 ? (const void*)eval_shared_kernel<RR, 1, 12, DD>                                                        \
+               : (const void*)eval_shared_kernel<RR, 1, 16, DD>)
+#define FC_SH(RR) (der ? FC_SH2(RR, true) : FC_SH2(RR, false))
     if (dtype == FASTCHEB_F64)
       kern = FC_SH(double);
     else
       kern = FC_SH(float);
+#undef FC_SH2
 #undef FC_SH
     FC_CUDA(ensure_max_smem(kern));
     int bps = 1;
