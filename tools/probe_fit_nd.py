@@ -46,6 +46,8 @@ def main():
         tag = "x".join(map(str, dims)) + "-" + np.dtype(dt).name
         if only and only not in tag:
             continue
+        if os.environ.get("FIT_HOWMANY"):
+            howmany = int(os.environ["FIT_HOWMANY"])
         tdt = torch.float64 if dt == np.float64 else torch.float32
         per = int(np.prod(dims))
         nbuf = max(2, int(np.ceil(300e6 / (howmany * per * 2 * np.dtype(dt).itemsize))) + 1)
