@@ -220,7 +220,11 @@ __device__ __forceinline__ void fit_nd_pass(R* x, const FitNdDim& d, const doubl
   const int s = d.stride;
   const int nlines = nlines_live >= 0 ? nlines_live : reals / d.n;
   constexpr int GB = sizeof(R) == 8 ? 2 : 4;  // groups per block of 8 GB lines
-  const int ngroups = (nlines + 8 * GB - 1) / (8 * GB) * GB;
+  // groups of the last, partial block that contain no line at all are skipped (the groups of a block start at lines
+  // blk + 2 t (Float64) / blk + t (Float32), so the live ones are its first): 65 lines are 9 groups, not 10 (Float64) or 12
+  // (Float32) — the pass phase is bound by shared-memory wavefronts, and a dead group costs as many as a live one
+  const int rem = nlines % (8 * GB);
+  const int ngroups = nlines / (8 * GB) * GB + (GB == 2 ? min(GB, (rem + 1) / 2) : min(GB, rem));
   for (int gi = warp; gi < ngroups; gi += nwarps) {
     // line L -> (outer o, inner i): base = o * n * s + i
     auto base_of = [&](int L) {
