@@ -347,6 +347,55 @@ def test_eval_many_large_batches_bit_identical(fc, orc, dt):
     assert ei.value.index == 417 * 100 + 63
 
 
+def test_eval_many_device_mode_matches_host_mode(fc):
+    """fastcheb_eval_many / fastcheb_eval_many_shared with mem = DEVICE (every pointer, the bounds included, in device
+    memory; the call only enqueues; status_dev carries the first out-of-domain index): the same bits as the synchronous
+    host-mode call, for per-polynomial and for shared points, values and derivatives."""
+    import ctypes
+    import torch
+    from fastcheb import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(81)
+    dev = torch.device("cuda", 0)
+    for dt, tdt, code in ((np.float64, torch.float64, _capi.F64), (np.float32, torch.float32, _capi.F32)):
+        for n, howmany, M in ((65, 300, 1000), (33, 130, 77), (8, 64, 200)):
+            c = (rng.uniform(-1, 1, (howmany, n)) * 0.9 ** np.arange(n)).astype(dt)
+            lb, ub = -1.5, 0.75
+            x_sh = np.clip((lb + (ub - lb) * rng.random(M)).astype(dt), dt(lb), dt(ub))
+            x_pp = np.clip((lb + (ub - lb) * rng.random((howmany, M))).astype(dt), dt(lb), dt(ub))
+            d_c = torch.from_numpy(c).to(dev)
+            d_lb = torch.tensor([lb], dtype=torch.float64, device=dev)
+            d_ub = torch.tensor([ub], dtype=torch.float64, device=dev)
+            sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for shared, x in ((True, x_sh), (False, x_pp)):
+                hv, hd = fc.eval_many(c, dt(lb), dt(ub), x, deriv=True)
+                d_x = torch.from_numpy(x).to(dev)
+                ov = torch.empty((howmany, M), dtype=tdt, device=dev)
+                od = torch.empty((howmany, M), dtype=tdt, device=dev)
+                st = torch.zeros(1, dtype=torch.int64, device=dev)
+                if shared:
+                    rc = L.fastcheb_eval_many_shared(howmany, n, code, 0, 1, d_c.data_ptr(), d_lb.data_ptr(), d_ub.data_ptr(),
+                                                     d_x.data_ptr(), M, ov.data_ptr(), od.data_ptr(), st.data_ptr(), _capi.MEM_DEVICE, 0, sp)
+                else:
+                    rc = L.fastcheb_eval_many(howmany, n, code, 0, 1, d_c.data_ptr(), d_lb.data_ptr(), d_ub.data_ptr(), 0,
+                                              d_x.data_ptr(), M, ov.data_ptr(), od.data_ptr(), st.data_ptr(), _capi.MEM_DEVICE, 0, sp)
+                assert rc == 0, _capi.last_error()
+                torch.cuda.synchronize()
+                assert int(st.item()) == 0x7fffffffffffffff
+                assert np.array_equal(ov.cpu().numpy(), hv), (dt, n, shared)
+                assert np.array_equal(od.cpu().numpy(), hd), (dt, n, shared)
+            # an out-of-domain shared point is reported through status_dev
+            bad = x_sh.copy()
+            bad[M // 2] = dt(2.0)
+            d_x = torch.from_numpy(bad).to(dev)
+            st = torch.zeros(1, dtype=torch.int64, device=dev)
+            rc = L.fastcheb_eval_many_shared(howmany, n, code, 0, 1, d_c.data_ptr(), d_lb.data_ptr(), d_ub.data_ptr(), d_x.data_ptr(), M,
+                                             ov.data_ptr(), None, st.data_ptr(), _capi.MEM_DEVICE, 0, sp)
+            assert rc == 0
+            torch.cuda.synchronize()
+            assert int(st.item()) == M // 2
+
+
 def test_cfg5_fit_then_eval_many(fc):
     """configs[4] end to end at full size: 10^5 order-64 fits (tensor-core DCT-I), then every polynomial evaluated at
     10^3 of its own points (10^8 evaluations) against the analytic functions f_i(x) = sin(a_i x + b_i)."""
