@@ -221,6 +221,8 @@ def run_all(device: int = 0, quick: bool = False):
         guard(f"cfg4_fit1d_order64_{nm}_2^20", lambda: fit_leg(torch, _capi, device, (65,), 1 << 20, dt, freps // 2))
     guard("fit2d_65x65_f64_x4096", lambda: fit_leg(torch, _capi, device, (65, 65), 4096, f64, reps))
     guard("fit2d_65x65_f32_x4096", lambda: fit_leg(torch, _capi, device, (65, 65), 4096, f32, reps))
+    guard("fit2d_33x33_f64_x65536", lambda: fit_leg(torch, _capi, device, (33, 33), 65536, f64, reps))
+    guard("fit2d_33x33_f32_x65536", lambda: fit_leg(torch, _capi, device, (33, 33), 65536, f32, reps))
     guard("fit3d_33x33x33_f64_x512", lambda: fit_leg(torch, _capi, device, (33, 33, 33), 512, f64, reps))
     guard("fit3d_33x33x33_f32_x512", lambda: fit_leg(torch, _capi, device, (33, 33, 33), 512, f32, reps))
     guard("fit1d_n129_f64_x2^18", lambda: fit_leg(torch, _capi, device, (129,), 1 << 18, f64, reps))

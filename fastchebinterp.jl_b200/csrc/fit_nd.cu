@@ -434,6 +434,38 @@ int fit_nd(const DeviceInfo* di, int dev, int ndim, const int64_t* dims, int K, 
   };
 
   if (!lines) {
+    // Batches of SMALL arrays (33 x 33 Float64 = 8.7 KB: 5 line groups per pass on 4 warps, a barrier per pass and array):
+    // a CTA takes B arrays at a time as one block — the passes enumerate the lines of the whole block (the arrays are one
+    // more, untransformed, outermost dimension), so the warps see B times as many line groups per barrier.  B: blocks of
+    // <= 36 KB (four CTAs per SM still fit), at most 16 arrays, and enough blocks left to fill the GPU.
+    long long B = 1;
+    static const int block_env = [] {  // experiments: FASTCHEB_FITND_BLOCK=1 disables, =n forces n arrays per block
+      const char* e = getenv("FASTCHEB_FITND_BLOCK");
+      return e ? atoi(e) : 0;
+    }();
+    const size_t abytes = (size_t)reals * rs;
+    if (block_env > 0)
+      B = std::min<long long>(block_env, howmany);
+    else if (abytes <= 18 * 1024 && howmany >= 16LL * di->sms)
+      B = std::max<long long>(1, std::min<long long>({(long long)(36 * 1024 / abytes), 16LL, howmany / (8LL * di->sms)}));
+    if (af_bytes + (size_t)B * abytes + 1024 + 256 > budget) B = 1;
+    if (B > 1) {
+      const long long nb = howmany / B, rest = howmany - nb * B;
+      int rc = run(vals, coefs, nb, B * reals, 0, B);
+      if (rc == -1) {
+        B = 1;  // not launchable as blocks: one array per CTA below
+      } else {
+        FC_TRY(rc);
+        if (rest > 0) {
+          rc = run((const char*)vals + (size_t)nb * B * reals * rs, (char*)coefs + (size_t)nb * B * reals * rs, 1, rest * reals,
+                   nb * B, rest);
+          if (rc == -1) return fail(FASTCHEB_ECUDA, "resident DCT-I kernel: tail block not launchable");
+          FC_TRY(rc);
+        }
+        *handled = true;
+        return FASTCHEB_OK;
+      }
+    }
     const int rc = run(vals, coefs, howmany, reals, 0, 1);
     if (rc == -1) return FASTCHEB_OK;
     FC_TRY(rc);

@@ -29,6 +29,10 @@ ND_CASES = [  # dims, K, complex, howmany
     ((33, 33, 33), 2, False, 3),          # too large for shared memory in both precisions: slabs + strided tiles, vector elements
     ((17, 17, 17, 9), None, True, 3),     # ... complex, unequal last dimension
     ((65, 65, 20), None, False, 2),       # ... once-folded last dimension (n - 1 = 19)
+    ((17, 17), None, False, 2501),        # small arrays in batches: a CTA takes blocks of several arrays (+ a ragged tail)
+    ((33, 33), None, False, 5003),
+    ((9, 9, 9), 2, False, 3000),
+    ((17, 9), None, True, 2400),
 ]
 
 

@@ -17,6 +17,9 @@ from fastcheb import _capi  # noqa: E402
 
 SHAPES = [  # dims, howmany, dtype
     ((65, 65), 4096, np.float64),
+    ((33, 33), 65536, np.float64),
+    ((33, 33), 65536, np.float32),
+    ((17, 17, 17), 8192, np.float64),
     ((65, 65), 4096, np.float32),
     ((33, 33, 33), 512, np.float64),
     ((33, 33, 33), 512, np.float32),
