@@ -95,6 +95,42 @@ def test_droptol_and_chebinterp(fc, orc):
         assert fc.droptol(cc, tol).shape == orc.droptol(cc, 2, tol).shape   # complex modulus (interp.jl:74)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_chebinterp_fused_droptol_matches_separate_calls(fc, seed):
+    """chebinterp's trimming statistics come from the resident fit kernel itself (fit_nd.cuh: max / min of the element
+    norms, then every element >= tol * max marks its hyperplanes); chebcoefs followed by droptol goes through the
+    separate reduction kernels.  Same coefficients, same decisions: shapes and coefficients must agree exactly, for random
+    shapes (size-1 dimensions, vector / complex elements), decay rates and tolerances."""
+    rng = np.random.default_rng(4000 + seed)
+    for _ in range(12):
+        N = int(rng.integers(1, 4))
+        dims = tuple(int(v) for v in rng.choice([1, 2, 3, 5, 9, 17, 20, 33, 40, 65], N))
+        if int(np.prod(dims)) > 60000:
+            dims = dims[:-1] + (5,)
+        dt = np.float32 if rng.integers(0, 3) == 0 else np.float64
+        cplx = bool(rng.integers(0, 4) == 0)
+        K = [None, None, 2, 3][int(rng.integers(0, 4))]
+        lb, ub = -np.ones(N), np.ones(N) * 2
+        x = fc.chebpoints(tuple(d - 1 for d in dims), lb, ub) if N > 1 else fc.chebpoints(dims[0] - 1, lb[0], ub[0])[..., None]
+        freq = rng.uniform(0.2, 6.0, N)
+        g = np.ones(dims)
+        for d in range(N):
+            g = g * np.cos(freq[d] * x[..., d] + rng.uniform(0, 3))
+        if K:
+            g = np.stack([g * (10.0 ** -int(rng.integers(0, 6))) + 0.1 * k for k in range(K)], axis=-1)
+        if cplx:
+            g = g + 1j * np.roll(g, 1, axis=0) * 10.0 ** -int(rng.integers(0, 9))
+        g = g.astype((np.complex64 if dt == np.float32 else np.complex128) if cplx else dt)
+        tol = [None, 0.0, 1e-2, 1e-5, 1e-9, 1e-14][int(rng.integers(0, 6))]
+        a = fc.chebinterp(g, lb, ub, tol=tol)
+        c = fc.chebcoefs(g, ndim=N)
+        eff = (np.finfo(dt).eps if tol is None else tol)
+        want = fc.droptol(c, eff, ndim=N)
+        assert a.coefs.shape == want.shape, (dims, K, cplx, np.dtype(dt).name, tol)
+        assert np.array_equal(a.coefs, want), (dims, K, cplx, np.dtype(dt).name, tol)
+        a.close()
+
+
 def test_fit_then_eval_roundtrip(fc):
     """Size-independent property: the interpolant reproduces its data on the Chebyshev grid."""
     lb, ub = np.array([-1.0, 0.0, 2.0]), np.array([1.0, 1.0, 5.0])
