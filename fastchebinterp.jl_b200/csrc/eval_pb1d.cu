@@ -146,8 +146,8 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
     const int G = pb_group(E), ngroups = M / G;
     const size_t count = ngroups * G == M ? (size_t)M * A * E : (size_t)pb_tail_base(A, E) + (size_t)(M - ngroups * G) * A * E;
     std::vector<unsigned char> out(count * rs, 0);
-    long double sum_abs = 0, sum_k2 = 0;
     for (int e = 0; e < E; ++e) {
+      long double sum_abs = 0, sum_k2 = 0;
       std::fill(D.begin(), D.end(), 0.0L);
       for (int hi = M - 1; hi >= 0; --hi)
         for (int lo = 0; lo < A; ++lo) {
@@ -175,12 +175,12 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
         sum_abs += fabsl(coef(k, e));
         sum_k2 += fabsl(coef(k, e)) * (long double)k * (long double)k;
       }
+      pb.sum_abs[e] = (double)sum_abs;
+      pb.sum_k2[e] = (double)sum_k2;
     }
     pb.h_D = out;  // the launches pass the coefficients in the kernel parameters
     pb.AMAX = A;
     pb.M = M;
-    pb.sum_abs = (double)sum_abs;
-    pb.sum_k2 = (double)sum_k2;
     pb.state.store(kPbBuilt);
   }
   if (forced || pb.checked) return FASTCHEB_OK;
@@ -225,22 +225,30 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
   if (rc != FASTCHEB_OK) return rc;
   if (ce != cudaSuccess || e2 != cudaSuccess)
     return fail(FASTCHEB_ECUDA, "product-basis self-check failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : e2));
-  double dv = 0, dJ = 0;
   auto get = [&](size_t off, size_t i) -> double {
     return p->dtype == FASTCHEB_F64 ? ((const double*)(h.data() + off))[i] : (double)((const float*)(h.data() + off))[i];
   };
-  bool finite = true;
-  for (size_t i = 0; i < (size_t)NP * E; ++i) {
-    const double a = fabs(get(2 * vb, i) - get(0, i)), b = fabs(get(3 * vb, i) - get(vb, i));
-    finite = finite && std::isfinite(a) && std::isfinite(b);
-    dv = std::max(dv, a);
-    dJ = std::max(dJ, b);
-  }
+  // the tolerances are PER COMPONENT (16 eps sum_k |c_{k,e}| for the values of component e): the worst ratio over the
+  // components decides (one sum over all components would be E times too lenient for a vector-valued polynomial)
   const double eps = p->dtype == FASTCHEB_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
-  pb.ok_val = finite && dv <= 0.25 * 16 * eps * pb.sum_abs;
-  pb.ok_jac = finite && pb.ok_val && dJ <= 0.25 * 16 * eps * pb.sum_k2 * 2.0 / span;
-  pb.check_dv = pb.sum_abs > 0 ? dv / (16 * eps * pb.sum_abs) : 0;
-  pb.check_dJ = pb.sum_k2 > 0 ? dJ / (16 * eps * pb.sum_k2 * 2.0 / span) : 0;
+  bool finite = true;
+  double rv = 0, rJ = 0;
+  for (int e = 0; e < E; ++e) {
+    double dv = 0, dJ = 0;
+    for (size_t i = e; i < (size_t)NP * E; i += E) {
+      const double a = fabs(get(2 * vb, i) - get(0, i)), b = fabs(get(3 * vb, i) - get(vb, i));
+      finite = finite && std::isfinite(a) && std::isfinite(b);
+      dv = std::max(dv, a);
+      dJ = std::max(dJ, b);
+    }
+    const double tv = 16 * eps * pb.sum_abs[e], tJ = 16 * eps * pb.sum_k2[e] * 2.0 / span;
+    rv = std::max(rv, tv > 0 ? dv / tv : (dv > 0 ? INFINITY : 0.0));
+    rJ = std::max(rJ, tJ > 0 ? dJ / tJ : (dJ > 0 ? INFINITY : 0.0));
+  }
+  pb.ok_val = finite && rv <= 0.25;
+  pb.ok_jac = finite && pb.ok_val && rJ <= 0.25;
+  pb.check_dv = rv;
+  pb.check_dJ = rJ;
   pb.checked = true;
   pb.state.store((pb.ok_val || pb.ok_jac) ? kPbAccepted : kPbRejected);
   return FASTCHEB_OK;

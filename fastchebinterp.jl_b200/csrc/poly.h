@@ -46,7 +46,7 @@ struct PbPlan {
   bool checked = false, ok_val = false, ok_jac = false;
   std::vector<unsigned char> h_D;  // product-basis coefficients (kernel layout, eval_pb1d.cuh), passed as kernel parameters
   int AMAX = 0, M = 0;
-  double sum_abs = 0, sum_k2 = 0;      // sum |c_k|, sum |c_k| k^2 over all components
+  double sum_abs[8] = {0}, sum_k2[8] = {0};  // per real component e: sum_k |c_{k,e}|, sum_k |c_{k,e}| k^2 (the tolerances are per component)
   double check_dv = 0, check_dJ = 0;   // self-check result: worst difference over the tolerance
 };
 
