@@ -303,8 +303,11 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
     hub = ub[0];
   }
   const int KS = (int)((n - 1 + 3) / 4);
-  int RS = 4 * std::max(KS, 1);
-  while (RS % 16 != 4) RS += 2;  // row stride = 4 (mod 16) doubles: the B-fragment loads of a half warp hit 16 distinct banks
+  const int ksu = KS <= 4 ? 4 : (KS <= 8 ? 8 : (KS <= 12 ? 12 : 16));  // k-steps the instantiation executes
+  // a table row holds the 4 ksu columns the kernel reads (zero beyond n - 1), padded to a stride = 4 (mod 16) doubles: the
+  // B-fragment loads of a half warp hit 16 distinct banks
+  int RS = 4 * ksu;
+  while (RS % 16 != 4) RS += 2;
   const long long ntiles = (M + kSharedPT - 1) / kSharedPT;
   const size_t tableBytes = (size_t)ntiles * kSharedPT * RS * sizeof(double);
   const size_t cbytes = (size_t)howmany * n * E * rs, pbytes = (size_t)M * rs, obytes = (size_t)howmany * M * E * rs;
@@ -352,7 +355,6 @@ extern "C" int fastcheb_eval_many_shared(int64_t howmany, int64_t n, int dtype, 
     return e ? atoi(e) : 0;
   }();
   const int rt = rt_env == 1 ? 1 : 2;
-  const int ksu = KS <= 4 ? 4 : (KS <= 8 ? 8 : (KS <= 12 ? 12 : 16));  // k-steps the instantiation executes
   const int rte = (rt == 2 && ksu == 16) ? 2 : 1;
   const long long nblocks = (rows + 64 * rte - 1) / (64 * rte);
   // as many tile stages as two resident CTAs per SM leave room for (3 at n = 65), at least 2

@@ -418,7 +418,9 @@ def test_eval_many_shared_points_matches_oracle(fc, orc, dt):
     rng = np.random.default_rng(78)
     eps = np.finfo(dt).eps
     for n, K, cplx, howmany, M in ((65, None, False, 301, 1000), (65, 3, False, 50, 130), (33, None, True, 77, 257), (1, None, False, 9, 5),
-                                   (2, 2, False, 20, 64), (40, 2, True, 130, 63)):
+                                   (2, 2, False, 20, 64), (40, 2, True, 130, 63),
+                                   # k-step counts between the instantiated ones (n = 19: 5 of 8, n = 37: 9 of 12, n = 51: 13 of 16)
+                                   (5, None, False, 3, 1), (19, 3, True, 758, 949), (37, None, False, 100, 64), (51, 2, False, 70, 200)):
         shape = (howmany, n) + ((K,) if K else ())
         # coefficients that decay like those of fitted smooth functions (what configs[4] evaluates).  For dense-random
         # coefficient vectors the Clenshaw recurrence itself carries ~k eps |c_k| of rounding at the end points, and a
