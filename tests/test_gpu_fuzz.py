@@ -2,12 +2,17 @@
 vector / complex, both precisions, odd batch sizes, non-trivial boxes.  Clenshaw must be bit-identical; whatever AUTO
 picks (Clenshaw, ring DMMA, resident 2-D DMMA) must be within 16 eps sum|c| (values) and the differentiated-series bound
 (Jacobians), as in test_gpu_eval.py."""
+import os
+
 import numpy as np
 import pytest
 
 from parity_util import jac_tol
 
 pytestmark = pytest.mark.gpu
+
+# other random streams on demand: FASTCHEB_FUZZ_OFFSET=n shifts every seed (the default run is deterministic)
+OFFSET = 100000 * int(os.environ.get("FASTCHEB_FUZZ_OFFSET", "0"))
 
 
 def random_case(rng):
@@ -24,7 +29,7 @@ def random_case(rng):
 
 @pytest.mark.parametrize("seed", range(40))
 def test_random_shapes(fc, orc, seed):
-    rng = np.random.default_rng(1000 + seed)
+    rng = np.random.default_rng(1000 + seed + OFFSET)
     for _ in range(10):
         dims, K, cplx, dt = random_case(rng)
         N = len(dims)
@@ -72,7 +77,7 @@ def test_random_shapes(fc, orc, seed):
 def test_random_fits(fc, orc, seed):
     """chebcoefs on random shapes: batches of 1-D lines of every length 2..65 (tensor-core path incl. ragged tails and
     vector / complex elements) and small N-d arrays (generic path), both precisions, vs the long-double oracle."""
-    rng = np.random.default_rng(2000 + seed)
+    rng = np.random.default_rng(2000 + seed + OFFSET)
     for _ in range(8):
         dt = np.float32 if rng.integers(0, 2) else np.float64
         tol = 1e-13 if dt == np.float64 else 450 * np.finfo(np.float32).eps
@@ -106,7 +111,7 @@ def test_random_fits(fc, orc, seed):
 def test_random_domain_errors(fc, seed):
     """The FIRST offending point (eval.jl:64: outside the closed box, or NaN) is what every kernel family reports,
     wherever it sits in the batch (first / last unit, several bad points, large batches that use all warps)."""
-    rng = np.random.default_rng(3000 + seed)
+    rng = np.random.default_rng(3000 + seed + OFFSET)
     for _ in range(6):
         dims, K, cplx, dt = random_case(rng)
         N = len(dims)
