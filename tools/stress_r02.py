@@ -126,5 +126,60 @@ for it in range(int(os.environ.get("STRESS_SHARED", "40"))):
     elif rd > 0.6 or rv > 0.6:
         print("shared: close", n, howmany, M, K, cplx, np.dtype(dt).name, rv, rd)
 print("shared points: worst value / derivative ratio to tolerance", worst["sh_v"], worst["sh_d"])
+# (d) random N-d / long-line fit batches through the resident kernel and its slab / tile path, against scipy's DCT-I
+#     (pocketfft REDFT00 + the normalisation of interp.jl:49-54) and against single-array fits
+import scipy.fft
+
+def ref_chebcoefs(v, ndim):
+    v = np.asarray(v, dtype=np.complex128 if np.iscomplexobj(v) else np.float64)
+    axes = [d for d in range(ndim) if v.shape[d] > 1]
+    def tr(a):
+        return scipy.fft.dctn(a, type=1, axes=axes) if axes else a.copy()
+    c = tr(v.real) + 1j * tr(v.imag) if np.iscomplexobj(v) else tr(v)
+    for d in axes:
+        nd = v.shape[d]
+        c = c / (2 * (nd - 1))
+        idx = [slice(None)] * c.ndim
+        idx[d] = slice(1, nd - 1)
+        c[tuple(idx)] *= 2
+    return c
+
+wfit = 0.0
+for it in range(int(os.environ.get("STRESS_FITS", "40"))):
+    N = int(rng.integers(1, 4))
+    dt = np.float32 if rng.integers(0, 2) else np.float64
+    K = [None, None, 2, 3][int(rng.integers(0, 4))]
+    cplx = bool(rng.integers(0, 4) == 0)
+    E = (K or 1) * (2 if cplx else 1)
+    while True:
+        if N == 1:
+            dims = (int(rng.choice([rng.integers(2, 66), rng.integers(66, 130), 129, 201, 257, 97, 81])),)
+        else:
+            dims = tuple(int(v) for v in rng.choice([1, 2, 3, 5, 9, 17, 20, 33, 40, 64, 65, 129], N))
+        nb = int(np.prod(dims)) * E * np.dtype(dt).itemsize
+        if nb <= 600 * 1024:
+            break
+    howmany = int(rng.integers(1, 200 if nb < 40 * 1024 else 12))
+    shape = (howmany,) + dims + ((K,) if K else ())
+    vals = rng.uniform(-1, 1, shape)
+    if cplx:
+        vals = vals + 1j * rng.uniform(-1, 1, shape)
+    vals = vals.astype((np.complex64 if dt == np.float32 else np.complex128) if cplx else dt)
+    if os.environ.get("STRESS_VERBOSE"):
+        print("fit cfg", dims, K, cplx, np.dtype(dt).name, howmany, flush=True)
+    got = fc.chebcoefs(vals, ndim=len(dims), howmany=howmany)
+    tol = 1e-13 if dt == np.float64 else 450 * np.finfo(np.float32).eps
+    for i in sorted({0, howmany // 2, howmany - 1}):
+        want = ref_chebcoefs(vals[i], len(dims))
+        r = np.abs(got[i] - want).max() / (tol * np.abs(want).max())
+        wfit = max(wfit, r)
+        if r > 1:
+            print("FIT VIOLATION", dims, K, cplx, np.dtype(dt).name, howmany, i, r); fail += 1
+        one = fc.chebcoefs(vals[i], ndim=len(dims))
+        if not np.array_equal(one, got[i]):
+            d1 = np.abs(one - got[i]).max() / (tol * np.abs(want).max())
+            if d1 > 1:
+                print("FIT single-vs-batch VIOLATION", dims, K, cplx, np.dtype(dt).name, howmany, i, d1); fail += 1
+print("random fit batches: worst ratio to tolerance", wfit)
 print("FAILURES", fail)
 sys.exit(1 if fail else 0)
