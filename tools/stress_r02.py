@@ -181,5 +181,54 @@ for it in range(int(os.environ.get("STRESS_FITS", "40"))):
             if d1 > 1:
                 print("FIT single-vs-batch VIOLATION", dims, K, cplx, np.dtype(dt).name, howmany, i, d1); fail += 1
 print("random fit batches: worst ratio to tolerance", wfit)
+# (e) N-d evaluation: the tensor-core paths against the Clenshaw kernel with the STRICT per-component tolerance
+#     (16 eps sum_k |c_{k,e}| for component e; the test suite sums over all components)
+wnd_v = wnd_J = 0.0
+for it in range(int(os.environ.get("STRESS_ND", "40"))):
+    N = int(rng.integers(2, 5))
+    while True:
+        dims = tuple(int(v) for v in rng.integers(5, 41, N))
+        if np.prod(dims) <= 60000 and np.prod(dims[1:]) >= 8:
+            break
+    K = [None, 2, 3, 5][int(rng.integers(0, 4))]
+    cplx = bool(rng.integers(0, 4) == 0)
+    dt = np.float32 if rng.integers(0, 3) == 0 else np.float64
+    shape = dims + ((K,) if K else ())
+    c = rng.uniform(-1, 1, shape)
+    if cplx:
+        c = c + 1j * rng.uniform(-1, 1, shape)
+    c = c.astype((np.complex64 if dt == np.float32 else np.complex128) if cplx else dt)
+    lb = rng.uniform(-2, 0, N).astype(dt)
+    ub = (lb + rng.uniform(0.5, 3, N)).astype(dt)
+    npts = int(rng.integers(1, 5000))
+    pts = np.clip((lb + (ub - lb) * rng.random((npts, N))).astype(dt), lb, ub)
+    pts[0], pts[-1] = lb, ub
+    p = fc.ChebPoly(c, lb, ub)
+    p.set_algo(fc.ALGO_CLENSHAW, dt)
+    v0, J0 = fc.chebjacobian(p, pts)
+    p.set_algo(fc.ALGO_DMMA, dt)
+    if p.get_algo(False, dt) not in (fc.ALGO_DMMA, fc.ALGO_DMMA_RING):
+        p.close(); continue
+    v1, J1 = fc.chebjacobian(p, pts)
+    eps = np.finfo(dt).eps
+    cr = (c.view(dt) if cplx else c).reshape(int(np.prod(dims)), -1).astype(np.float64)   # (coefficients, real components)
+    tol = 16 * eps * np.abs(cr).sum(axis=0)
+    real = lambda a: (np.ascontiguousarray(a).view(dt) if cplx else a)
+    rv = (np.abs(real(v1).reshape(npts, -1).astype(np.float64) - real(v0).reshape(npts, -1).astype(np.float64)).max(axis=0) / tol).max()
+    wnd_v = max(wnd_v, rv)
+    for d in range(N):
+        kshape = [1] * N + [1]
+        kshape[d] = dims[d]
+        k2 = (np.arange(dims[d], dtype=np.float64) ** 2).reshape(kshape)
+        ca = np.abs((c.view(dt) if cplx else c).reshape(dims + (-1,)).astype(np.float64))
+        tolJ = 16 * eps * (ca * k2).reshape(int(np.prod(dims)), -1).sum(axis=0) * 2 / (float(ub[d]) - float(lb[d]))
+        Jd0 = real(np.ascontiguousarray(J0[..., d] if J0.ndim == 3 else J0)).reshape(npts, -1).astype(np.float64)
+        Jd1 = real(np.ascontiguousarray(J1[..., d] if J1.ndim == 3 else J1)).reshape(npts, -1).astype(np.float64)
+        rJ = (np.abs(Jd1 - Jd0).max(axis=0) / tolJ).max()
+        wnd_J = max(wnd_J, rJ)
+    if rv > 1 or wnd_J > 1:
+        print("ND VIOLATION", dims, K, cplx, np.dtype(dt).name, rv, wnd_J); fail += 1
+    p.close()
+print("N-d tensor-core paths vs Clenshaw, per-component tolerances: worst value / Jacobian ratio", wnd_v, wnd_J)
 print("FAILURES", fail)
 sys.exit(1 if fail else 0)
