@@ -12,13 +12,17 @@ namespace fastcheb {
 namespace {
 
 template <typename R, int AMAX, int EC, int P, bool JAC>
-cudaError_t launch_p(const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
+cudaError_t launch_p(const Pb1dParams& prm, const void* h_D, const void* h_D2, size_t d_count, int sms, cudaStream_t st) {
   auto kern = eval_pb1d_kernel<R, AMAX, EC, P, JAC>;
-  constexpr int CAP = pb_cap(AMAX, EC);
-  if (d_count > (size_t)CAP) return cudaErrorInvalidValue;
-  Pb1dArgs<R, CAP> args;
+  constexpr int CAP = pb_cap(AMAX, EC, JAC);
+  constexpr int CAP2 = JAC ? pb_cap2<R>(AMAX, EC) : 1;
+  static_assert(!JAC || CAP2 == CAP || pb_group(EC, true) == 1, "a shortened second table needs the single-row layout");
+  if (d_count > (size_t)CAP || (JAC && (!h_D2 || d_count > (size_t)CAP2))) return cudaErrorInvalidValue;
+  Pb1dArgs<R, CAP, CAP2> args;
+  static_assert(sizeof(args) <= 32764, "kernel parameter space");
   args.p = prm;
   memcpy(args.D, h_D, d_count * sizeof(R));
+  if constexpr (JAC) memcpy(args.D2, h_D2, d_count * sizeof(R));
   int threads = 256;
   if (const char* t = getenv("FASTCHEB_PB_THREADS")) {
     const int v = atoi(t);
@@ -38,37 +42,40 @@ cudaError_t launch_p(const Pb1dParams& prm, const void* h_D, size_t d_count, int
 }
 
 template <typename R, int AMAX, int EC, bool JAC>
-cudaError_t launch(const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
-  // points per thread: the T_a(w) tables are AMAX (2 AMAX with derivatives) registers per point
+cudaError_t launch(const Pb1dParams& prm, const void* h_D, const void* h_D2, size_t d_count, int sms, cudaStream_t st) {
+  // points per thread: the T_lo(z) table is AMAX registers per point, the inner sums P * EC (twice that with the
+  // derivative series of the gradient kernels) — 2 points unless the sums of a gradient kernel would not fit
   // (Float32: half the registers per point, and the FP32 pipe is fast enough for the kernel to be issue-bound — twice
   // the points per thread halve the non-FMA instructions per point)
-  constexpr int P0 = JAC ? 1 : 2;
-  constexpr int P = P0 * ((sizeof(R) == 4 && EC <= 2) ? 2 : 1);
+  constexpr int EF = EC * (JAC ? 2 : 1);  // inner sums per point and row
+  // (Float64 value kernel, 16-entry tables, 4 components: 2 points spill ~1 KB per thread)
+  constexpr int P0 = ((JAC && EC > 1) || (sizeof(R) == 8 && AMAX == 16 && EC == 4)) ? 1 : 2;
+  constexpr int P = P0 * ((sizeof(R) == 4 && EF <= 2) ? 2 : 1);
   if constexpr (P != P0) {
     static const bool small = getenv("FASTCHEB_PB_SMALLP") != nullptr;  // experiments
-    if (small) return launch_p<R, AMAX, EC, P0, JAC>(prm, h_D, d_count, sms, st);
+    if (small) return launch_p<R, AMAX, EC, P0, JAC>(prm, h_D, h_D2, d_count, sms, st);
   }
-  return launch_p<R, AMAX, EC, P, JAC>(prm, h_D, d_count, sms, st);
+  return launch_p<R, AMAX, EC, P, JAC>(prm, h_D, h_D2, d_count, sms, st);
 }
 
 template <typename R, int AMAX, bool JAC>
-cudaError_t launch_ec(int ec, const Pb1dParams& prm, const void* h_D, size_t d_count, int sms, cudaStream_t st) {
+cudaError_t launch_ec(int ec, const Pb1dParams& prm, const void* h_D, const void* h_D2, size_t d_count, int sms, cudaStream_t st) {
   switch (ec) {
-    case 1: return launch<R, AMAX, 1, JAC>(prm, h_D, d_count, sms, st);
-    case 2: return launch<R, AMAX, 2, JAC>(prm, h_D, d_count, sms, st);
-    case 3: return launch<R, AMAX, 3, JAC>(prm, h_D, d_count, sms, st);
-    case 4: return launch<R, AMAX, 4, JAC>(prm, h_D, d_count, sms, st);
+    case 1: return launch<R, AMAX, 1, JAC>(prm, h_D, h_D2, d_count, sms, st);
+    case 2: return launch<R, AMAX, 2, JAC>(prm, h_D, h_D2, d_count, sms, st);
+    case 3: return launch<R, AMAX, 3, JAC>(prm, h_D, h_D2, d_count, sms, st);
+    case 4: return launch<R, AMAX, 4, JAC>(prm, h_D, h_D2, d_count, sms, st);
   }
   return cudaErrorInvalidValue;
 }
 
 template <typename R>
-cudaError_t launch_any(int amax, int ec, bool jac, const Pb1dParams& prm, const void* h_D, size_t d_count, int sms,
+cudaError_t launch_any(int amax, int ec, bool jac, const Pb1dParams& prm, const void* h_D, const void* h_D2, size_t d_count, int sms,
                        cudaStream_t st) {
   if (amax == 8)
-    return jac ? launch_ec<R, 8, true>(ec, prm, h_D, d_count, sms, st) : launch_ec<R, 8, false>(ec, prm, h_D, d_count, sms, st);
+    return jac ? launch_ec<R, 8, true>(ec, prm, h_D, h_D2, d_count, sms, st) : launch_ec<R, 8, false>(ec, prm, h_D, h_D2, d_count, sms, st);
   if (amax == 16)
-    return jac ? launch_ec<R, 16, true>(ec, prm, h_D, d_count, sms, st) : launch_ec<R, 16, false>(ec, prm, h_D, d_count, sms, st);
+    return jac ? launch_ec<R, 16, true>(ec, prm, h_D, h_D2, d_count, sms, st) : launch_ec<R, 16, false>(ec, prm, h_D, h_D2, d_count, sms, st);
   return cudaErrorInvalidValue;
 }
 
@@ -82,6 +89,8 @@ int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
               int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
               const void* tan) {
   const PbPlan& pb = p->pb;
+  if (jac && pb.h_D2.empty())
+    return fail(FASTCHEB_EUNSUPPORTED, "product-basis gradients: two coefficient tables of this shape exceed the kernel parameter space");
   Pb1dParams prm;
   memset(&prm, 0, sizeof prm);
   prm.pts = pts;
@@ -100,10 +109,11 @@ int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
   prm.ub = p->ub[0];
   prm.tan = tan;
   prm.mode = mode;
-  const size_t d_count = pb.h_D.size() / real_size(p->dtype);
+  const std::vector<unsigned char>& hD = (jac && !pb.h_DJ.empty()) ? pb.h_DJ : pb.h_D;
+  const size_t d_count = hD.size() / real_size(p->dtype);
   const cudaError_t e = p->dtype == FASTCHEB_F64
-                            ? launch_any<double>(pb.AMAX, p->E, jac, prm, pb.h_D.data(), d_count, p->di->sms, st)
-                            : launch_any<float>(pb.AMAX, p->E, jac, prm, pb.h_D.data(), d_count, p->di->sms, st);
+                            ? launch_any<double>(pb.AMAX, p->E, jac, prm, hD.data(), pb.h_D2.empty() ? nullptr : pb.h_D2.data(), d_count, p->di->sms, st)
+                            : launch_any<float>(pb.AMAX, p->E, jac, prm, hD.data(), pb.h_D2.empty() ? nullptr : pb.h_D2.data(), d_count, p->di->sms, st);
   if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "product-basis kernel launch failed: %s", cudaGetErrorString(e));
   return FASTCHEB_OK;
 }
@@ -143,15 +153,25 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
     std::vector<long double> D((size_t)(M + 1) * A);
     // kernel layout (eval_pb1d.cuh): full groups of G rows interleaved [group][lo][j][e] from offset 0, the M % G
     // remaining rows [t][lo][e] from the fixed offset pb_tail_base
-    const int G = pb_group(E), ngroups = M / G;
-    const size_t count = ngroups * G == M ? (size_t)M * A * E : (size_t)pb_tail_base(A, E) + (size_t)(M - ngroups * G) * A * E;
-    std::vector<unsigned char> out(count * rs, 0);
-    for (int e = 0; e < E; ++e) {
-      long double sum_abs = 0, sum_k2 = 0;
+    // (the scalar gradient kernel groups 2 rows, the value kernel 4: pb_group — it gets its own copy of D, h_DJ)
+    auto count_of = [&](int G) {
+      const int ngroups = M / G;
+      return ngroups * G == M ? (size_t)M * A * E : (size_t)pb_tail_base(A, E) + (size_t)(M - ngroups * G) * A * E;
+    };
+    const int Gv = pb_group(E, false), Gj = pb_group(E, true);
+    std::vector<unsigned char> out(count_of(Gv) * rs, 0), outj, out2;
+    // gradient kernels: the same table for the derivative series p' = sum_k c'_k T_k, c'_{k-1} = c'_{k+1} + 2 k c_k
+    // (c'_0 halved) — skipped where two tables do not fit the kernel parameter space (pb_cap2)
+    const bool grad = count_of(Gj) <= (size_t)(rs == 8 ? pb_cap2<double>(A, E) : pb_cap2<float>(A, E));
+    if (grad) out2.assign(count_of(Gj) * rs, 0);
+    if (grad && Gj != Gv) outj.assign(count_of(Gj) * rs, 0);
+    std::vector<long double> cd((size_t)n + 2);
+    auto table = [&](auto&& cf, int e, int G, std::vector<unsigned char>& dst) {
+      const int ngroups = M / G;
       std::fill(D.begin(), D.end(), 0.0L);
       for (int hi = M - 1; hi >= 0; --hi)
         for (int lo = 0; lo < A; ++lo) {
-          const long double c = coef(A * hi + lo, e);
+          const long double c = cf(A * hi + lo);
           long double v;
           if (lo == 0)
             v = c;
@@ -167,10 +187,21 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
                                ? (((size_t)(hi / G) * A + lo) * G + (size_t)(hi % G)) * E + e
                                : (size_t)pb_tail_base(A, E) + ((size_t)(hi - ngroups * G) * A + lo) * E + e;
           if (p->dtype == FASTCHEB_F64)
-            ((double*)out.data())[o] = (double)D[(size_t)hi * A + lo];
+            ((double*)dst.data())[o] = (double)D[(size_t)hi * A + lo];
           else
-            ((float*)out.data())[o] = (float)D[(size_t)hi * A + lo];
+            ((float*)dst.data())[o] = (float)D[(size_t)hi * A + lo];
         }
+    };
+    for (int e = 0; e < E; ++e) {
+      long double sum_abs = 0, sum_k2 = 0;
+      table([&](int k) { return coef(k, e); }, e, Gv, out);
+      if (!outj.empty()) table([&](int k) { return coef(k, e); }, e, Gj, outj);
+      if (grad) {
+        std::fill(cd.begin(), cd.end(), 0.0L);
+        for (int k = n - 1; k >= 1; --k) cd[k - 1] = cd[k + 1] + 2.0L * (long double)k * coef(k, e);
+        cd[0] *= 0.5L;
+        table([&](int k) { return k < n ? cd[k] : 0.0L; }, e, Gj, out2);
+      }
       for (int k = 0; k < n; ++k) {
         sum_abs += fabsl(coef(k, e));
         sum_k2 += fabsl(coef(k, e)) * (long double)k * (long double)k;
@@ -178,6 +209,8 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
       pb.sum_abs[e] = (double)sum_abs;
       pb.sum_k2[e] = (double)sum_k2;
     }
+    pb.h_D2 = out2;
+    pb.h_DJ = outj;
     pb.h_D = out;  // the launches pass the coefficients in the kernel parameters
     pb.AMAX = A;
     pb.M = M;
@@ -216,9 +249,10 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
   unsigned char *d_x = dbuf + 4 * vb, *d_v0 = dbuf, *d_J0 = dbuf + vb, *d_v1 = dbuf + 2 * vb, *d_J1 = dbuf + 3 * vb;
   std::vector<unsigned char> h((size_t)4 * vb);
   int rc = FASTCHEB_OK;
+  const bool has_grad = !pb.h_D2.empty();
   cudaError_t ce = cudaMemcpyAsync(d_x, hx.data(), hx.size(), cudaMemcpyHostToDevice, st);
   if (ce == cudaSuccess) rc = eval_clenshaw_device(p, d_x, NP, d_v0, E, d_J0, E, true, nullptr, 0, st, 0, nullptr);
-  if (ce == cudaSuccess && rc == FASTCHEB_OK) rc = pb1d_eval(p, d_x, NP, d_v1, E, d_J1, E, true, nullptr, 0, st, 0, nullptr);
+  if (ce == cudaSuccess && rc == FASTCHEB_OK) rc = pb1d_eval(p, d_x, NP, d_v1, E, d_J1, E, has_grad, nullptr, 0, st, 0, nullptr);
   if (ce == cudaSuccess && rc == FASTCHEB_OK) ce = cudaMemcpyAsync(h.data(), dbuf, 4 * vb, cudaMemcpyDeviceToHost, st);
   const cudaError_t e2 = cudaStreamSynchronize(st);
   cudaFreeAsync(dbuf, st);
@@ -236,7 +270,7 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
   for (int e = 0; e < E; ++e) {
     double dv = 0, dJ = 0;
     for (size_t i = e; i < (size_t)NP * E; i += E) {
-      const double a = fabs(get(2 * vb, i) - get(0, i)), b = fabs(get(3 * vb, i) - get(vb, i));
+      const double a = fabs(get(2 * vb, i) - get(0, i)), b = has_grad ? fabs(get(3 * vb, i) - get(vb, i)) : 0.0;
       finite = finite && std::isfinite(a) && std::isfinite(b);
       dv = std::max(dv, a);
       dJ = std::max(dJ, b);
@@ -246,7 +280,7 @@ int pb1d_plan(const fastcheb_poly* cp, bool forced) {
     rJ = std::max(rJ, tJ > 0 ? dJ / tJ : (dJ > 0 ? INFINITY : 0.0));
   }
   pb.ok_val = finite && rv <= 0.25;
-  pb.ok_jac = finite && pb.ok_val && rJ <= 0.25;
+  pb.ok_jac = has_grad && finite && pb.ok_val && rJ <= 0.25;
   pb.check_dv = rv;
   pb.check_dJ = rJ;
   pb.checked = true;

@@ -32,8 +32,9 @@
 namespace fastcheb {
 
 // rows hi of D processed together (their coefficients are interleaved, see the kernel): 8 independent accumulation
-// chains per thread whatever the number of components
-__host__ __device__ constexpr int pb_group(int ec) { return ec == 1 ? 4 : (ec == 2 ? 2 : 1); }
+// chains per thread whatever the number of components (the gradient kernels carry two inner sums per component: the
+// scalar one takes 2 rows x 2 points x 2 sums, so its tables are laid out in groups of 2, not 4)
+__host__ __device__ constexpr int pb_group(int ec, bool jac = false) { return ec == 1 ? (jac ? 2 : 4) : (ec == 2 ? 2 : 1); }
 
 struct Pb1dParams {
   const void* pts;  // npts reals
@@ -61,12 +62,23 @@ struct Pb1dParams {
 // H <= pb_mmax(AMAX) rows; the groups sit at compile-time offsets, the H % BU single rows after the LAST POSSIBLE group
 __host__ __device__ constexpr int pb_mmax(int amax) { return amax == 8 ? 16 : 32; }
 __host__ __device__ constexpr int pb_tail_base(int amax, int ec) { return pb_mmax(amax) * amax * ec; }
-__host__ __device__ constexpr int pb_cap(int amax, int ec) { return (pb_mmax(amax) + pb_group(ec) - 1) * amax * ec; }
+__host__ __device__ constexpr int pb_cap(int amax, int ec, bool jac = false) { return (pb_mmax(amax) + pb_group(ec, jac) - 1) * amax * ec; }
 
-template <typename R, int CAP>
+// Gradient kernels carry a second table, the product-basis coefficients of the DERIVATIVE series (see the kernel), in
+// the same layout.  Both must fit the kernel parameter space (32 764 bytes): Float64, 16-entry tables and 4 components
+// leave room for 31 of the 32 rows of the second table (single rows, no tail section: the table is simply cut short —
+// gradients of such polynomials with more than 496 coefficients stay on the Clenshaw kernel).
+template <typename R>
+__host__ __device__ constexpr int pb_cap2(int amax, int ec) {
+  const int cap = pb_cap(amax, ec, true);
+  const int room = (32764 - 256 - cap * (int)sizeof(R)) / (int)sizeof(R);
+  return cap <= room ? cap : room / (amax * ec) * (amax * ec);
+}
+template <typename R, int CAP, int CAP2 = 1>
 struct Pb1dArgs {
   Pb1dParams p;
   R D[CAP];
+  R D2[CAP2];
 };
 
 // resident CTAs of 256 threads the register allocation aims at: the short-table (AMAX = 8) scalar Float64 value kernel
@@ -78,9 +90,10 @@ __host__ __device__ constexpr int pb_min_ctas() {
 }
 
 template <typename R, int AMAX, int EC, int P, bool JAC>
-__global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1d_kernel(const __grid_constant__ Pb1dArgs<R, pb_cap(AMAX, EC)> args) {
+__global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1d_kernel(const __grid_constant__ Pb1dArgs<R, pb_cap(AMAX, EC, JAC), JAC ? pb_cap2<R>(AMAX, EC) : 1> args) {
   const Pb1dParams& prm = args.p;
   const R* Ds = args.D;
+  [[maybe_unused]] const R* Ds2 = args.D2;  // the derivative series (JAC)
   const int M = prm.M;
   const R* __restrict__ pts = reinterpret_cast<const R*>(prm.pts);
   R* __restrict__ out_v = reinterpret_cast<R*>(prm.out_v);
@@ -102,7 +115,6 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
     long long idx[P];
     bool live[P];
     R z[P], w[P];
-    [[maybe_unused]] R dw[P];
     long long first_bad = 0x7fffffffffffffffLL;
     R xc[P];
 #pragma unroll
@@ -125,12 +137,15 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
     }
     if (first_bad != 0x7fffffffffffffffLL && prm.bad) atomicMin(prm.bad, first_bad + prm.idx_base);
 
-    // T_lo(z) (and T_lo'(z)) for lo < L = AMAX of every point, in registers; one more step of the same recurrence is
-    // w = T_L(z) (and w' = T_L'(z)), the argument of the outer factor: T_{L hi}(z) = T_hi(w).  (Doubling formulas
-    // T_{2m} = 2 T_m^2 - 1 would cut the dependency depth to log2 L but measured less accurate — they failed the
-    // 16 eps sum|c| check on the order-200 README polynomial — and no faster.)
+    // T_lo(z) for lo < L = AMAX of every point, in registers; one more step of the same recurrence is w = T_L(z), the
+    // argument of the outer factor: T_{L hi}(z) = T_hi(w).  (Doubling formulas T_{2m} = 2 T_m^2 - 1 would cut the
+    // dependency depth to log2 L but measured less accurate — they failed the 16 eps sum|c| check on the order-200 README
+    // polynomial — and no faster.)
+    // The gradient is NOT formed from derivative tables (T_lo', T_hi', w': three operations per recurrence step and three
+    // folds per row): the Chebyshev coefficients of p' are computed at plan time, rewritten in the same product basis
+    // (second table, Ds2), and p'(z) is a second set of inner sums over the SAME T_lo(z), T_hi(w) — n more multiply-adds
+    // and one more fold per row, nothing else.
     R Ta[P][AMAX];
-    [[maybe_unused]] R dTa[JAC ? P : 1][JAC ? AMAX : 1];
     {
       R z2[P];
 #pragma unroll
@@ -138,23 +153,13 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
         z2[p] = rmul(R(2), z[p]);
         Ta[p][0] = R(1);
         Ta[p][1] = z[p];
-        if constexpr (JAC) {
-          dTa[p][0] = R(0);
-          dTa[p][1] = R(1);
-        }
       }
 #pragma unroll
       for (int a = 2; a < AMAX; ++a)
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-          Ta[p][a] = rfma(z2[p], Ta[p][a - 1], -Ta[p][a - 2]);
-          if constexpr (JAC) dTa[p][a] = rsub(rfma(z2[p], dTa[p][a - 1], rmul(R(2), Ta[p][a - 1])), dTa[p][a - 2]);
-        }
+        for (int p = 0; p < P; ++p) Ta[p][a] = rfma(z2[p], Ta[p][a - 1], -Ta[p][a - 2]);
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        w[p] = rfma(z2[p], Ta[p][AMAX - 1], -Ta[p][AMAX - 2]);
-        if constexpr (JAC) dw[p] = rsub(rfma(z2[p], dTa[p][AMAX - 1], rmul(R(2), Ta[p][AMAX - 1])), dTa[p][AMAX - 2]);
-      }
+      for (int p = 0; p < P; ++p) w[p] = rfma(z2[p], Ta[p][AMAX - 1], -Ta[p][AMAX - 2]);
     }
 
     // A loop that never runs (spin = 0).  Without it the tile loop is an INNERMOST loop, and ptxas hoists the ~250
@@ -164,55 +169,40 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
     for (int r = 0; r < prm.spin; ++r) __nanosleep(1);
     // sums over the rows hi, two interleaved accumulators each (even / odd rows) so that consecutive rows do not chain
     R v[2][P][EC];
-    [[maybe_unused]] R dv1[2][JAC ? P : 1][EC], dv2[2][JAC ? P : 1][EC];  // sum_hi T_hi'(w) g_hi and sum_hi T_hi(w) g'_hi
-    R tbm[P], tb[P], z2[P];                                                // T_{hi-1}(w), T_hi(w); z2 = 2 w
-    [[maybe_unused]] R dbm[JAC ? P : 1], db[JAC ? P : 1];
+    [[maybe_unused]] R dv[2][JAC ? P : 1][EC];  // sum_hi T_hi(w) g'_hi, g' from the derivative series
+    R tbm[P], tb[P], z2[P];                      // T_{hi-1}(w), T_hi(w); z2 = 2 w
 #pragma unroll
     for (int p = 0; p < P; ++p) {
 #pragma unroll
       for (int e = 0; e < EC; ++e) {
         v[0][p][e] = v[1][p][e] = R(0);
-        if constexpr (JAC) dv1[0][p][e] = dv1[1][p][e] = dv2[0][p][e] = dv2[1][p][e] = R(0);
+        if constexpr (JAC) dv[0][p][e] = dv[1][p][e] = R(0);
       }
       z2[p] = rmul(R(2), w[p]);
       tbm[p] = w[p];  // T_{-1} = T_1: the recurrence T_{b+1} = 2 w T_b - T_{b-1} then also yields T_1 from T_0
       tb[p] = R(1);
-      if constexpr (JAC) {
-        dbm[p] = R(1);  // T_{-1}' = T_1' = 1: the derivative recurrence T_{b+1}' = 2 T_b + 2 w T_b' - T_{b-1}' then gives
-        db[p] = R(0);   // T_1' = 2 - 1 = 1 from T_0' = 0
-      }
     }
-    // T_hi(w), T_hi'(w) of the next row: taken BEFORE the row's contraction, so the recurrence step overlaps it
-    auto next_tb = [&](R (&t)[P], [[maybe_unused]] R (&d)[JAC ? P : 1]) {
+    // T_hi(w) of the next row: taken BEFORE the row's contraction, so the recurrence step overlaps it
+    auto next_tb = [&](R (&t)[P]) {
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         t[p] = tb[p];
         const R tn = rfma(z2[p], tb[p], -tbm[p]);
-        if constexpr (JAC) {
-          d[p] = db[p];
-          const R dn = rsub(rfma(z2[p], db[p], rmul(R(2), tb[p])), dbm[p]);
-          dbm[p] = db[p];
-          db[p] = dn;
-        }
         tbm[p] = tb[p];
         tb[p] = tn;
       }
     };
     // fold g (and g') of one row into the sums
-    auto fold = [&](int par, const R (&t)[P], [[maybe_unused]] const R (&d)[JAC ? P : 1], const R (&g)[P][EC],
-                    [[maybe_unused]] const R (&gd)[JAC ? P : 1][EC]) {
+    auto fold = [&](int par, const R (&t)[P], const R (&g)[P][EC], [[maybe_unused]] const R (&gd)[JAC ? P : 1][EC]) {
 #pragma unroll
       for (int p = 0; p < P; ++p)
 #pragma unroll
         for (int e = 0; e < EC; ++e) {
           v[par][p][e] = rfma(t[p], g[p][e], v[par][p][e]);
-          if constexpr (JAC) {
-            dv1[par][p][e] = rfma(d[p], g[p][e], dv1[par][p][e]);
-            dv2[par][p][e] = rfma(t[p], gd[p][e], dv2[par][p][e]);
-          }
+          if constexpr (JAC) dv[par][p][e] = rfma(t[p], gd[p][e], dv[par][p][e]);
         }
     };
-    constexpr int BU = pb_group(EC), MAXG = pb_mmax(AMAX) / BU;
+    constexpr int BU = pb_group(EC, JAC), MAXG = pb_mmax(AMAX) / BU;
     const int ngroups = M / BU;
     // the group loop is unrolled completely (with a uniform exit), so that every coefficient is a constant-bank
     // operand at a compile-time offset
@@ -220,20 +210,20 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
     for (int gi = 0; gi < MAXG; ++gi) {
       if (gi >= ngroups) break;
       const R* Dg = Ds + gi * BU * AMAX * EC;
+      [[maybe_unused]] const R* Dg2 = Ds2 + (JAC ? gi * BU * AMAX * EC : 0);
       R g[BU][P][EC];
       [[maybe_unused]] R gd[BU][JAC ? P : 1][EC];
       R tbv[BU][P];
-      [[maybe_unused]] R dbv[BU][JAC ? P : 1];
 #pragma unroll
-      for (int j = 0; j < BU; ++j) next_tb(tbv[j], dbv[j]);
+      for (int j = 0; j < BU; ++j) next_tb(tbv[j]);
 #pragma unroll
       for (int j = 0; j < BU; ++j)
 #pragma unroll
         for (int p = 0; p < P; ++p)
 #pragma unroll
           for (int e = 0; e < EC; ++e) {
-            g[j][p][e] = Dg[j * EC + e];  // lo = 0: T_0(z) = 1, T_0'(z) = 0
-            if constexpr (JAC) gd[j][p][e] = R(0);
+            g[j][p][e] = Dg[j * EC + e];  // lo = 0: T_0(z) = 1
+            if constexpr (JAC) gd[j][p][e] = Dg2[j * EC + e];
           }
 #pragma unroll
       for (int a = 1; a < AMAX; ++a) {
@@ -243,14 +233,16 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
           for (int e = 0; e < EC; ++e) {
             const R d = Dg[(a * BU + j) * EC + e];
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-              g[j][p][e] = rfma(d, Ta[p][a], g[j][p][e]);
-              if constexpr (JAC) gd[j][p][e] = rfma(d, dTa[p][a], gd[j][p][e]);
+            for (int p = 0; p < P; ++p) g[j][p][e] = rfma(d, Ta[p][a], g[j][p][e]);
+            if constexpr (JAC) {
+              const R d2 = Dg2[(a * BU + j) * EC + e];
+#pragma unroll
+              for (int p = 0; p < P; ++p) gd[j][p][e] = rfma(d2, Ta[p][a], gd[j][p][e]);
             }
           }
       }
 #pragma unroll
-      for (int j = 0; j < BU; ++j) fold((gi * BU + j) & 1, tbv[j], dbv[j], g[j], gd[j]);
+      for (int j = 0; j < BU; ++j) fold((gi * BU + j) & 1, tbv[j], g[j], gd[j]);
     }
     // the M % BU remaining rows, one at a time ([t][a][e] at pb_tail_base)
     if constexpr (BU > 1) {
@@ -259,17 +251,17 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
       for (int t = 0; t < BU - 1; ++t) {
         if (t >= ntail) break;
         const R* Dt = Ds + pb_tail_base(AMAX, EC) + t * AMAX * EC;
+        [[maybe_unused]] const R* Dt2 = Ds2 + (JAC ? pb_tail_base(AMAX, EC) + t * AMAX * EC : 0);
         R g[P][EC];
         [[maybe_unused]] R gd[JAC ? P : 1][EC];
         R tbt[P];
-        [[maybe_unused]] R dbt[JAC ? P : 1];
-        next_tb(tbt, dbt);
+        next_tb(tbt);
 #pragma unroll
         for (int p = 0; p < P; ++p)
 #pragma unroll
           for (int e = 0; e < EC; ++e) {
             g[p][e] = Dt[e];
-            if constexpr (JAC) gd[p][e] = R(0);
+            if constexpr (JAC) gd[p][e] = Dt2[e];
           }
         // the LAST row of D is short (its entries lo >= n - L (H - 1) are zero): stop at the next multiple of 4
         const int alim = t == ntail - 1 ? prm.last_len : AMAX;
@@ -280,13 +272,15 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
           for (int e = 0; e < EC; ++e) {
             const R d = Dt[a * EC + e];
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-              g[p][e] = rfma(d, Ta[p][a], g[p][e]);
-              if constexpr (JAC) gd[p][e] = rfma(d, dTa[p][a], gd[p][e]);
+            for (int p = 0; p < P; ++p) g[p][e] = rfma(d, Ta[p][a], g[p][e]);
+            if constexpr (JAC) {
+              const R d2 = Dt2[a * EC + e];
+#pragma unroll
+              for (int p = 0; p < P; ++p) gd[p][e] = rfma(d2, Ta[p][a], gd[p][e]);
             }
           }
         }
-        fold(t & 1, tbt, dbt, g, gd);
+        fold(t & 1, tbt, g, gd);
       }
     }
 
@@ -300,7 +294,7 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
         R Js[EC];
 #pragma unroll
         for (int e = 0; e < EC; ++e)
-          Js[e] = rdiv(rmul(rfma(dw[p], dv1[0][p][e] + dv1[1][p][e], dv2[0][p][e] + dv2[1][p][e]), R(2)), span);  // eval.jl:151
+          Js[e] = rdiv(rmul(dv[0][p][e] + dv[1][p][e], R(2)), span);  // eval.jl:151
         if (prm.mode == 0) {
 #pragma unroll
           for (int e = 0; e < EC; ++e) out_J[idx[p] * prm.J_stride + prm.e0 + e] = Js[e];

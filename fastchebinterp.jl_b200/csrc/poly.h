@@ -45,6 +45,8 @@ struct PbPlan {
   std::atomic<int> state{kPbNone};
   bool checked = false, ok_val = false, ok_jac = false;
   std::vector<unsigned char> h_D;  // product-basis coefficients (kernel layout, eval_pb1d.cuh), passed as kernel parameters
+  std::vector<unsigned char> h_D2;  // the same for the derivative series p' (gradient kernels); empty: gradients not covered
+  std::vector<unsigned char> h_DJ;  // h_D in the gradient kernel's row grouping where that differs (scalar polynomials), else empty
   int AMAX = 0, M = 0;
   double sum_abs[8] = {0}, sum_k2[8] = {0};  // per real component e: sum_k |c_{k,e}|, sum_k |c_{k,e}| k^2 (the tolerances are per component)
   double check_dv = 0, check_dJ = 0;   // self-check result: worst difference over the tolerance

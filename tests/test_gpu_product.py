@@ -125,3 +125,31 @@ def test_product_path_unsupported_shapes(fc):
         p = fc.ChebPoly(rng.uniform(-1, 1, shape), lb, ub)
         with pytest.raises(fc.CudaError):
             p.set_algo(fc.ALGO_PRODUCT)
+
+
+def test_product_gradient_second_table_limit(fc, orc):
+    """Gradient kernels carry a second coefficient table (the derivative series) in the kernel parameters; Float64 with 4
+    real components and more than 496 coefficients does not fit: the forced path refuses gradients (values still work),
+    AUTO keeps such gradients on the bit-exact Clenshaw kernel."""
+    rng = np.random.default_rng(23)
+    lbv, ubv = np.array([-1.0]), np.array([1.5])
+    x = _points(rng, -1.0, 1.5, 20_000, np.float64)
+    for n, covered in ((496, True), (500, False)):
+        xg = orc.chebpoints(n - 1, -1.0, 1.5)
+        c = orc.chebcoefs(np.stack([np.sin((40.0 + 9 * k) * xg + 0.3 * k) * np.exp(-0.2 * xg) for k in range(4)], axis=-1), 1)
+        o = orc.OracleChebPoly(c, lbv, ubv)
+        v0, J0 = o.jacobian(x)
+        p = fc.ChebPoly(c, lbv, ubv)
+        p.set_algo(fc.ALGO_PRODUCT)
+        tol = 16 * np.finfo(float).eps * np.abs(c).sum(axis=0).max()
+        assert np.abs(p(x) - v0).max() <= tol
+        if covered:
+            v, J = fc.chebjacobian(p, x)
+            assert np.abs(v - v0).max() <= tol
+            assert np.abs(J - J0).max() <= jac_tol(c, 1, 0, lbv, ubv)
+        else:
+            with pytest.raises(fc.CudaError):
+                fc.chebjacobian(p, x)
+            p.set_algo(fc.ALGO_AUTO)
+            v, J = fc.chebjacobian(p, x)
+            assert np.array_equal(v, v0) and np.array_equal(J, J0)

@@ -1,4 +1,6 @@
+# product-basis gradient from the derivative series (second table), 2 points per thread for scalar gradients
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_sharded.py tests/test_gpu_threads.py -x -q 2>&1 | tail -4
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_2gpu_val.json 2> gpurun_out/bench_2gpu.err; tail -2 gpurun_out/bench_2gpu.err; cut -c1-220 gpurun_out/r02_bench_2gpu_val.json
+python -m pytest tests/test_gpu_product.py tests/test_gpu_adrules.py tests/test_gpu_jac_parity.py -x -q 2>&1 | tail -5
+python tools/probe_pb1d.py 2>&1 | tail -8 | tee gpurun_out/r02_pb1d_probe_job44.txt
+STRESS_SHARED=0 STRESS_FITS=0 STRESS_ND=0 python tools/stress_r02.py 2>&1 | tail -6 | tee gpurun_out/r02_stress_job44.txt
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
