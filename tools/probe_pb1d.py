@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """1-D evaluation legs only (configs[0] order 200, configs[4] order 64) + the product-basis self-check ratios.
-usage: probe_pb1d.py [once N]   ("once": a single order-N launch, for ncu)"""
+usage: probe_pb1d.py [once N [grad]]   ("once": a single order-N launch, for ncu)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -16,7 +16,7 @@ c64 = np.asarray(fastcheb.chebinterp(np.sin(2.3 * x64 + 0.4), -1.0, 1.0, tol=0.0
 if len(sys.argv) > 2 and sys.argv[1] == "once":
     n = int(sys.argv[2])
     co, lb, ub = (c1, [0.0], [10.0]) if n == 201 else (c64, [-1.0], [1.0])
-    r = B.eval_leg(torch, fastcheb, _capi, 0, (n,), None, False, f64, 1 << 24, False, 1, coefs=co, lb=lb, ub=ub)
+    r = B.eval_leg(torch, fastcheb, _capi, 0, (n,), None, False, f64, 1 << 24, len(sys.argv) > 3 and sys.argv[3] == "grad", 1, coefs=co, lb=lb, ub=ub)
     print(json.dumps(r))
     sys.exit(0)
 reps = 5
