@@ -333,10 +333,34 @@ struct ClenshawCta {
 #pragma unroll
     for (int d = 0; d < N; ++d) sdiv[d].init((R)prm.lb[d], (R)prm.ub[d]);
 
+    // The coordinates of the NEXT tile are loaded before the current one is evaluated: low-order polynomials are
+    // memory-bound (8-100 bytes per point against a few dozen operations), and an unprefetched load at the head of
+    // every tile left a third of the resident warps waiting on it (ncu: long_scoreboard, 48 % of the HBM bandwidth on
+    // a 1-D order-4 polynomial).
+    // (Not for N >= 4: the extra P * N registers spill there, and those nests are never memory-bound.)
+    constexpr bool PF = N <= 3;
+    [[maybe_unused]] R xn[P][N];
+    auto fetch = [&](long long tile) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const long long i = tile * tile_pts + (long long)p * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int d = 0; d < N; ++d) xn[p][d] = (tile < ntiles && i < prm.npts) ? pts[i * N + d] : (R)prm.lb[d];
+      }
+    };
+    if constexpr (PF) fetch(blockIdx.x);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       long long idx[P];
       bool live[P];
       long long first_bad = 0x7fffffffffffffffLL;
+      [[maybe_unused]] R xc[P][N];
+      if constexpr (PF) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+          for (int d = 0; d < N; ++d) xc[p][d] = xn[p][d];
+        fetch(tile + gridDim.x);
+      }
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         idx[p] = tile * tile_pts + (long long)p * blockDim.x + threadIdx.x;
@@ -345,7 +369,11 @@ struct ClenshawCta {
 #pragma unroll
         for (int d = 0; d < N; ++d) {
           const R lb = (R)prm.lb[d], ub = (R)prm.ub[d];
-          const R x = live[p] ? pts[idx[p] * N + d] : lb;
+          R x;
+          if constexpr (PF)
+            x = xc[p][d];
+          else
+            x = live[p] ? pts[idx[p] * N + d] : lb;
           ok = ok && (lb <= x) && (x <= ub);                           // eval.jl:64 (closed box, NaN fails)
           R zz = rsub(sdiv[d].div(rmul(rsub(x, lb), R(2))), R(1));  // eval.jl:65, this operation order (SpanDiv: the IEEE quotient)
           if (!(lb <= x && x <= ub)) zz = R(0);

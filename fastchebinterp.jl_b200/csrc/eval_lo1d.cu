@@ -1,0 +1,111 @@
+// Host side of the low-order 1-D evaluation path (eval_lo1d.cuh): when it applies, coefficient copy, launch.
+#include <algorithm>
+#include <cstring>
+#include "eval_lo1d.cuh"
+#include "poly.h"
+
+namespace fastcheb {
+namespace {
+
+template <typename R, int EC, bool JAC>
+cudaError_t launch(const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t st) {
+  auto kern = eval_lo1d_kernel<R, EC, JAC>;
+  Lo1dArgs<R, EC> args;
+  args.p = prm;
+  memcpy(args.c, h_c, sizeof(args.c));
+  const int threads = 256;
+  int bps = 1;
+  cudaError_t e = cached_occupancy(&bps, reinterpret_cast<const void*>(kern), threads, 0);
+  if (e != cudaSuccess) return e;
+  const long long tile = (long long)threads * lo_pts<R>(EC);
+  const long long ntiles = (prm.npts + tile - 1) / tile;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)sms * std::max(1, bps)));
+  kern<<<grid, threads, 0, st>>>(args);
+  note_launch();
+  return cudaGetLastError();
+}
+
+template <typename R, bool JAC>
+cudaError_t launch_ec(int ec, const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t st) {
+  switch (ec) {
+    case 1: return launch<R, 1, JAC>(prm, h_c, sms, st);
+    case 2: return launch<R, 2, JAC>(prm, h_c, sms, st);
+    case 3: return launch<R, 3, JAC>(prm, h_c, sms, st);
+    case 4: return launch<R, 4, JAC>(prm, h_c, sms, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+// SpanDiv's test (ptx_util.cuh) on the host: the span in the polynomial's real type has a mantissa that is not all ones
+// and an exponent well inside the range — the kernel then divides by the span without a per-point test
+bool span_fast(const fastcheb_poly* p) {
+  if (p->dtype == FASTCHEB_F64) {
+    const volatile double span = p->ub[0] - p->lb[0];
+    const double sp = span;
+    unsigned long long u;
+    memcpy(&u, &sp, sizeof u);
+    const unsigned e = (unsigned)(u >> 52) & 0x7ffu;
+    return (u & 0xfffffffffffffull) != 0xfffffffffffffull && e > 1023u - 500u && e < 1023u + 500u;
+  }
+  const volatile float lbf = (float)p->lb[0], ubf = (float)p->ub[0];
+  const volatile float span = ubf - lbf;
+  const float sp = span;
+  unsigned u;
+  memcpy(&u, &sp, sizeof u);
+  const unsigned e = (u >> 23) & 0xffu;
+  return (u & 0x7fffffu) != 0x7fffffu && e > 127u - 60u && e < 127u + 60u;
+}
+
+}  // namespace
+
+bool lo1d_ok(const fastcheb_poly* p, const void* pts, int64_t npts, const void* out_v, int64_t v_stride, const void* out_J,
+             int64_t J_stride, bool jac, int mode) {
+  static const bool off = getenv("FASTCHEB_LO1D") != nullptr && atoi(getenv("FASTCHEB_LO1D")) == 0;  // experiments
+  if (off || p->algo.load() != FASTCHEB_ALGO_AUTO) return false;  // FASTCHEB_ALGO_CLENSHAW keeps the generic kernel
+  if (p->ndim != 1 || p->dims[0] > kLoMaxN || p->E > 4 || mode != 0 || npts < kLoMinBatch) return false;
+  if (!aligned16(pts) || !aligned16(out_v) || v_stride != p->E) return false;
+  if (jac && (!aligned16(out_J) || J_stride != p->E)) return false;
+  return span_fast(p);
+}
+
+int lo1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_J, bool jac, long long* bad_dev,
+              long long idx_base, cudaStream_t st) {
+  LoPlan& lo = p->lo;
+  const size_t rs = real_size(p->dtype);
+  const int n = (int)p->dims[0], E = p->E;
+  if (!lo.ready.load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lk(lo.mu);
+    if (!lo.ready.load(std::memory_order_relaxed)) {
+      DeviceGuard dg(p->device);
+      std::vector<unsigned char> h((size_t)kLoMaxN * E * rs, 0);  // zero above c_{n-1}: exact no-op recurrence steps
+      cudaStream_t s2 = cudaStreamPerThread;
+      FC_CUDA(cudaMemcpyAsync(h.data(), p->d_coefs, (size_t)n * E * rs, cudaMemcpyDeviceToHost, s2));
+      FC_CUDA(cudaStreamSynchronize(s2));
+      lo.h_c.swap(h);
+      lo.ngroups = (n - 1 + 3) / 4;
+      lo.ready.store(1, std::memory_order_release);
+    }
+  }
+  Lo1dParams prm;
+  memset(&prm, 0, sizeof prm);
+  prm.pts = pts;
+  prm.out_v = out_v;
+  prm.out_J = out_J;
+  prm.bad = bad_dev;
+  prm.npts = npts;
+  prm.idx_base = idx_base;
+  prm.ngroups = lo.ngroups;
+  prm.lb = p->lb[0];
+  prm.ub = p->ub[0];
+  const int sms = p->di->sms;
+  const cudaError_t e =
+      p->dtype == FASTCHEB_F64
+          ? (jac ? launch_ec<double, true>(E, prm, lo.h_c.data(), sms, st) : launch_ec<double, false>(E, prm, lo.h_c.data(), sms, st))
+          : (jac ? launch_ec<float, true>(E, prm, lo.h_c.data(), sms, st) : launch_ec<float, false>(E, prm, lo.h_c.data(), sms, st));
+  if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "low-order 1-D kernel launch failed: %s", cudaGetErrorString(e));
+  return FASTCHEB_OK;
+}
+
+}  // namespace fastcheb

@@ -52,6 +52,14 @@ struct PbPlan {
   double check_dv = 0, check_dJ = 0;   // self-check result: worst difference over the tolerance
 };
 
+// low-order 1-D path (eval_lo1d.cuh): host copy of the zero-padded coefficients, made on the first large batch
+struct LoPlan {
+  std::mutex mu;
+  std::atomic<int> ready{0};
+  std::vector<unsigned char> h_c;  // [17][E] reals
+  int ngroups = 0;
+};
+
 }  // namespace fastcheb
 
 struct fastcheb_poly {
@@ -68,6 +76,7 @@ struct fastcheb_poly {
   fastcheb::DmmaPlan dmma;
   std::atomic<int> algo{FASTCHEB_ALGO_AUTO};
   mutable fastcheb::PbPlan pb;
+  mutable fastcheb::LoPlan lo;
   bool eval_ok = true;  // false: N-d polynomial whose dimension-1 line does not fit shared memory (plan_clenshaw)
 };
 
@@ -85,6 +94,12 @@ bool pb1d_shape_ok(const fastcheb_poly* p);
 int pb1d_plan(const fastcheb_poly* p, bool forced);
 int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
               int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode, const void* tan);
+// low-order 1-D path (eval_lo1d.cu): bit-identical to the Clenshaw kernel, vector loads / stores; lo1d_ok: shape, batch
+// size, alignment and strides allow it
+bool lo1d_ok(const fastcheb_poly* p, const void* pts, int64_t npts, const void* out_v, int64_t v_stride, const void* out_J,
+             int64_t J_stride, bool jac, int mode);
+int lo1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_J, bool jac, long long* bad_dev,
+              long long idx_base, cudaStream_t st);
 // build the handle from coefficients already on the device (Julia layout); takes no ownership of d_src
 int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,
                        const void* d_src, const double* lb, const double* ub, int device, cudaStream_t st);

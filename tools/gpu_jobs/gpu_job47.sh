@@ -1,3 +1,4 @@
-for b in 2 3 4 6; do echo "65x65 BLOCK=$b"; for s in 65x65-float64 65x65-float32; do FASTCHEB_FITND_BLOCK=$b FIT_ONLY=$s python tools/probe_fit_nd.py 2>&1 | grep "\"$s" | cut -c1-50,95-175; done; done
-for b in 6 8 12 16 24; do echo "33x33 BLOCK=$b"; for s in 33x33-float64 33x33-float32; do FASTCHEB_FITND_BLOCK=$b FIT_ONLY=$s python tools/probe_fit_nd.py 2>&1 | grep "\"$s" | cut -c1-50,95-175; done; done
-for b in 2 3 4; do echo "17^3 BLOCK=$b"; FASTCHEB_FITND_BLOCK=$b FIT_ONLY=17x17x17-float64 python tools/probe_fit_nd.py 2>&1 | grep "\"17x17x17-" | cut -c1-50,95-175; done
+# randomized stress with fresh seeds after the gradient-kernel change (product basis a: every n; b-e: fits, shared points, N-d)
+mkdir -p gpurun_out
+for s in 11 12 13; do echo "seed $s"; STRESS_SEED=$s timeout 600 python tools/stress_r02.py 2>&1 | tail -7; done | tee gpurun_out/r02_stress_job47.txt
+for o in 101 202; do echo "fuzz offset $o"; FASTCHEB_FUZZ_OFFSET=$o timeout 600 python -m pytest tests/test_gpu_fuzz.py -x -q 2>&1 | tail -2; done | tee -a gpurun_out/r02_stress_job47.txt
