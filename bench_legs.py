@@ -215,6 +215,14 @@ def run_all(device: int = 0, quick: bool = False):
         if hasattr(_capi.lib(), "fastcheb_eval_many_shared"):
             guard(f"cfg4_eval_many_shared_points_{nm}_val", lambda: eval_many_leg(torch, _capi, device, dt, False, reps, shared=True))
     guard("cfg4_eval_many_f64_grad", lambda: eval_many_leg(torch, _capi, device, f64, True, reps))
+    # low-order, memory-bound evaluations (north_star: "achieved HBM GB/s ... for the fit and the low-order, memory-bound
+    # evaluations"): a point's coordinates and results cost more than its arithmetic (eval_lo1d.cuh / eval_lond.cuh)
+    guard("loworder_eval1d_order4_f64_val", lambda: eval_leg(torch, fastcheb, _capi, device, (5,), None, False, f64, 1 << 26, False, reps))
+    guard("loworder_eval1d_order4_f32_val", lambda: eval_leg(torch, fastcheb, _capi, device, (5,), None, False, f32, 1 << 27, False, reps))
+    guard("loworder_eval1d_order8_f64_val", lambda: eval_leg(torch, fastcheb, _capi, device, (9,), None, False, f64, 1 << 26, False, reps))
+    guard("loworder_eval1d_order8_f64_grad", lambda: eval_leg(torch, fastcheb, _capi, device, (9,), None, False, f64, 1 << 26, True, reps))
+    guard("loworder_eval2d_order4_f64_val", lambda: eval_leg(torch, fastcheb, _capi, device, (5, 5), None, False, f64, 1 << 25, False, reps))
+    guard("loworder_eval2d_order4_f64_grad", lambda: eval_leg(torch, fastcheb, _capi, device, (5, 5), None, False, f64, 1 << 25, True, reps))
     freps = 10 if quick else 40
     for dt, nm in ((f64, "f64"), (f32, "f32")):
         guard(f"cfg4_fit1d_order64_{nm}_1e5", lambda: fit_leg(torch, _capi, device, (65,), 100_000, dt, freps))

@@ -38,26 +38,6 @@ cudaError_t launch_ec(int ec, const Lo1dParams& prm, const void* h_c, int sms, c
 
 bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-// SpanDiv's test (ptx_util.cuh) on the host: the span in the polynomial's real type has a mantissa that is not all ones
-// and an exponent well inside the range — the kernel then divides by the span without a per-point test
-bool span_fast(const fastcheb_poly* p) {
-  if (p->dtype == FASTCHEB_F64) {
-    const volatile double span = p->ub[0] - p->lb[0];
-    const double sp = span;
-    unsigned long long u;
-    memcpy(&u, &sp, sizeof u);
-    const unsigned e = (unsigned)(u >> 52) & 0x7ffu;
-    return (u & 0xfffffffffffffull) != 0xfffffffffffffull && e > 1023u - 500u && e < 1023u + 500u;
-  }
-  const volatile float lbf = (float)p->lb[0], ubf = (float)p->ub[0];
-  const volatile float span = ubf - lbf;
-  const float sp = span;
-  unsigned u;
-  memcpy(&u, &sp, sizeof u);
-  const unsigned e = (u >> 23) & 0xffu;
-  return (u & 0x7fffffu) != 0x7fffffu && e > 127u - 60u && e < 127u + 60u;
-}
-
 }  // namespace
 
 bool lo1d_ok(const fastcheb_poly* p, const void* pts, int64_t npts, const void* out_v, int64_t v_stride, const void* out_J,
@@ -67,7 +47,7 @@ bool lo1d_ok(const fastcheb_poly* p, const void* pts, int64_t npts, const void* 
   if (p->ndim != 1 || p->dims[0] > kLoMaxN || p->E > 4 || mode != 0 || npts < kLoMinBatch) return false;
   if (!aligned16(pts) || !aligned16(out_v) || v_stride != p->E) return false;
   if (jac && (!aligned16(out_J) || J_stride != p->E)) return false;
-  return span_fast(p);
+  return span_fast(p, 0);
 }
 
 int lo1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_J, bool jac, long long* bad_dev,

@@ -221,6 +221,8 @@ int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out
     return pb1d_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
   if (use_dmma(p, jac))
     return dmma_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
+  if (lond_ok(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, mode))
+    return lond_eval(p, pts, npts, out_v, out_J, jac, bad_dev, idx_base, st);
   return eval_clenshaw(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
 }
 

@@ -56,7 +56,7 @@ struct PbPlan {
 struct LoPlan {
   std::mutex mu;
   std::atomic<int> ready{0};
-  std::vector<unsigned char> h_c;  // [17][E] reals
+  std::vector<unsigned char> h_c;  // 1-D: [17][E] reals; N-d: the tensor with dimension 1 zero-padded to 1 + 4 ngroups
   int ngroups = 0;
 };
 
@@ -99,6 +99,13 @@ int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
 bool lo1d_ok(const fastcheb_poly* p, const void* pts, int64_t npts, const void* out_v, int64_t v_stride, const void* out_J,
              int64_t J_stride, bool jac, int mode);
 int lo1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_J, bool jac, long long* bad_dev,
+              long long idx_base, cudaStream_t st);
+// low-order N-d path (eval_lond.cu), 2 <= N <= 4: the same for small tensor-product nests (taken where AUTO would use the
+// generic Clenshaw kernel)
+bool span_fast(const fastcheb_poly* p, int d);
+bool lond_ok(const fastcheb_poly* p, const void* pts, int64_t npts, const void* out_v, int64_t v_stride, const void* out_J,
+             int64_t J_stride, bool jac, int mode);
+int lond_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, void* out_J, bool jac, long long* bad_dev,
               long long idx_base, cudaStream_t st);
 // build the handle from coefficients already on the device (Julia layout); takes no ownership of d_src
 int create_from_device(fastcheb_poly** out, int ndim, const int64_t* dims, int dtype, int is_complex, int ncomp,

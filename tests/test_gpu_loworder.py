@@ -95,3 +95,58 @@ def test_low_order_division_corner_cases(fc, orc, dt):
             v0, J0 = orc.OracleChebPoly(c, lb, ub).jacobian(x)
         v, J = fc.chebjacobian(fc.ChebPoly(c, lb, ub), x)
         assert np.array_equal(v, v0, equal_nan=True) and np.array_equal(J, J0, equal_nan=True), (lb0, ub0, scale)
+
+
+ND_SHAPES = [(5, 5), (2, 7), (9, 1), (1, 6), (9, 9), (4, 4, 4), (3, 1, 5), (2, 2, 2), (5, 5, 5), (3, 3, 3, 3), (2, 4, 3, 2), (13, 3)]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("K,cplx", [(None, False), (2, False), (3, False), (None, True), (4, False)],
+                         ids=["scalar", "K2", "K3", "complex", "K4"])
+def test_low_order_nd_bit_identical(fc, orc, dt, K, cplx):
+    """N-d low-order path (eval_lond.cuh): bit-identical to the oracle and the generic kernel, ragged tails, face points,
+    size-1 dimensions; shapes the path does not take (register budget, coefficient capacity) run the same assertions."""
+    rng = np.random.default_rng(43)
+    for shape in ND_SHAPES:
+        N = len(shape)
+        full = shape + ((K,) if K else ())
+        c = rng.uniform(-1, 1, full)
+        if cplx:
+            c = (c + 1j * rng.uniform(-1, 1, full)).astype(np.complex128 if dt == np.float64 else np.complex64)
+        else:
+            c = c.astype(dt)
+        lb = rng.uniform(-2, -0.5, N).astype(dt)
+        ub = rng.uniform(0.5, 3, N).astype(dt)
+        npts = int(rng.integers(4096, 7000)) | 1
+        x = (lb + (ub - lb) * rng.random((npts, N))).astype(dt)
+        x[0], x[1], x[-1] = lb, ub, ub
+        x[2, 0] = lb[0]
+        x = np.clip(x, lb, ub)
+        o = orc.OracleChebPoly(c, lb, ub)
+        v0, J0 = o.jacobian(x)
+        p = fc.ChebPoly(c, lb, ub)
+        v, J = fc.chebjacobian(p, x)
+        assert np.array_equal(p(x), v0), (shape, "value")
+        assert np.array_equal(v, v0) and np.array_equal(J, J0), (shape, "jacobian")
+        p.set_algo(fc.ALGO_CLENSHAW, dt)
+        v2, J2 = fc.chebjacobian(p, x)
+        assert np.array_equal(v2, v0) and np.array_equal(J2, J0)
+
+
+def test_low_order_nd_domain_errors(fc):
+    rng = np.random.default_rng(6)
+    p = fc.ChebPoly(rng.uniform(-1, 1, (4, 5, 3)), [0.0, 0.0, -1.0], [1.0, 2.0, 1.0])
+    x = rng.random((30_001, 3)) * [1, 2, 2] - [0, 0, 1]
+    good = p(x)
+    for bad_at, d, val in ((0, 2, -1.0000001), (4099, 1, 2.0 + 1e-9), (30_000, 0, np.nan), (12_347, 1, -0.5)):
+        bad = x.copy()
+        bad[bad_at, d] = val
+        if bad_at + 3 < len(bad):
+            bad[bad_at + 3, 0] = 9.0      # a later offender: the FIRST index is reported
+        with pytest.raises(fc.ArgumentError) as ei:
+            p(bad)
+        assert ei.value.index == bad_at
+        with pytest.raises(fc.ArgumentError) as ei:
+            fc.chebgradient(p, bad)
+        assert ei.value.index == bad_at
+    assert np.array_equal(p(x), good)

@@ -24,6 +24,14 @@ SHAPES = [
     ("3d_order3_K3_f64_jac", (4, 4, 4), 3, False, f64, 1 << 24, True),
     ("3d_order2_complex_f64_val", (3, 3, 3), None, True, f64, 1 << 24, False),
     ("4d_order2_f32_val", (3, 3, 3, 3), None, False, f32, 1 << 25, False),
+    ("2d_order8_f64_val", (9, 9), None, False, f64, 1 << 25, False),
+    ("2d_order8_f64_grad", (9, 9), None, False, f64, 1 << 25, True),
+    ("2d_order4_K3_f64_jac", (5, 5), 3, False, f64, 1 << 24, True),
+    ("3d_order4_f64_val", (5, 5, 5), None, False, f64, 1 << 24, False),
+    ("3d_order4_f64_grad", (5, 5, 5), None, False, f64, 1 << 24, True),
+    ("3d_order3_K2_f32_jac", (4, 4, 4), 2, False, f32, 1 << 24, True),
+    ("4d_order2_f64_grad", (3, 3, 3, 3), None, False, f64, 1 << 24, True),
+    ("4d_order3_K2_f64_val", (4, 4, 4, 4), 2, False, f64, 1 << 23, False),
 ]
 LEGS = {s[0]: s for s in SHAPES}
 
