@@ -7,10 +7,11 @@
 namespace fastcheb {
 namespace {
 
-template <typename R, int EC, bool JAC>
-cudaError_t launch(const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t st) {
-  auto kern = eval_lo1d_kernel<R, EC, JAC>;
-  Lo1dArgs<R, EC> args;
+template <typename R, int EC, bool JAC, int NCAP>
+cudaError_t launch_cap(const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t st) {
+  auto kern = eval_lo1d_kernel<R, EC, JAC, NCAP>;
+  Lo1dArgs<R, EC, NCAP> args;
+  static_assert(sizeof(args) <= 32764, "kernel parameter space");
   args.p = prm;
   memcpy(args.c, h_c, sizeof(args.c));
   const int threads = 256;
@@ -25,13 +26,23 @@ cudaError_t launch(const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t
   return cudaGetLastError();
 }
 
+template <typename R, int EC, bool JAC>
+cudaError_t launch(int cap, const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t st) {
+  switch (cap) {
+    case 17: return launch_cap<R, EC, JAC, 17>(prm, h_c, sms, st);
+    case 129: return launch_cap<R, EC, JAC, 129>(prm, h_c, sms, st);
+    case 513: return launch_cap<R, EC, JAC, 513>(prm, h_c, sms, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
 template <typename R, bool JAC>
-cudaError_t launch_ec(int ec, const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t st) {
+cudaError_t launch_ec(int ec, int cap, const Lo1dParams& prm, const void* h_c, int sms, cudaStream_t st) {
   switch (ec) {
-    case 1: return launch<R, 1, JAC>(prm, h_c, sms, st);
-    case 2: return launch<R, 2, JAC>(prm, h_c, sms, st);
-    case 3: return launch<R, 3, JAC>(prm, h_c, sms, st);
-    case 4: return launch<R, 4, JAC>(prm, h_c, sms, st);
+    case 1: return launch<R, 1, JAC>(cap, prm, h_c, sms, st);
+    case 2: return launch<R, 2, JAC>(cap, prm, h_c, sms, st);
+    case 3: return launch<R, 3, JAC>(cap, prm, h_c, sms, st);
+    case 4: return launch<R, 4, JAC>(cap, prm, h_c, sms, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -44,7 +55,7 @@ bool lo1d_ok(const fastcheb_poly* p, const void* pts, int64_t npts, const void* 
              int64_t J_stride, bool jac, int mode) {
   static const bool off = getenv("FASTCHEB_LO1D") != nullptr && atoi(getenv("FASTCHEB_LO1D")) == 0;  // experiments
   if (off || p->algo.load() != FASTCHEB_ALGO_AUTO) return false;  // FASTCHEB_ALGO_CLENSHAW keeps the generic kernel
-  if (p->ndim != 1 || p->dims[0] > kLoMaxN || p->E > 4 || mode != 0 || npts < kLoMinBatch) return false;
+  if (p->ndim != 1 || p->dims[0] > kLoMaxNAny || p->E > 4 || mode != 0 || npts < kLoMinBatch) return false;
   if (!aligned16(pts) || !aligned16(out_v) || v_stride != p->E) return false;
   if (jac && (!aligned16(out_J) || J_stride != p->E)) return false;
   return span_fast(p, 0);
@@ -59,7 +70,7 @@ int lo1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
     std::lock_guard<std::mutex> lk(lo.mu);
     if (!lo.ready.load(std::memory_order_relaxed)) {
       DeviceGuard dg(p->device);
-      std::vector<unsigned char> h((size_t)kLoMaxN * E * rs, 0);  // zero above c_{n-1}: exact no-op recurrence steps
+      std::vector<unsigned char> h((size_t)lo_cap(n) * E * rs, 0);  // zero above c_{n-1}: exact no-op recurrence steps
       cudaStream_t s2 = cudaStreamPerThread;
       FC_CUDA(cudaMemcpyAsync(h.data(), p->d_coefs, (size_t)n * E * rs, cudaMemcpyDeviceToHost, s2));
       FC_CUDA(cudaStreamSynchronize(s2));
@@ -82,8 +93,8 @@ int lo1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
   const int sms = p->di->sms;
   const cudaError_t e =
       p->dtype == FASTCHEB_F64
-          ? (jac ? launch_ec<double, true>(E, prm, lo.h_c.data(), sms, st) : launch_ec<double, false>(E, prm, lo.h_c.data(), sms, st))
-          : (jac ? launch_ec<float, true>(E, prm, lo.h_c.data(), sms, st) : launch_ec<float, false>(E, prm, lo.h_c.data(), sms, st));
+          ? (jac ? launch_ec<double, true>(E, lo_cap(n), prm, lo.h_c.data(), sms, st) : launch_ec<double, false>(E, lo_cap(n), prm, lo.h_c.data(), sms, st))
+          : (jac ? launch_ec<float, true>(E, lo_cap(n), prm, lo.h_c.data(), sms, st) : launch_ec<float, false>(E, lo_cap(n), prm, lo.h_c.data(), sms, st));
   if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "low-order 1-D kernel launch failed: %s", cudaGetErrorString(e));
   return FASTCHEB_OK;
 }

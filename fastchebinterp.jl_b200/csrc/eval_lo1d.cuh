@@ -20,7 +20,13 @@
 
 namespace fastcheb {
 
-constexpr int kLoMaxN = 17;      // coefficients c_0 .. c_16
+constexpr int kLoMaxN = 17;      // coefficients c_0 .. c_16: the memory-bound range (table capacity of the first instantiation)
+// Longer series are FP64-bound, but the same kernel is also the faster Clenshaw kernel for them (4 independent
+// recurrences per thread fed from uniform operands: FP64 pipe ~90 % busy = 45 % of peak against the generic kernel's ~30 %):
+// AUTO uses it for every 1-D polynomial up to 513 coefficients that the product-basis path does not take (n < 40, or
+// rejected by its self-check, e.g. dense random coefficients).  Table capacities 17 / 129 / 513 keep the parameter copy small.
+constexpr int kLoMaxNAny = 513;
+__host__ __device__ constexpr int lo_cap(int n) { return n <= 17 ? 17 : (n <= 129 ? 129 : 513); }
 constexpr int kLoMinBatch = 4096;  // smaller batches are launch-latency-bound: the generic kernel serves them
 
 struct Lo1dParams {
@@ -33,10 +39,10 @@ struct Lo1dParams {
   double lb, ub;
 };
 
-template <typename R, int EC>
+template <typename R, int EC, int NCAP>
 struct Lo1dArgs {
   Lo1dParams p;
-  R c[kLoMaxN * EC];  // [j][e], zero above j = n - 1
+  R c[NCAP * EC];  // [j][e], zero above j = n - 1
 };
 
 // points per thread: 32 bytes of coordinates for scalar polynomials, 16 for vector-valued ones
@@ -107,8 +113,8 @@ __device__ __forceinline__ void lo_store(R* __restrict__ ptr, bool keep, const b
   }
 }
 
-template <typename R, int EC, bool JAC>
-__global__ void __launch_bounds__(256) eval_lo1d_kernel(const __grid_constant__ Lo1dArgs<R, EC> args) {
+template <typename R, int EC, bool JAC, int NCAP>
+__global__ void __launch_bounds__(256) eval_lo1d_kernel(const __grid_constant__ Lo1dArgs<R, EC, NCAP> args) {
   constexpr int P = lo_pts<R>(EC);
   const Lo1dParams& prm = args.p;
   const R* __restrict__ pts = reinterpret_cast<const R*>(prm.pts);

@@ -215,10 +215,10 @@ int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out
                 int64_t J_stride, bool jac, long long* bad_dev, long long idx_base, cudaStream_t st, int mode,
                 const void* tan) {
   if (npts == 0) return FASTCHEB_OK;
-  if (lo1d_ok(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, mode))
-    return lo1d_eval(p, pts, npts, out_v, out_J, jac, bad_dev, idx_base, st);
   if (use_pb(p, jac, npts))
     return pb1d_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
+  if (lo1d_ok(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, mode))  // n < 40, or not taken by the product basis
+    return lo1d_eval(p, pts, npts, out_v, out_J, jac, bad_dev, idx_base, st);
   if (use_dmma(p, jac))
     return dmma_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
   if (lond_ok(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, mode))

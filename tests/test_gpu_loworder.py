@@ -150,3 +150,24 @@ def test_low_order_nd_domain_errors(fc):
             fc.chebgradient(p, bad)
         assert ei.value.index == bad_at
     assert np.array_equal(p(x), good)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("K", [None, 3], ids=["scalar", "K3"])
+def test_lo1d_is_the_clenshaw_kernel_for_longer_series(fc, orc, dt, K):
+    """Up to 513 coefficients the same kernel is AUTO's Clenshaw kernel for every 1-D polynomial the product-basis path does
+    not take (n < 40, or rejected by its self-check — dense random coefficients are): bit-identical to the oracle, table
+    capacities 17 / 129 / 513 and the generic kernel beyond."""
+    rng = np.random.default_rng(47)
+    for n in (18, 25, 39, 40, 64, 65, 128, 129, 130, 257, 512, 513, 514, 700):
+        c = rng.uniform(-1, 1, (n,) + ((K,) if K else ())).astype(dt)
+        lb, ub = np.array([-1.5], dtype=dt), np.array([0.5], dtype=dt)
+        npts = 8192 + 3
+        x = np.clip((lb[0] + (ub[0] - lb[0]) * rng.random(npts)).astype(dt), lb[0], ub[0])
+        x[0], x[-1] = lb[0], ub[0]
+        p = fc.ChebPoly(c, lb, ub)
+        v, J = fc.chebjacobian(p, x)
+        assert p.get_algo(False, dt) != fc.ALGO_PRODUCT and p.get_algo(True, dt) != fc.ALGO_PRODUCT, n
+        v0, J0 = orc.OracleChebPoly(c, lb, ub).jacobian(x)
+        assert np.array_equal(p(x), v0), (n, "value")
+        assert np.array_equal(v, v0) and np.array_equal(J, J0), (n, "jacobian")

@@ -32,6 +32,14 @@ SHAPES = [
     ("3d_order3_K2_f32_jac", (4, 4, 4), 2, False, f32, 1 << 24, True),
     ("4d_order2_f64_grad", (3, 3, 3, 3), None, False, f64, 1 << 24, True),
     ("4d_order3_K2_f64_val", (4, 4, 4, 4), 2, False, f64, 1 << 23, False),
+    # longer dense-random 1-D series (the product basis rejects them): FP64-bound, the same kernel as the Clenshaw kernel
+    ("1d_order24_f64_val", (25,), None, False, f64, 1 << 25, False),
+    ("1d_order64_dense_f64_val", (65,), None, False, f64, 1 << 25, False),
+    ("1d_order64_dense_f64_grad", (65,), None, False, f64, 1 << 25, True),
+    ("1d_order64_dense_f32_val", (65,), None, False, f32, 1 << 25, False),
+    ("1d_order200_dense_f64_val", (201,), None, False, f64, 1 << 24, False),
+    ("1d_order200_dense_K3_f64_val", (201,), 3, False, f64, 1 << 23, False),
+    ("1d_order512_dense_f64_val", (513,), None, False, f64, 1 << 23, False),
 ]
 LEGS = {s[0]: s for s in SHAPES}
 
