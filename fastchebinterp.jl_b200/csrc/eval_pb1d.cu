@@ -81,8 +81,10 @@ cudaError_t launch_any(int amax, int ec, bool jac, const Pb1dParams& prm, const 
 
 }  // namespace
 
+// (the kernel divides by the span with the reciprocal + exact-remainder correction unconditionally: spans that fail
+// SpanDiv's applicability test — mantissa all ones, extreme exponents — stay on the Clenshaw kernels)
 bool pb1d_shape_ok(const fastcheb_poly* p) {
-  return p->ndim == 1 && p->dims[0] >= kPbMinN && p->dims[0] <= kPbMaxN && p->E <= 4;
+  return p->ndim == 1 && p->dims[0] >= kPbMinN && p->dims[0] <= kPbMaxN && p->E <= 4 && span_fast(p, 0);
 }
 
 int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v, int64_t v_stride, void* out_J,
@@ -109,6 +111,9 @@ int pb1d_eval(const fastcheb_poly* p, const void* pts, int64_t npts, void* out_v
   prm.ub = p->ub[0];
   prm.tan = tan;
   prm.mode = mode;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  prm.vec = (al16(pts) ? 1 : 0) |
+            ((mode == 0 && v_stride == p->E && al16(out_v) && (!jac || (J_stride == p->E && al16(out_J)))) ? 2 : 0);
   const std::vector<unsigned char>& hD = (jac && !pb.h_DJ.empty()) ? pb.h_DJ : pb.h_D;
   const size_t d_count = hD.size() / real_size(p->dtype);
   const cudaError_t e = p->dtype == FASTCHEB_F64

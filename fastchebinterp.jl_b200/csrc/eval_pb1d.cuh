@@ -50,6 +50,7 @@ struct Pb1dParams {
   int mode;
   int spin;      // always 0 (see the kernel)
   int last_len;  // number of non-zero entries of the last row of D: n - L (H - 1)
+  int vec;       // bit 0: pts is 16-byte aligned (vector loads); bit 1: mode 0, contiguous 16-byte-aligned results (vector stores)
 };
 
 // The coefficients travel IN THE KERNEL PARAMETERS (constant bank 0; up to 18 KB of the 32 KB parameter space): every
@@ -81,6 +82,48 @@ struct Pb1dArgs {
   R D2[CAP2];
 };
 
+// K contiguous reals as 16-byte (or, when K reals are only 8 bytes more, 8-byte) vectors; `ptr` aligned accordingly
+template <typename R, int K>
+__device__ __forceinline__ void pb_vec_load(const R* __restrict__ ptr, R (&x)[K]) {
+  constexpr int B = K * (int)sizeof(R);
+  if constexpr (B % 16 == 0) {
+    union { uint4 v[B / 16]; R r[K]; } u;
+#pragma unroll
+    for (int i = 0; i < B / 16; ++i) u.v[i] = reinterpret_cast<const uint4*>(ptr)[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = u.r[k];
+  } else if constexpr (B % 8 == 0) {
+    union { uint2 v[B / 8]; R r[K]; } u;
+#pragma unroll
+    for (int i = 0; i < B / 8; ++i) u.v[i] = reinterpret_cast<const uint2*>(ptr)[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = u.r[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = ptr[k];
+  }
+}
+template <typename R, int K>
+__device__ __forceinline__ void pb_vec_store(R* __restrict__ ptr, const R (&x)[K]) {
+  constexpr int B = K * (int)sizeof(R);
+  if constexpr (B % 16 == 0) {
+    union { uint4 v[B / 16]; R r[K]; } u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) u.r[k] = x[k];
+#pragma unroll
+    for (int i = 0; i < B / 16; ++i) reinterpret_cast<uint4*>(ptr)[i] = u.v[i];
+  } else if constexpr (B % 8 == 0) {
+    union { uint2 v[B / 8]; R r[K]; } u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) u.r[k] = x[k];
+#pragma unroll
+    for (int i = 0; i < B / 8; ++i) reinterpret_cast<uint2*>(ptr)[i] = u.v[i];
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ptr[k] = x[k];
+  }
+}
+
 // resident CTAs of 256 threads the register allocation aims at: the short-table (AMAX = 8) scalar Float64 value kernel
 // needs 82 registers, which the allocation granularity turns into 2 CTAs per SM — capped at 80 it runs 3 (24 warps:
 // the order-64 shapes are latency-bound, profiles/r02_pb1d_order64_ncu_summary.txt)
@@ -99,43 +142,69 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
   R* __restrict__ out_v = reinterpret_cast<R*>(prm.out_v);
   R* __restrict__ out_J = reinterpret_cast<R*>(prm.out_J);
   const R lb = (R)prm.lb, ub = (R)prm.ub;
-  SpanDiv<R> sdiv;
-  sdiv.init(lb, ub);
+  // The host takes this path only when the span passes SpanDiv's test (span_fast): the quotient by the span is the
+  // reciprocal + exact-remainder correction (still the IEEE quotient) with no per-point test and no division subroutine
+  const R span = rsub(ub, lb), rcp = rdiv(R(1), span);
+  auto div_span = [&](R a) {
+    const R q = rmul(a, rcp);
+    return rfma(rfma(-span, q, a), rcp, q);
+  };
+  // derivative scale 2/(ub-lb) (eval.jl:151), any numerator: the same correction while nothing can underflow or overflow
+  // on the way (numerator exponent within +-400, Float32 +-40), the true division otherwise
+  [[maybe_unused]] auto div_any = [&](R a) {
+    bool safe;
+    if constexpr (sizeof(R) == 8) {
+      const unsigned e = ((unsigned)(__double_as_longlong((double)a) >> 52)) & 0x7ffu;
+      safe = e > 1023u - 400u && e < 1023u + 400u;
+    } else {
+      const unsigned e = (__float_as_uint((float)a) >> 23) & 0xffu;
+      safe = e > 127u - 40u && e < 127u + 40u;
+    }
+    return safe ? div_span(a) : rdiv(a, span);
+  };
+  // A thread owns P CONSECUTIVE points (as in eval_lo1d.cuh): with 16-byte-aligned contiguous buffers (prm.vec) the
+  // coordinates arrive and the results leave as 8- or 16-byte vectors, with one index computation per thread — at order 64
+  // the per-point work around the series (index arithmetic, domain test, division test, scalar loads and stores) was as
+  // large as the series itself.
   const long long tile_pts = (long long)blockDim.x * P;
   const long long ntiles = (prm.npts + tile_pts - 1) / tile_pts;
+  const long long toff = (long long)threadIdx.x * P;
+  const bool vec_in = (prm.vec & 1) != 0, vec_out = (prm.vec & 2) != 0;
+  auto count = [&](long long i0) {
+    const long long left = prm.npts - i0;
+    return left >= P ? P : (left > 0 ? (int)left : 0);
+  };
+  auto fetch = [&](long long tile, R (&x)[P]) {
+    const long long i0 = tile * tile_pts + toff;
+    const int c = count(i0);
+    if (vec_in && c == P) {
+      pb_vec_load<R, P>(pts + i0, x);
+    } else {
+#pragma unroll
+      for (int p = 0; p < P; ++p) x[p] = p < c ? pts[i0 + p] : lb;
+    }
+  };
   // the coordinates of the next tile are loaded while the current one is computed (a tile is ~1000 pipe cycles per
   // warp; an unprefetched global load at its head leaves the FP64 pipe idle for a quarter of the time)
   R xn[P];
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    const long long i = (long long)blockIdx.x * tile_pts + (long long)p * blockDim.x + threadIdx.x;
-    xn[p] = i < prm.npts ? pts[i] : lb;
-  }
+  fetch(blockIdx.x, xn);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    long long idx[P];
+    const long long i0 = tile * tile_pts + toff;
+    const int cnt = count(i0);
     bool live[P];
     R z[P], w[P];
-    long long first_bad = 0x7fffffffffffffffLL;
-    R xc[P];
+    unsigned badmask = 0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      xc[p] = xn[p];
-      const long long i = (tile + gridDim.x) * tile_pts + (long long)p * blockDim.x + threadIdx.x;
-      xn[p] = i < prm.npts ? pts[i] : lb;
+      const R x = xn[p];
+      const bool ok = (lb <= x) && (x <= ub);                            // eval.jl:64 (closed box, NaN fails)
+      z[p] = ok ? rsub(div_span(rmul(rsub(x, lb), R(2))), R(1)) : R(0);  // eval.jl:65, the oracle's operation order
+      live[p] = ok && p < cnt;
+      if (!ok && p < cnt) badmask |= 1u << p;
     }
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      idx[p] = tile * tile_pts + (long long)p * blockDim.x + threadIdx.x;
-      live[p] = idx[p] < prm.npts;
-      const R x = xc[p];
-      const bool ok = (lb <= x) && (x <= ub);                                 // eval.jl:64 (closed box, NaN fails)
-      z[p] = ok ? rsub(sdiv.div(rmul(rsub(x, lb), R(2))), R(1)) : R(0);       // eval.jl:65, the oracle's operation order
-      if (live[p] && !ok) {
-        live[p] = false;
-        if (idx[p] < first_bad) first_bad = idx[p];
-      }
-    }
-    if (first_bad != 0x7fffffffffffffffLL && prm.bad) atomicMin(prm.bad, first_bad + prm.idx_base);
+    const bool all = cnt == P && badmask == 0;
+    if (badmask && prm.bad) atomicMin(prm.bad, i0 + (__ffs(badmask) - 1) + prm.idx_base);
+    fetch(tile + gridDim.x, xn);
 
     // T_lo(z) for lo < L = AMAX of every point, in registers; one more step of the same recurrence is w = T_L(z), the
     // argument of the outer factor: T_{L hi}(z) = T_hi(w).  (Doubling formulas T_{2m} = 2 T_m^2 - 1 would cut the
@@ -284,30 +353,46 @@ __global__ void __launch_bounds__(256, pb_min_ctas<R, AMAX, EC, JAC>()) eval_pb1
       }
     }
 
+    if (vec_out && all) {
+      // contiguous results of P consecutive points (mode 0, v_stride = J_stride = EC): vector stores
+      R ov[P * EC];
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-      if (!live[p]) continue;
+      for (int p = 0; p < P; ++p)
 #pragma unroll
-      for (int e = 0; e < EC; ++e) out_v[idx[p] * prm.v_stride + prm.e0 + e] = v[0][p][e] + v[1][p][e];
+        for (int e = 0; e < EC; ++e) ov[p * EC + e] = v[0][p][e] + v[1][p][e];
+      pb_vec_store<R, P * EC>(out_v + i0 * EC, ov);
       if constexpr (JAC) {
-        const R span = sdiv.span;
-        R Js[EC];
 #pragma unroll
-        for (int e = 0; e < EC; ++e)
-          Js[e] = rdiv(rmul(dv[0][p][e] + dv[1][p][e], R(2)), span);  // eval.jl:151
-        if (prm.mode == 0) {
+        for (int p = 0; p < P; ++p)
 #pragma unroll
-          for (int e = 0; e < EC; ++e) out_J[idx[p] * prm.J_stride + prm.e0 + e] = Js[e];
-        } else if (prm.mode == 1) {  // pullback: real(J' dy), chainrules.jl:7,14
-          const R* dy = reinterpret_cast<const R*>(prm.tan) + idx[p] * prm.Etot + prm.e0;
-          R acc = R(0);
+          for (int e = 0; e < EC; ++e) ov[p * EC + e] = div_any(rmul(dv[0][p][e] + dv[1][p][e], R(2)));  // eval.jl:151
+        pb_vec_store<R, P * EC>(out_J + i0 * EC, ov);
+      }
+    } else {
 #pragma unroll
-          for (int e = 0; e < EC; ++e) acc = rfma(Js[e], dy[e], acc);
-          out_J[idx[p]] = acc;
-        } else {  // pushforward: J dx, chainrules.jl:24
-          const R dx = reinterpret_cast<const R*>(prm.tan)[idx[p]];
+      for (int p = 0; p < P; ++p) {
+        if (!live[p]) continue;
+        const long long ip = i0 + p;
 #pragma unroll
-          for (int e = 0; e < EC; ++e) out_J[idx[p] * prm.Etot + prm.e0 + e] = rmul(Js[e], dx);
+        for (int e = 0; e < EC; ++e) out_v[ip * prm.v_stride + prm.e0 + e] = v[0][p][e] + v[1][p][e];
+        if constexpr (JAC) {
+          R Js[EC];
+#pragma unroll
+          for (int e = 0; e < EC; ++e) Js[e] = div_any(rmul(dv[0][p][e] + dv[1][p][e], R(2)));  // eval.jl:151
+          if (prm.mode == 0) {
+#pragma unroll
+            for (int e = 0; e < EC; ++e) out_J[ip * prm.J_stride + prm.e0 + e] = Js[e];
+          } else if (prm.mode == 1) {  // pullback: real(J' dy), chainrules.jl:7,14
+            const R* dy = reinterpret_cast<const R*>(prm.tan) + ip * prm.Etot + prm.e0;
+            R acc = R(0);
+#pragma unroll
+            for (int e = 0; e < EC; ++e) acc = rfma(Js[e], dy[e], acc);
+            out_J[ip] = acc;
+          } else {  // pushforward: J dx, chainrules.jl:24
+            const R dx = reinterpret_cast<const R*>(prm.tan)[ip];
+#pragma unroll
+            for (int e = 0; e < EC; ++e) out_J[ip * prm.Etot + prm.e0 + e] = rmul(Js[e], dx);
+          }
         }
       }
     }
