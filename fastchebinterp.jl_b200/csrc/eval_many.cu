@@ -13,6 +13,10 @@
 #include "host_util.h"
 #include "ptx_util.cuh"
 
+#ifndef FC_MANY_P1
+#define FC_MANY_P1 8  // points per lane of the scalar Float64 value kernel
+#endif
+
 namespace fastcheb {
 namespace {
 
@@ -26,11 +30,181 @@ struct ManyParams {
   long long* bad;      // first out-of-domain flat point index (atomicMin)
   long long howmany, M;
   int n, bounds_per_poly;
+  int vec;  // rows of pts / out_v / out_d start 16-byte aligned: vector loads and stores
 };
 
 template <typename R> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
+
+// K contiguous reals as 16- or 8-byte vectors (`ptr` aligned accordingly), else one by one
+template <typename R, int K>
+__device__ __forceinline__ void many_vec_load(const R* __restrict__ ptr, R (&x)[K]) {
+  constexpr int B = K * (int)sizeof(R);
+  if constexpr (B % 16 == 0) {
+    union { uint4 v[B / 16]; R r[K]; } u;
+#pragma unroll
+    for (int i = 0; i < B / 16; ++i) u.v[i] = reinterpret_cast<const uint4*>(ptr)[i];
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = u.r[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) x[k] = ptr[k];
+  }
+}
+template <typename R, int K>
+__device__ __forceinline__ void many_vec_store(R* __restrict__ ptr, const R (&x)[K]) {
+  constexpr int B = K * (int)sizeof(R);
+  if constexpr (B % 16 == 0) {
+    union { uint4 v[B / 16]; R r[K]; } u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) u.r[k] = x[k];
+#pragma unroll
+    for (int i = 0; i < B / 16; ++i) reinterpret_cast<uint4*>(ptr)[i] = u.v[i];
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ptr[k] = x[k];
+  }
+}
+
+// The M points of polynomial f, by one warp.  A lane owns P CONSECUTIVE points of every 32 P-point chunk: with 16-byte
+// aligned rows (prm.vec) coordinates arrive and results leave as 16-byte vectors, one index computation per lane and chunk.
+template <typename R, int E, int P, bool DER, bool FAST>
+__device__ __forceinline__ void poly_points(const ManyParams& prm, long long f, int lane, const R* cs, R lb, R ub,
+                                            const SpanDiv<R>& sdiv) {
+  const R* __restrict__ pts = reinterpret_cast<const R*>(prm.pts) + f * prm.M;
+  R* __restrict__ out_v = reinterpret_cast<R*>(prm.out_v) + f * prm.M * E;
+  R* __restrict__ out_d = DER ? reinterpret_cast<R*>(prm.out_d) + f * prm.M * E : nullptr;
+  const int n = prm.n;
+  const R span = sdiv.span, rcp = sdiv.y;
+  auto div_span = [&](R a) {
+    if constexpr (FAST) {
+      const R q = rmul(a, rcp);
+      return rfma(rfma(-span, q, a), rcp, q);
+    } else {
+      return rdiv(a, span);
+    }
+  };
+  // derivative scale (eval.jl:151), any numerator: the correction is the IEEE quotient while nothing can underflow or
+  // overflow on the way (numerator exponent within +-400, Float32 +-40)
+  [[maybe_unused]] auto div_any = [&](R a) {
+    if constexpr (FAST) {
+      bool safe;
+      if constexpr (sizeof(R) == 8) {
+        const unsigned e = ((unsigned)(__double_as_longlong((double)a) >> 52)) & 0x7ffu;
+        safe = e > 1023u - 400u && e < 1023u + 400u;
+      } else {
+        const unsigned e = (__float_as_uint((float)a) >> 23) & 0xffu;
+        safe = e > 127u - 40u && e < 127u + 40u;
+      }
+      if (safe) {
+        const R q = rmul(a, rcp);
+        return rfma(rfma(-span, q, a), rcp, q);
+      }
+    }
+    return rdiv(a, span);
+  };
+  const bool vec = prm.vec != 0;
+  auto count = [&](long long i0) {
+    const long long left = prm.M - i0;
+    return left >= P ? P : (left > 0 ? (int)left : 0);
+  };
+  auto fetch = [&](long long i0, R (&x)[P]) {
+    const int c = count(i0);
+    if (vec && c == P) {
+      many_vec_load<R, P>(pts + i0, x);
+    } else {
+#pragma unroll
+      for (int p = 0; p < P; ++p) x[p] = p < c ? pts[i0 + p] : lb;
+    }
+  };
+  // the points of the next chunk are loaded while the current one is evaluated (the recurrence is ~130 dependent FP64
+  // operations per chunk; an unprefetched load at its head stalls the warp for a global-memory latency every time)
+  R xn[P];
+  fetch((long long)lane * P, xn);
+  for (long long i0 = (long long)lane * P; i0 < prm.M; i0 += 32 * P) {
+    const int cnt = count(i0);
+    R z[P], z2[P];
+    bool live[P];
+    unsigned badmask = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const R x = xn[p];
+      const bool ok = (lb <= x) && (x <= ub);                               // eval.jl:64 (closed box, NaN fails)
+      z[p] = ok ? rsub(div_span(rmul(rsub(x, lb), R(2))), R(1)) : R(0);     // eval.jl:65 (the IEEE quotient)
+      z2[p] = rmul(R(2), z[p]);
+      live[p] = ok && p < cnt;
+      if (!ok && p < cnt) badmask |= 1u << p;
+    }
+    const bool all = cnt == P && badmask == 0;
+    if (badmask && prm.bad) atomicMin(prm.bad, f * prm.M + i0 + (__ffs(badmask) - 1));
+    fetch(i0 + 32 * P, xn);
+
+    R b1[P][E], b2[P][E], d1[DER ? P : 1][E], d2[DER ? P : 1][E];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        b1[p][e] = b2[p][e] = R(0);
+        if constexpr (DER) d1[p][e] = d2[p][e] = R(0);
+      }
+    auto step = [&](int e, R cj) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const R nb = rsub(rfma(z2[p], b1[p][e], cj), b2[p][e]);                    // eval.jl:28 / :96
+        if constexpr (DER) {
+          const R nd = rsub(rfma(z2[p], d1[p][e], rmul(R(2), b1[p][e])), d2[p][e]);  // eval.jl:97
+          d2[p][e] = d1[p][e];
+          d1[p][e] = nd;
+        }
+        b2[p][e] = b1[p][e];
+        b1[p][e] = nb;
+      }
+    };
+    if constexpr (E == 1) {
+      // scalar coefficients: two per shared-memory load (the warp's region is 16-byte aligned, pairs (c_{j-1}, c_j), j odd)
+      int j = n - 1;
+      if (j >= 1 && (j & 1) == 0) {
+        step(0, cs[j]);
+        --j;
+      }
+      for (; j >= 3; j -= 2) {
+        const auto c2 = *reinterpret_cast<const typename Vec2<R>::type*>(cs + j - 1);
+        step(0, c2.y);
+        step(0, c2.x);
+      }
+      if (j == 1) step(0, cs[1]);
+    } else {
+      for (int j = n - 1; j >= 1; --j) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) step(e, cs[j * E + e]);
+      }
+    }
+    R ov[P * E];
+    [[maybe_unused]] R od[DER ? P * E : 1];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        ov[p * E + e] = rsub(rfma(z[p], b1[p][e], cs[e]), b2[p][e]);  // eval.jl:31 / :101
+        if constexpr (DER) od[p * E + e] = div_any(rmul(rsub(rfma(z[p], d1[p][e], b1[p][e]), d2[p][e]), R(2)));  // eval.jl:101, :151
+      }
+    if (vec && all) {
+      many_vec_store<R, P * E>(out_v + i0 * E, ov);
+      if constexpr (DER) many_vec_store<R, P * E>(out_d + i0 * E, od);
+    } else {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        if (!live[p]) continue;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          out_v[(i0 + p) * E + e] = ov[p * E + e];
+          if constexpr (DER) out_d[(i0 + p) * E + e] = od[p * E + e];
+        }
+      }
+    }
+  }
+}
 
 template <typename R, int E, int P, bool DER>
 __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ ManyParams prm) {
@@ -39,9 +213,6 @@ __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ 
   const int n = prm.n, nE = n * E;
   R* cs = reinterpret_cast<R*>(fastcheb_smem) + (size_t)warp * ((nE + 1) & ~1);  // even stride: 16-byte aligned pairs
   const R* coefs = reinterpret_cast<const R*>(prm.coefs);
-  const R* pts = reinterpret_cast<const R*>(prm.pts);
-  R* out_v = reinterpret_cast<R*>(prm.out_v);
-  R* out_d = reinterpret_cast<R*>(prm.out_d);
   const long long gw = (long long)blockIdx.x * nwarps + warp, tw = (long long)gridDim.x * nwarps;
   for (long long f = gw; f < prm.howmany; f += tw) {
     __syncwarp();
@@ -50,91 +221,20 @@ __global__ void __launch_bounds__(256) eval_many_kernel(const __grid_constant__ 
     const R lb = (R)prm.lb[prm.bounds_per_poly ? f : 0], ub = (R)prm.ub[prm.bounds_per_poly ? f : 0];
     SpanDiv<R> sdiv;
     sdiv.init(lb, ub);
-    const R span = sdiv.span;
-    // the points of the next chunk are loaded while the current one is evaluated (the recurrence is ~130 dependent FP64
-    // operations per chunk; an unprefetched load at its head stalls the warp for a global-memory latency every time)
-    R xn[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      const long long ip = lane + 32 * p;
-      xn[p] = ip < prm.M ? pts[f * prm.M + ip] : lb;
-    }
-    for (long long p0 = lane; p0 < prm.M; p0 += 32 * P) {
-      R z[P], z2[P];
-      bool live[P];
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const long long ip = p0 + 32 * p;
-        live[p] = ip < prm.M;
-        const R x = xn[p];
-        const long long in = ip + 32 * P;
-        xn[p] = in < prm.M ? pts[f * prm.M + in] : lb;
-        const bool ok = (lb <= x) && (x <= ub);                       // eval.jl:64 (closed box, NaN fails)
-        z[p] = ok ? rsub(sdiv.div(rmul(rsub(x, lb), R(2))), R(1)) : R(0);  // eval.jl:65 (SpanDiv: the IEEE quotient)
-        z2[p] = rmul(R(2), z[p]);
-        if (live[p] && !ok) {
-          live[p] = false;
-          if (prm.bad) atomicMin(prm.bad, f * prm.M + ip);
-        }
-      }
-      R b1[P][E], b2[P][E], d1[DER ? P : 1][E], d2[DER ? P : 1][E];
-#pragma unroll
-      for (int p = 0; p < P; ++p)
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          b1[p][e] = b2[p][e] = R(0);
-          if constexpr (DER) d1[p][e] = d2[p][e] = R(0);
-        }
-      auto step = [&](int e, R cj) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const R nb = rsub(rfma(z2[p], b1[p][e], cj), b2[p][e]);                    // eval.jl:28 / :96
-          if constexpr (DER) {
-            const R nd = rsub(rfma(z2[p], d1[p][e], rmul(R(2), b1[p][e])), d2[p][e]);  // eval.jl:97
-            d2[p][e] = d1[p][e];
-            d1[p][e] = nd;
-          }
-          b2[p][e] = b1[p][e];
-          b1[p][e] = nb;
-        }
-      };
-      if constexpr (E == 1) {
-        // scalar coefficients: two per shared-memory load (the warp's region is 16-byte aligned, pairs (c_{j-1}, c_j), j odd)
-        int j = n - 1;
-        if (j >= 1 && (j & 1) == 0) {
-          step(0, cs[j]);
-          --j;
-        }
-        for (; j >= 3; j -= 2) {
-          const auto c2 = *reinterpret_cast<const typename Vec2<R>::type*>(cs + j - 1);
-          step(0, c2.y);
-          step(0, c2.x);
-        }
-        if (j == 1) step(0, cs[1]);
-      } else {
-        for (int j = n - 1; j >= 1; --j) {
-#pragma unroll
-          for (int e = 0; e < E; ++e) step(e, cs[j * E + e]);
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        if (!live[p]) continue;
-        const long long o = (f * prm.M + p0 + 32 * p) * E;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          out_v[o + e] = rsub(rfma(z[p], b1[p][e], cs[e]), b2[p][e]);  // eval.jl:31 / :101
-          if constexpr (DER)
-            out_d[o + e] = rdiv(rmul(rsub(rfma(z[p], d1[p][e], b1[p][e]), d2[p][e]), R(2)), span);  // eval.jl:101, :151
-        }
-      }
-    }
+    // The applicability test of the reciprocal division (SpanDiv) is made once per polynomial, not once per point: the
+    // point loop exists in two copies.
+    if (sdiv.fast)
+      poly_points<R, E, P, DER, true>(prm, f, lane, cs, lb, ub, sdiv);
+    else
+      poly_points<R, E, P, DER, false>(prm, f, lane, cs, lb, ub, sdiv);
   }
 }
 
 template <typename R, int E, bool DER>
 cudaError_t launch(const ManyParams& prm, int sms, cudaStream_t st) {
-  constexpr int P = sizeof(R) == 8 ? (E >= 3 ? 2 : 4) : (E >= 3 ? 2 : 4);
+  // (8 points per lane measured faster only for the scalar Float64 value kernel: 8.68e10 -> 9.31e10 points/s; the derivative
+  // kernel then needs 172 registers and slows down, Float32 does not move)
+  constexpr int P = (E == 1 && !DER && sizeof(R) == 8) ? FC_MANY_P1 : (E >= 3 ? 2 : 4);
   const int warps = 8;
   const size_t smem = (size_t)warps * (((size_t)prm.n * E + 1) & ~(size_t)1) * sizeof(R);
   auto kern = eval_many_kernel<R, E, P, DER>;
@@ -255,6 +355,10 @@ extern "C" int fastcheb_eval_many(int64_t howmany, int64_t n, int dtype, int is_
     prm.out_d = out_d;
     prm.lb = lb;  // device pointers in device mode
     prm.ub = ub;
+  }
+  {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    prm.vec = ((size_t)M * rs) % 16 == 0 && al16(prm.pts) && al16(prm.out_v) && (!prm.out_d || al16(prm.out_d));
   }
   cudaError_t e;
   if (dtype == FASTCHEB_F64)
