@@ -18,7 +18,7 @@ cudaError_t launch_cap(const Lo1dParams& prm, const void* h_c, int sms, cudaStre
   int bps = 1;
   cudaError_t e = cached_occupancy(&bps, reinterpret_cast<const void*>(kern), threads, 0);
   if (e != cudaSuccess) return e;
-  const long long tile = (long long)threads * lo_pts<R>(EC);
+  const long long tile = (long long)threads * lo_pts<R>(EC, NCAP, JAC);
   const long long ntiles = (prm.npts + tile - 1) / tile;
   const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)sms * std::max(1, bps)));
   kern<<<grid, threads, 0, st>>>(args);

@@ -18,6 +18,10 @@
 #include <cstdint>
 #include "ptx_util.cuh"
 
+#ifndef FC_LO_P8
+#define FC_LO_P8 1
+#endif
+
 namespace fastcheb {
 
 constexpr int kLoMaxN = 17;      // coefficients c_0 .. c_16: the memory-bound range (table capacity of the first instantiation)
@@ -45,9 +49,12 @@ struct Lo1dArgs {
   R c[NCAP * EC];  // [j][e], zero above j = n - 1
 };
 
-// points per thread: 32 bytes of coordinates for scalar polynomials, 16 for vector-valued ones
+// points per thread: 32 bytes of coordinates for scalar polynomials, 16 for vector-valued ones; the FP64-bound scalar
+// Float64 value kernels of the longer series (table capacity > 17) take 64 bytes = 8 independent recurrences
 template <typename R>
-__host__ __device__ constexpr int lo_pts(int ec) { return (ec == 1 ? 32 : 16) / (int)sizeof(R); }
+__host__ __device__ constexpr int lo_pts(int ec, int ncap = 17, bool jac = false) {
+  return (ec == 1 ? ((FC_LO_P8 && ncap > 17 && !jac && sizeof(R) == 8) ? 64 : 32) : 16) / (int)sizeof(R);
+}
 
 template <typename R> struct LoVec;
 template <> struct LoVec<double> {
@@ -115,7 +122,7 @@ __device__ __forceinline__ void lo_store(R* __restrict__ ptr, bool keep, const b
 
 template <typename R, int EC, bool JAC, int NCAP>
 __global__ void __launch_bounds__(256) eval_lo1d_kernel(const __grid_constant__ Lo1dArgs<R, EC, NCAP> args) {
-  constexpr int P = lo_pts<R>(EC);
+  constexpr int P = lo_pts<R>(EC, NCAP, JAC);
   const Lo1dParams& prm = args.p;
   const R* __restrict__ pts = reinterpret_cast<const R*>(prm.pts);
   R* __restrict__ out_v = reinterpret_cast<R*>(prm.out_v);

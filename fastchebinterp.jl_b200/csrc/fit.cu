@@ -377,19 +377,20 @@ int fastcheb_fit(int ndim, const int64_t* dims, int dtype, int is_complex, int n
     void* dbuf[2] = {nullptr, nullptr};
     const size_t cb = (size_t)chunk * fit_bytes, cb_al = (cb + 255) / 256 * 256;
     const size_t mxb = maxabs ? (size_t)chunk * sizeof(double) : 0;
+    StreamPair sp;  // the two chunk streams come from the per-device pool (no stream creation per call)
+    sp.dev = -1;
     auto cleanup = [&]() {
-      for (int i = 0; i < 2; ++i) {
-        if (ss[i]) cudaStreamDestroy(ss[i]);
+      streams_release(sp);
+      sp.dev = -1;
+      for (int i = 0; i < 2; ++i)
         if (dbuf[i]) ws_release(device, dbuf[i]);
-      }
     };
+    if (nbuf > 1) {
+      FC_TRY(streams_acquire(device, &sp));
+      ss[0] = sp.s[0];
+      ss[1] = sp.s[1];
+    }
     for (int i = 0; i < nbuf; ++i) {
-      if (nbuf == 1) {
-        ss[i] = nullptr;
-      } else if (cudaStreamCreateWithFlags(&ss[i], cudaStreamNonBlocking) != cudaSuccess) {
-        cleanup();
-        return fail(FASTCHEB_ECUDA, "cudaStreamCreate failed");
-      }
       dbuf[i] = ws_acquire(device, 2 * cb_al + mxb);
       if (!dbuf[i]) {
         cleanup();

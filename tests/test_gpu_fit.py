@@ -197,3 +197,22 @@ def test_batched_fit_linearity_and_constants(fc):
     want = np.zeros((M, n))
     want[np.arange(M), k] = 1.0
     assert np.abs(ck - want).max() <= 1e-13
+
+
+def test_large_host_batch_runs_in_chunks_on_pooled_streams(fc, orc):
+    """Host batches above 64 MB are cut into chunks on two internal streams (fit.cu; the streams come from the per-device
+    pool, so a second call reuses them): every fit equals the same fit made alone, and the per-fit maxima are right."""
+    rng = np.random.default_rng(99)
+    howmany, n = 150_000, 65                                  # 78 MB of Float64
+    vals = rng.uniform(-1, 1, (howmany, n))
+    for _ in range(2):
+        c, mx = fc.chebcoefs(vals, ndim=1, howmany=howmany, return_maxabs=True)
+        assert c.shape == vals.shape
+        for i in (0, 1, 37_499, 37_500, 74_999, 75_000, 112_500, 149_999):
+            ref = orc.chebcoefs(vals[i], 1)
+            assert np.abs(c[i] - ref).max() <= 1e-13 * np.abs(ref).max()
+            assert np.isclose(mx[i], np.abs(c[i]).max(), rtol=1e-14, atol=0)
+    bad = vals.copy()
+    bad[120_000, 7] = np.inf
+    with pytest.raises(fc.DomainError):
+        fc.chebcoefs(bad, ndim=1, howmany=howmany)
