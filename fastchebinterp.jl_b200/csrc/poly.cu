@@ -368,7 +368,8 @@ int fastcheb_set_algo(fastcheb_poly* p, int algo) {
     return fail(FASTCHEB_EUNSUPPORTED, "the DMMA path needs ndim >= 2, n1 >= 5 and at least 8 coefficient columns");
   if (algo == FASTCHEB_ALGO_PRODUCT) {
     if (!pb1d_shape_ok(p))
-      return fail(FASTCHEB_EUNSUPPORTED, "the product-basis path covers 1-D polynomials with %d <= n <= %d and at most 4 real components",
+      return fail(FASTCHEB_EUNSUPPORTED, "the product-basis path covers 1-D polynomials with %d <= n <= %d, at most 4 real components and a span ub - lb that "
+                  "passes the reciprocal-division test (mantissa not all ones, exponent within +-500)",
                   kPbMinN, kPbMaxN);
     FC_TRY(pb1d_plan(p, true));
   } else if (algo != FASTCHEB_ALGO_AUTO && algo != FASTCHEB_ALGO_CLENSHAW && algo != FASTCHEB_ALGO_DMMA &&

@@ -153,3 +153,20 @@ def test_product_gradient_second_table_limit(fc, orc):
             p.set_algo(fc.ALGO_AUTO)
             v, J = fc.chebjacobian(p, x)
             assert np.array_equal(v, v0) and np.array_equal(J, J0)
+
+
+def test_product_path_refuses_spans_that_fail_the_division_test(fc, orc):
+    """The product-basis kernel divides by the span with reciprocal + exact-remainder correction unconditionally; a span whose
+    mantissa is all ones fails that test: forcing the path is refused and AUTO stays bit-identical to the oracle."""
+    n, lb, ub = 101, 0.0, float(np.nextafter(2.0, 0.0))
+    xg = orc.chebpoints(n - 1, lb, ub)
+    c = orc.chebcoefs(np.sin(3 * xg) * np.exp(-xg), 1)
+    lbv, ubv = np.array([lb]), np.array([ub])
+    p = fc.ChebPoly(c, lbv, ubv)
+    with pytest.raises(fc.CudaError):
+        p.set_algo(fc.ALGO_PRODUCT)
+    rng = np.random.default_rng(2)
+    x = _points(rng, lb, ub, 20_000, np.float64)
+    v0, J0 = orc.OracleChebPoly(c, lbv, ubv).jacobian(x)
+    v, J = fc.chebjacobian(p, x)
+    assert np.array_equal(v, v0) and np.array_equal(J, J0)
