@@ -7,10 +7,11 @@
 namespace fastcheb {
 namespace {
 
-template <typename R, int N, int EC, bool JAC>
-cudaError_t launch(const LoNdParams& prm, const void* h_c, size_t c_bytes, int sms, cudaStream_t st) {
-  auto kern = eval_lond_kernel<R, N, EC, JAC>;
-  LoNdArgs<R> args;
+template <typename R, int N, int EC, bool JAC, int CAP>
+cudaError_t launch_cap(const LoNdParams& prm, const void* h_c, size_t c_bytes, int sms, cudaStream_t st) {
+  auto kern = eval_lond_kernel<R, N, EC, JAC, CAP>;
+  LoNdArgs<R, CAP> args;
+  static_assert(sizeof(args) <= 32764, "kernel parameter space");
   args.p = prm;
   memcpy(args.c, h_c, std::min(c_bytes, sizeof(args.c)));
   const int threads = 256;
@@ -23,6 +24,16 @@ cudaError_t launch(const LoNdParams& prm, const void* h_c, size_t c_bytes, int s
   kern<<<grid, threads, 0, st>>>(args);
   note_launch();
   return cudaGetLastError();
+}
+
+template <typename R, int N, int EC, bool JAC>
+cudaError_t launch(const LoNdParams& prm, const void* h_c, size_t c_bytes, int sms, cudaStream_t st) {
+  if constexpr (JAC && N * EC > 6) {
+    return cudaErrorInvalidValue;  // not instantiated: the Jacobian nest would spill (lond_ok keeps these on the generic kernel)
+  } else {
+    if (lond_cap((long long)(c_bytes / sizeof(R))) == 512) return launch_cap<R, N, EC, JAC, 512>(prm, h_c, c_bytes, sms, st);
+    return launch_cap<R, N, EC, JAC, 2048>(prm, h_c, c_bytes, sms, st);
+  }
 }
 
 template <typename R, int N, bool JAC>

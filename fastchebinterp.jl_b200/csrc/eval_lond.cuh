@@ -13,7 +13,8 @@
 namespace fastcheb {
 
 constexpr int kLoNdMaxN = 4;
-constexpr int kLoNdCap = 512;  // reals in the kernel parameters: prod(n_d) * E with n_1 padded
+constexpr int kLoNdCap = 2048;  // reals in the kernel parameters: prod(n_d) * E with n_1 padded (two table capacities: 512, 2048)
+__host__ __device__ constexpr int lond_cap(long long tot) { return tot <= 512 ? 512 : 2048; }
 
 struct LoNdParams {
   const void* pts;  // npts x N reals (AoS), 16-byte aligned
@@ -27,17 +28,17 @@ struct LoNdParams {
   double lb[kLoNdMaxN], ub[kLoNdMaxN];
 };
 
-template <typename R>
+template <typename R, int CAP>
 struct LoNdArgs {
   LoNdParams p;
-  R c[kLoNdCap];  // [i_N]...[i_2][i_1 < n1p][e]
+  R c[CAP];  // [i_N]...[i_2][i_1 < n1p][e]
 };
 
-template <typename R, int N, int EC, int P, bool JAC>
+template <typename R, int N, int EC, int P, bool JAC, int CAP>
 struct LoNest {
-  const LoNdArgs<R>& a;
+  const LoNdArgs<R, CAP>& a;
   R z[N][P], z2[N][P];
-  __device__ __forceinline__ LoNest(const LoNdArgs<R>& args) : a(args) {}
+  __device__ __forceinline__ LoNest(const LoNdArgs<R, CAP>& args) : a(args) {}
 
   template <int D>
   __device__ __forceinline__ void level(int off, R (&out)[P][EC]) {
@@ -180,8 +181,8 @@ __host__ __device__ constexpr int lond_pts(int n, int ec, bool jac) {
   return (16 / (int)sizeof(R)) * ((jac ? n * ec <= 2 : n * ec <= 3) ? 2 : 1);
 }
 
-template <typename R, int N, int EC, bool JAC>
-__global__ void __launch_bounds__(256) eval_lond_kernel(const __grid_constant__ LoNdArgs<R> args) {
+template <typename R, int N, int EC, bool JAC, int CAP>
+__global__ void __launch_bounds__(256) eval_lond_kernel(const __grid_constant__ LoNdArgs<R, CAP> args) {
   constexpr int P = lond_pts<R>(N, EC, JAC);
   const LoNdParams& prm = args.p;
   const R* __restrict__ pts = reinterpret_cast<const R*>(prm.pts);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256) eval_lond_kernel(const __grid_constant__ 
     const int c0 = count(i0);
     lo_load<R, P * N>(pts + (c0 ? i0 * N : 0), c0 * N, R(0), xn);
   }
-  LoNest<R, N, EC, P, JAC> nest(args);
+  LoNest<R, N, EC, P, JAC, CAP> nest(args);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long i0 = tile * tile_pts + toff;
     const int cnt = count(i0);

@@ -219,6 +219,13 @@ int eval_device(const fastcheb_poly* p, const void* pts, int64_t npts, void* out
     return pb1d_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
   if (lo1d_ok(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, mode))  // n < 40, or not taken by the product basis
     return lo1d_eval(p, pts, npts, out_v, out_J, jac, bad_dev, idx_base, st);
+  // Scalar 2-D polynomials with n1 <= 17: the low-order nest measured equal to the tensor-core path on 17 x 17 and 1.2-1.26x
+  // faster on 17 x 33 and 13 x 60 (tools/probe_crossover.py; 33 x 33, 12^3, 6^4 and vector-valued shapes stay on the tensor
+  // cores).  FASTCHEB_LOND_FIRST: experiments, the nest wherever it applies.
+  static const bool lond_first = getenv("FASTCHEB_LOND_FIRST") != nullptr;
+  const bool small2d = p->ndim == 2 && p->E == 1 && p->dims[0] <= 17;
+  if ((lond_first || small2d) && lond_ok(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, mode))
+    return lond_eval(p, pts, npts, out_v, out_J, jac, bad_dev, idx_base, st);
   if (use_dmma(p, jac))
     return dmma_eval(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, bad_dev, idx_base, st, mode, tan);
   if (lond_ok(p, pts, npts, out_v, v_stride, out_J, J_stride, jac, mode))

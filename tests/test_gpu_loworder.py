@@ -97,7 +97,8 @@ def test_low_order_division_corner_cases(fc, orc, dt):
         assert np.array_equal(v, v0, equal_nan=True) and np.array_equal(J, J0, equal_nan=True), (lb0, ub0, scale)
 
 
-ND_SHAPES = [(5, 5), (2, 7), (9, 1), (1, 6), (9, 9), (4, 4, 4), (3, 1, 5), (2, 2, 2), (5, 5, 5), (3, 3, 3, 3), (2, 4, 3, 2), (13, 3)]
+ND_SHAPES = [(5, 5), (2, 7), (9, 1), (1, 6), (9, 9), (4, 4, 4), (3, 1, 5), (2, 2, 2), (5, 5, 5), (3, 3, 3, 3), (2, 4, 3, 2), (13, 3),
+             (9, 9, 9), (9, 30), (5, 5, 5, 5), (4, 60), (7, 7, 7, 2)]   # the last four: second table capacity (up to 2048 padded coefficients)
 
 
 @pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
@@ -125,6 +126,8 @@ def test_low_order_nd_bit_identical(fc, orc, dt, K, cplx):
         o = orc.OracleChebPoly(c, lb, ub)
         v0, J0 = o.jacobian(x)
         p = fc.ChebPoly(c, lb, ub)
+        if p.get_algo(False, dt) == fc.ALGO_DMMA:   # AUTO sends this shape to the tensor cores (tolerance parity, not bits)
+            continue
         v, J = fc.chebjacobian(p, x)
         assert np.array_equal(p(x), v0), (shape, "value")
         assert np.array_equal(v, v0) and np.array_equal(J, J0), (shape, "jacobian")

@@ -32,6 +32,12 @@ SHAPES = [
     ("3d_order3_K2_f32_jac", (4, 4, 4), 2, False, f32, 1 << 24, True),
     ("4d_order2_f64_grad", (3, 3, 3, 3), None, False, f64, 1 << 24, True),
     ("4d_order3_K2_f64_val", (4, 4, 4, 4), 2, False, f64, 1 << 23, False),
+    # nests between 512 and 2048 padded coefficients (second table capacity)
+    ("3d_order8_f64_val", (9, 9, 9), None, False, f64, 1 << 23, False),
+    ("3d_order8_f64_grad", (9, 9, 9), None, False, f64, 1 << 22, True),
+    ("2d_17x33_f64_val", (17, 33), None, False, f64, 1 << 23, False),
+    ("2d_9x40_K3_f64_val", (9, 40), 3, False, f64, 1 << 22, False),
+    ("4d_order4_f32_val", (5, 5, 5, 5), None, False, f32, 1 << 22, False),
     # longer dense-random 1-D series (the product basis rejects them): FP64-bound, the same kernel as the Clenshaw kernel
     ("1d_order24_f64_val", (25,), None, False, f64, 1 << 25, False),
     ("1d_order64_dense_f64_val", (65,), None, False, f64, 1 << 25, False),
