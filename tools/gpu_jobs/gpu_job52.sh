@@ -10,3 +10,5 @@ FASTCHEB_LOND=0 FASTCHEB_LO1D=0 python tools/probe_loworder.py > gpurun_out/r02_
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:eval_lo1d_kernel -s 1 -c 1 -f -o gpurun_out/r02_lo1d_order8 python tools/probe_loworder.py once 2 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:eval_lond_kernel -s 1 -c 1 -f -o gpurun_out/r02_lond_5x5 python tools/probe_loworder.py once 4 > /dev/null 2>&1
 python tools/latency_probe.py > gpurun_out/r02_latency.txt 2>&1; tail -3 gpurun_out/r02_latency.txt
+timeout 600 python tools/big_index_loworder.py 2>&1 | tail -4 | tee gpurun_out/r02_big_index_loworder.txt
+timeout 300 python tools/leak_check.py 2>&1 | tail -2
