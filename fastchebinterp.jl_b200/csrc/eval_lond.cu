@@ -20,7 +20,13 @@ cudaError_t launch_cap(const LoNdParams& prm, const void* h_c, size_t c_bytes, i
   if (e != cudaSuccess) return e;
   const long long tile = (long long)threads * lond_pts<R>(N, EC, JAC);
   const long long ntiles = (prm.npts + tile - 1) / tile;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)sms * std::max(1, bps)));
+  // 4 CTAs per resident slot: with exactly one CTA per slot the warps that finish first leave their slots empty (ncu: 18 of 24
+  // warps active on average); the hardware scheduler balances the tail — measured +1 to +10 % (FASTCHEB_LO_OVERSUB: experiments)
+  static const int over = [] {
+    const char* t = getenv("FASTCHEB_LO_OVERSUB");
+    return t ? std::max(1, std::min(16, atoi(t))) : 4;
+  }();
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)sms * std::max(1, bps) * over));
   kern<<<grid, threads, 0, st>>>(args);
   note_launch();
   return cudaGetLastError();

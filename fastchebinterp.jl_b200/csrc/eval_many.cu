@@ -244,7 +244,12 @@ cudaError_t launch(const ManyParams& prm, int sms, cudaStream_t st) {
   e = cached_occupancy(&bps, reinterpret_cast<const void*>(kern), warps * 32, smem);
   if (e != cudaSuccess) return e;
   const long long want = (prm.howmany + warps - 1) / warps;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * std::max(1, bps)));
+  // 4 CTAs per resident slot (the hardware scheduler balances the tail: +3 to +5 %; FASTCHEB_MANY_OVERSUB: experiments)
+  static const int over = [] {
+    const char* t = getenv("FASTCHEB_MANY_OVERSUB");
+    return t ? std::max(1, std::min(16, atoi(t))) : 4;
+  }();
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * std::max(1, bps) * over));
   kern<<<grid, warps * 32, smem, st>>>(prm);
   note_launch();
   return cudaGetLastError();

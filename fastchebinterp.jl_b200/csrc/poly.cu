@@ -165,7 +165,11 @@ int eval_clenshaw(const fastcheb_poly* p, const void* pts, int64_t npts, void* o
     if (bps < 1) return fail(FASTCHEB_ECUDA, "Clenshaw kernel does not fit an SM (smem %zu B)", g.smem);
     const long long tile = (long long)threads * P;
     const long long ntiles = (npts + tile - 1) / tile;
-    const int grid = (int)std::min<long long>(ntiles, (long long)p->di->sms * bps);
+    static const int over = [] {  // CTAs per resident slot (FASTCHEB_CL_OVERSUB: experiments)
+      const char* t = getenv("FASTCHEB_CL_OVERSUB");
+      return t ? std::max(1, std::min(16, atoi(t))) : 1;
+    }();
+    const int grid = (int)std::min<long long>(ntiles, (long long)p->di->sms * bps * over);
     e = fn(kOpLaunch, p->ndim, g.ec, prm, threads, grid, g.smem, st, nullptr);
     if (e != cudaSuccess) return fail(FASTCHEB_ECUDA, "Clenshaw kernel launch failed: %s", cudaGetErrorString(e));
   }
